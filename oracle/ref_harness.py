@@ -1,0 +1,220 @@
+"""Builds the reference's own (unmodified) model / controller / env objects without MuJoCo.
+
+TEST INFRASTRUCTURE ONLY (see ref_shims.py).  Only usable where ``/root/reference`` is mounted, i.e. in
+the build container: used by ``tests/golden/make_golden.py`` (fixture generation) and
+``oracle/validate_against_reference.py``.  Never imported by product code, never needed on the GPU box.
+
+Environment objects are created with ``object.__new__`` and given exactly the attributes the hot path
+reads (fpp_construction_env.py:32-125, playground_env_wgoals.py:24-72); every *method* that runs
+(``cost_fn``, ``obs_preproc``, ``obs_postproc``, the ``*_tensor`` helpers) is the reference's code.
+"""
+import os
+import sys
+import tempfile
+import types
+import warnings
+
+import numpy as np
+import torch
+
+REFERENCE_ROOT = os.environ.get("CEEUS_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "mbrl"))
+
+
+_ready = False
+
+
+def _prepare():
+    global _ready
+    if _ready:
+        return
+    if not reference_available():
+        raise RuntimeError("reference tree not mounted at %s" % REFERENCE_ROOT)
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import ref_shims  # noqa: F401
+
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    from mbrl import allogger
+
+    logdir = tempfile.mkdtemp(prefix="ceeus_allogger_")
+    allogger.basic_configure(logdir=logdir, default_outputs=["tensorboard"], manual_flush=True)
+    warnings.filterwarnings("ignore", message=".*resized.*")
+    warnings.filterwarnings("ignore", category=UserWarning)
+    _ready = True
+
+
+def make_construction_env(num_blocks, case="Singletower", sparse=False, shaped_reward=True, goal=None):
+    _prepare()
+    from gym import spaces
+    from mbrl.environments.fpp_construction_env import FetchPickAndPlaceConstruction
+
+    N = num_blocks
+    env = object.__new__(FetchPickAndPlaceConstruction)
+    env.name = "FetchPickAndPlaceConstruction"
+    env.num_blocks = N
+    env.case = case
+    env.shaped_reward = shaped_reward
+    env.sparse = sparse
+    env.agent_dim, env.object_dyn_dim, env.object_stat_dim, env.nObj = 10, 12, 0, N
+    orig = 10 + 12 * N
+    gsz = 3 * N + 3
+    env.goal_idx = np.arange(orig, orig + gsz)
+    if case == "Flip":
+        ach = [np.arange(10 + i * 12 + 3, 10 + i * 12 + 6) for i in range(N)]
+    else:
+        ach = [np.arange(10 + i * 12, 10 + i * 12 + 3) for i in range(N)]
+    ach.append([0, 1, 2])
+    env.achieved_goal_idx = np.asarray(ach).flatten()
+    env.observation_space = spaces.Box(-np.inf, np.inf, shape=(orig + gsz,), dtype="float32")
+    env.action_space = spaces.Box(-1.0, 1.0, shape=(4,), dtype="float32")
+    env.observation_space_size_preproc = orig
+    env.goal_space_size = gsz
+    env.height_offset = 0.42
+    if "tower" in case or case == "Pyramid":
+        env.threshold = 0.02
+    elif case == "PickAndPlace":
+        env.threshold = 0.025
+    elif case == "Slide":
+        env.threshold = 0.1
+    elif case == "Flip":
+        env.threshold = 0.087 * 2
+    else:
+        env.threshold = 0.05
+    env.goal_idx_tensor = torch.tensor(env.goal_idx, dtype=torch.int32)
+    env.achieved_goal_idx_tensor = torch.tensor(env.achieved_goal_idx, dtype=torch.int32)
+    if case == "Flip":
+        env.coord_weights = torch.tensor([[1.0, 0.0, 0.0]], dtype=torch.float32)
+        env.buffer_threshold = torch.tensor(1e-4, dtype=torch.float32)
+        env.cost_thres = env.coord_weights * 0.087
+    elif case == "Slide":
+        env.coord_weights = torch.tensor([1.0, 1.0, 1.0], dtype=torch.float32)
+        env.buffer_threshold = torch.tensor([0.1, 0.1, env.height_offset], dtype=torch.float32)
+        env.cost_thres = env.coord_weights * 0.1
+        env.cost_thres[-1] = env.height_offset
+    else:
+        env.buffer_threshold = torch.tensor(0.025, dtype=torch.float32)
+    env.robot_base_xy = np.array([0.69189994, 0.74409998])
+    env.manipulability_r = 0.8531
+    env.robot_base_xy_tensor = torch.tensor(env.robot_base_xy, dtype=torch.float32)
+    env.gripper_init = np.array([1.344, 0.749, 0.5319])
+    env.gripper_init_tensor = torch.tensor(env.gripper_init, dtype=torch.float32)
+    env.goal = np.zeros(gsz, dtype=np.float32) if goal is None else np.asarray(goal, dtype=np.float32)
+    return env
+
+
+def make_playground_env(num_objs, goal=None):
+    _prepare()
+    from gym import spaces
+    from mbrl.environments.playground_env_wgoals import PlaygroundwGoals
+
+    N = num_objs
+    env = object.__new__(PlaygroundwGoals)
+    env.name = "PlaygroundwGoals"
+    env.num_objs = env.nObj = N
+    env.dofs = 2
+    env.agent_dim, env.object_dyn_dim, env.object_stat_dim = 4, 6, 3
+    env.model = types.SimpleNamespace(nq=2 + 3 * N, nv=2 + 3 * N)
+    orig = 4 + 9 * N
+    gsz = 2 * N
+    env.goal_idx = np.arange(orig, orig + gsz)
+    env.achieved_goal_idx = np.asarray([np.arange(4 + 6 * i, 4 + 6 * i + 2) for i in range(N)]).flatten()
+    env.observation_space = spaces.Box(-np.inf, np.inf, shape=(orig + gsz,), dtype="float32")
+    env.action_space = spaces.Box(-1.0, 1.0, shape=(2,), dtype="float32")
+    env.observation_space_size_preproc = orig
+    env.goal_space_size = gsz
+    env.goal_idx_tensor = torch.tensor(env.goal_idx, dtype=torch.int32)
+    env.achieved_goal_idx_tensor = torch.tensor(env.achieved_goal_idx, dtype=torch.int32)
+    env.goal = np.zeros(gsz, dtype=np.float32) if goal is None else np.asarray(goal, dtype=np.float32)
+    return env
+
+
+_TRAIN_PARAMS = dict(batch_size=125, epochs=25, iterations=0, learning_rate=1e-5, weight_decay=1e-3,
+                     optimizer="Adam", bootstrapped=False, train_epochs_only_with_latest_data=False)
+
+
+def make_gnn_model(env, hidden_dim=128, num_layers=2, n=5, running_stats=False, seed=0):
+    _prepare()
+    from mbrl.models.gnn_ensemble import GNNForwardEnsembleModel
+
+    torch.manual_seed(seed)
+    return GNNForwardEnsembleModel(
+        env=env,
+        model_params=dict(n=n, hidden_dim=hidden_dim, num_layers=num_layers, layer_norm=True,
+                          num_message_passing=1, act_fn="relu", output_act_fn="none"),
+        train_params=dict(_TRAIN_PARAMS),
+        use_input_normalization=True,
+        use_output_normalization=True,
+        target_is_delta=True,
+        normalize_w_running_stats=running_stats,
+    )
+
+
+def make_mlp_model(env, hidden_dim=256, num_layers=3, n=5, running_stats=False, seed=0):
+    _prepare()
+    from mbrl.models.mlp_ensemble import ParallelNNDeterministicEnsemble
+
+    torch.manual_seed(seed)
+    return ParallelNNDeterministicEnsemble(
+        env=env,
+        model_params=dict(n=n, hidden_dim=hidden_dim, num_layers=num_layers, act_fn="silu", output_act_fn="none",
+                          layer_norm=False),
+        train_params=dict(_TRAIN_PARAMS),
+        use_input_normalization=True,
+        use_output_normalization=True,
+        target_is_delta=True,
+        normalize_w_running_stats=running_stats,
+    )
+
+
+def make_controller(env, model, *, curiosity, horizon, num_traj, cost_along_trajectory="sum", sampler=None,
+                    extrinsic_reward=False, extrinsic_reward_scale=1.0):
+    _prepare()
+    from mbrl.controllers.mpc_torch import TorchMpcICem
+    from mbrl.controllers.mpc_torch_curiosity import TorchCuriosityMpcICem
+
+    sp = dict(opt_iterations=3, elites_size=10, alpha=0.1, init_std=0.8, relative_init=True,
+              execute_best_elite=True, keep_previous_elites=True, shift_elites_over_time=True,
+              finetune_first_action=False, fraction_elites_reused=0.3, use_mean_actions=True,
+              colored_noise=True, noise_beta=3.5, use_ensemble_cost_std=False)
+    if sampler:
+        sp.update(sampler)
+    kw = dict(env=env, forward_model=model, horizon=horizon, num_simulated_trajectories=num_traj,
+              factor_decrease_num=1, use_env_reward=False, cost_along_trajectory=cost_along_trajectory,
+              action_sampler_params=sp, verbose=False, do_visualize_plan=False, use_async_action=False,
+              logging=False)
+    if curiosity:
+        return TorchCuriosityMpcICem(extrinsic_reward=extrinsic_reward,
+                                     extrinsic_reward_scale=extrinsic_reward_scale, **kw)
+    return TorchMpcICem(**kw)
+
+
+class NoiseTap:
+    """Replaces colored_noise.torch_powerlaw_psd_gaussian by a replay of pre-drawn noise tensors and records
+    the call order -- the RNG boundary of SURVEY.md section 8c."""
+
+    def __init__(self, provider):
+        self.provider = provider
+        self.calls = []
+
+    def __enter__(self):
+        from mbrl.controllers import colored_noise
+
+        self._mod = colored_noise
+        self._orig = colored_noise.torch_powerlaw_psd_gaussian
+
+        def fake(exponent, size, fmin=0):
+            y = self.provider(exponent, tuple(size))
+            self.calls.append((tuple(size), y.clone()))
+            return y
+
+        colored_noise.torch_powerlaw_psd_gaussian = fake
+        return self
+
+    def __exit__(self, *a):
+        self._mod.torch_powerlaw_psd_gaussian = self._orig

@@ -1,0 +1,96 @@
+"""Case table + seeded input builders shared by the golden generator (make_golden.py) and the tests.
+
+TEST INFRASTRUCTURE.  Imports only the oracle module (no reference code), so it works on the GPU box."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+if os.path.join(ROOT, "oracle") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import icem_oracle as orc  # noqa: E402
+
+
+class SeededNoise:
+    """Noise provider used on both sides of every parity test: standard normal draws from a numpy
+    RandomState pushed through the float64 irDFT matrix of icem_oracle (-> realistic colored noise)."""
+
+    def __init__(self, seed, beta):
+        self.rs = np.random.RandomState(seed)
+        self.beta = beta
+        self._M = {}
+
+    def __call__(self, size):
+        n, U, H = size
+        F = H // 2 + 1
+        if H not in self._M:
+            self._M[H] = orc.irdft_matrix(self.beta, H).astype(np.float64)
+        z = self.rs.standard_normal((n, U, 2 * F))
+        return torch.from_numpy((z @ self._M[H]).astype(np.float32))
+
+
+# ---- case table ---------------------------------------------------------------------------------
+# Every case is fully described by this dict; tests rebuild the inputs from it.
+CASES = {
+    # rollouts + costs
+    "rollout_gnn_c2": dict(kind="rollout", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=24, H=6,
+                           wseed=11, identity_norm=True, running=False, oseed=3),
+    "rollout_gnn_c6_stack": dict(kind="rollout", env="construction", n_obj=6, model="gnn", hidden=128, layers=2, P=7,
+                                 H=5, wseed=12, identity_norm=False, running=False, oseed=4),
+    "rollout_gnn_pg4": dict(kind="rollout", env="playground", n_obj=4, model="gnn", hidden=64, layers=2, P=12, H=5,
+                            wseed=13, identity_norm=False, running=True, oseed=5),
+    "rollout_mlp_c4": dict(kind="rollout", env="construction", n_obj=4, model="mlp", hidden=256, layers=3, P=10, H=5,
+                           wseed=14, identity_norm=False, running=False, oseed=6),
+    "rollout_gnn_c3_pp_sparse": dict(kind="rollout", env="construction", n_obj=3, model="gnn", hidden=128, layers=2,
+                                     P=9, H=4, wseed=15, identity_norm=True, running=False, oseed=7,
+                                     case="PickAndPlace", sparse=False),
+    # full MPC steps (3 consecutive get_action calls after beginning_of_rollout)
+    "mpc_gnn_c2_curious": dict(kind="mpc", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=128, H=20,
+                               wseed=21, identity_norm=True, running=False, oseed=8, nseed=100, steps=3,
+                               curiosity=True, cost="sum", sampler={}),  # BASELINE config 1
+    "mpc_gnn_c6_stack_extr": dict(kind="mpc", env="construction", n_obj=6, model="gnn", hidden=128, layers=2, P=48,
+                                  H=8, wseed=22, identity_norm=False, running=False, oseed=9, nseed=101, steps=3,
+                                  curiosity=True, extrinsic=True, cost="best",
+                                  sampler=dict(init_std=0.5, use_mean_actions=False)),  # config 3 style
+    "mpc_gnn_c2_task": dict(kind="mpc", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=64, H=10,
+                            wseed=23, identity_norm=True, running=False, oseed=10, nseed=102, steps=2,
+                            curiosity=False, cost="best", sampler=dict(init_std=0.5, use_mean_actions=False)),
+    "mpc_gnn_pg4_curious": dict(kind="mpc", env="playground", n_obj=4, model="gnn", hidden=64, layers=2, P=64, H=10,
+                                wseed=24, identity_norm=False, running=True, oseed=11, nseed=103, steps=3,
+                                curiosity=True, cost="sum",
+                                sampler=dict(keep_previous_elites=False, shift_elites_over_time=False,
+                                             fraction_elites_reused=0.1)),  # config 4 hyper-parameters
+    "mpc_mlp_c4_curious": dict(kind="mpc", env="construction", n_obj=4, model="mlp", hidden=256, layers=3, P=64, H=10,
+                               wseed=25, identity_norm=False, running=False, oseed=12, nseed=104, steps=2,
+                               curiosity=True, cost="sum", sampler={}),  # config 5 style
+}
+
+
+def build_inputs(c):
+    """Everything derivable from the case dict (used by the generator *and* by the tests)."""
+    if c["env"] == "construction":
+        spec = orc.construction_spec(c["n_obj"], case=c.get("case", "Singletower"), sparse=c.get("sparse", False))
+    else:
+        spec = orc.playground_spec(c["n_obj"])
+    E = 5
+    if c["model"] == "gnn":
+        shapes = orc.gnn_weight_shapes(spec, c["hidden"], c["layers"], E)
+        ndims = orc.gnn_normalizer_dims(spec)
+    else:
+        shapes = orc.mlp_weight_shapes(spec, c["hidden"], c["layers"], E)
+        ndims = orc.mlp_normalizer_dims(spec)
+    weights = orc.synth_weights(shapes, c["wseed"])
+    norms = orc.synth_normalizers(ndims, c["wseed"], identity=c["identity_norm"])
+    obs, goal = orc.synth_start_obs(spec, c["oseed"])
+    return spec, weights, norms, obs, goal
+
+
+def rollout_actions(c, spec):
+    rs = np.random.RandomState(c["oseed"] + 1000)
+    return np.clip(0.8 * rs.standard_normal((c["P"], c["H"], spec.action_dim)), -1, 1).astype(np.float32)
+
+

@@ -1,0 +1,104 @@
+"""CPU: the oracle restatement (oracle/icem_oracle.py) against the fixtures the REFERENCE produced
+(tests/golden/*.npz, generator: tests/golden/make_golden.py).  This is the pin of the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import icem_oracle as orc
+from cases import CASES, SeededNoise, build_inputs, rollout_actions
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def make_oracle_model(c, spec, weights, norms):
+    cls = orc.GNNEnsembleOracle if c["model"] == "gnn" else orc.MLPEnsembleOracle
+    return cls(spec=spec, weights=weights, normalizers=norms, hidden=c["hidden"], num_layers=c["layers"])
+
+
+def icem_params(c):
+    kw = dict(horizon=c["H"], num_traj=c["P"], cost_along_trajectory=c["cost"], curiosity=c["curiosity"],
+              extrinsic_reward=c.get("extrinsic", False))
+    kw.update(c["sampler"])
+    return orc.ICEMParams(**kw)
+
+
+@pytest.mark.parametrize("name", [k for k, c in CASES.items() if c["kind"] == "rollout"])
+def test_rollout_and_costs_match_reference(name):
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec, weights, norms, obs, goal = build_inputs(c)
+    model = make_oracle_model(c, spec, weights, norms)
+    acts = torch.from_numpy(rollout_actions(c, spec))
+    start = torch.from_numpy(obs).view(1, -1).expand(c["P"], -1)
+    traj = orc.rollout(model, start, acts, torch.from_numpy(goal))
+    nxt = traj[1:].permute(2, 1, 0, 3)
+    ob = traj[:-1].permute(2, 1, 0, 3)
+    np.testing.assert_allclose(nxt.numpy(), g["next_observations"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(ob[:, :, 0].numpy(), g["first_observation"], rtol=0, atol=0)
+    np.testing.assert_allclose(orc.disagreement_bonus(nxt).numpy(), g["disagreement_bonus"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(orc.env_cost(spec, ob, nxt).numpy(), g["env_cost"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", [k for k, c in CASES.items() if c["kind"] == "mpc"])
+def test_mpc_steps_match_reference(name):
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec, weights, norms, obs, goal = build_inputs(c)
+    model = make_oracle_model(c, spec, weights, norms)
+    ctrl = orc.ICEMOracle(model, icem_params(c), SeededNoise(c["nseed"], 3.5))
+    ctrl.set_goal(goal)
+    ctrl.beginning_of_rollout()
+    for s in range(c["steps"]):
+        a = ctrl.get_action(g[f"s{s}_obs"])
+        tr = ctrl.trace[-1]
+        for i, it in enumerate(tr["iters"]):
+            np.testing.assert_allclose(it["costs"].numpy(), g[f"s{s}_i{i}_costs"], rtol=2e-4, atol=1e-5,
+                                       err_msg=f"{name} step {s} iter {i} costs")
+            np.testing.assert_array_equal(it["elite_idx"].numpy(), g[f"s{s}_i{i}_elite_idx"])
+            np.testing.assert_allclose(it["mean"].numpy(), g[f"s{s}_i{i}_mean"], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(it["std"].numpy(), g[f"s{s}_i{i}_std"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(a, g[f"s{s}_action"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(ctrl.mean_.numpy(), g[f"s{s}_mean_after"], rtol=1e-5, atol=1e-6)
+
+
+def test_colored_noise_matches_reference():
+    g = np.load(os.path.join(GOLD, "colored_noise.npz"))
+    for H in (20, 30, 35):
+        zr, zi, y = (torch.from_numpy(g[f"H{H}_{k}"]) for k in ("zr", "zi", "y"))
+        mine = orc.colored_noise_from_gaussians(zr, zi, 3.5, H)
+        np.testing.assert_allclose(mine.numpy(), y.numpy(), rtol=1e-5, atol=2e-6)
+        M = torch.from_numpy(orc.irdft_matrix(3.5, H))
+        via_matrix = torch.cat([zr, zi], dim=-1) @ M
+        np.testing.assert_allclose(via_matrix.numpy(), y.numpy(), rtol=1e-4, atol=5e-6)
+
+
+def test_philox_known_answers():
+    # Random123 known-answer vectors for Philox4x32-10 (kat_vectors in the Random123 distribution)
+    ctr = np.array([[0, 0, 0, 0], [0xFFFFFFFF] * 4, [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344]], dtype=np.uint32)
+    key = np.array([[0, 0], [0xFFFFFFFF, 0xFFFFFFFF], [0xA4093822, 0x299F31D0]], dtype=np.uint32)
+    out = orc.philox4x32(ctr, key)
+    exp = np.array([[0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8],
+                    [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD],
+                    [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]], dtype=np.uint32)
+    np.testing.assert_array_equal(out, exp)
+    z = orc.philox_normals(1234, 3, 4096, 32)
+    assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1.0) < 0.01
+
+
+def test_flops_per_model_step_matches_survey():
+    # SURVEY.md 8d table
+    for n, want in ((2, 372736), (4, 1275904), (6, 2781184)):
+        spec = orc.construction_spec(n)
+        m = orc.GNNEnsembleOracle(spec, orc.synth_weights(orc.gnn_weight_shapes(spec, 128, 2, 1), 0),
+                                  orc.synth_normalizers(orc.gnn_normalizer_dims(spec), 0, True))
+        assert orc.flops_per_model_step(m) == want
+    spec = orc.playground_spec(4)
+    m = orc.GNNEnsembleOracle(spec, orc.synth_weights(orc.gnn_weight_shapes(spec, 64, 2, 1), 0),
+                              orc.synth_normalizers(orc.gnn_normalizer_dims(spec), 0, True), hidden=64)
+    assert orc.flops_per_model_step(m) == 327424
+    spec = orc.construction_spec(4)
+    m = orc.MLPEnsembleOracle(spec, orc.synth_weights(orc.mlp_weight_shapes(spec, 256, 3, 1), 0),
+                              orc.synth_normalizers(orc.mlp_normalizer_dims(spec), 0, True))
+    assert orc.flops_per_model_step(m) == 323584
