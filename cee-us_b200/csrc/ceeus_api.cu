@@ -1,0 +1,490 @@
+// C ABI of libceeus_b200.so (see include/ceeus_b200.h): handle, weight hand-off, and the launch sequence of one
+// iCEM planning step.  No CPU fallback: every entry point either enqueues CUDA work or returns an error.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+using namespace ceeus;
+
+namespace {
+std::string g_create_error;
+
+struct TensorSpec {
+  int rows, cols;  // per member
+  int dst_off, dst_ld;
+};
+}  // namespace
+
+struct CeeusHandle_t {
+  CeeusConfig cfg{};
+  ModelDesc md{};
+  CostDesc cd{};
+  int device = 0, num_sms = 0;
+  float* d_weights = nullptr;
+  float* d_norm = nullptr;
+  float* d_low = nullptr;
+  float* d_high = nullptr;
+  float* d_goal = nullptr;
+  float* d_obs = nullptr;
+  float* d_irdft = nullptr;
+  float* h_obs = nullptr;     // pinned staging
+  float* h_action = nullptr;  // pinned staging
+  int norm_floats = 0;
+  CeeusBuffers bufs{};
+  bool bound = false, weights_set = false, norms_set = false;
+  bool has_elites = false;
+  uint64_t step_counter = 0;
+  int64_t launches = 0;
+  int F = 0;
+  std::vector<TensorSpec> wspec;
+  std::string err;
+};
+
+namespace {
+
+int fail(CeeusHandle h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define CU_CHECK(h, expr)                                                                                \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(h, CEEUS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+#define LAUNCH(h, expr)   \
+  do {                    \
+    CU_CHECK(h, expr);    \
+    (h)->launches += 1;   \
+  } while (0)
+
+void add_mlp(CeeusHandle h, MlpDesc& m, int din, int dout, int Hd, int L, bool ln, int& off) {
+  m.n_layers = L + 1;
+  for (int l = 0; l <= L; ++l) {
+    LayerDesc& ld = m.layer[l];
+    ld.K = l == 0 ? din : Hd;
+    ld.N = l == L ? dout : Hd;
+    ld.Kpad = round_up(ld.K, 4);
+    ld.Npad = round_up(ld.N, 64);
+    ld.w_off = off;
+    off += ld.Kpad * ld.Npad;
+    ld.b_off = off;
+    off += ld.Npad;
+    ld.g_off = ld.be_off = 0;
+    h->wspec.push_back({ld.K, ld.N, ld.w_off, ld.Npad});
+    h->wspec.push_back({1, ld.N, ld.b_off, ld.Npad});
+    if (l < L && ln) {
+      ld.g_off = off;
+      off += ld.Npad;
+      ld.be_off = off;
+      off += ld.Npad;
+      h->wspec.push_back({1, ld.N, ld.g_off, ld.Npad});
+      h->wspec.push_back({1, ld.N, ld.be_off, ld.Npad});
+    }
+  }
+}
+
+// irDFT matrix of the power-law noise (colored_noise.py:174-216), built in double.
+std::vector<float> build_irdft(double beta, int H) {
+  const int F = H / 2 + 1;
+  std::vector<double> s(F);
+  for (int k = 0; k < F; ++k) s[k] = std::pow((double)(k == 0 ? 1 : k) / H, -beta / 2.0);
+  double sum = 0;
+  for (int k = 1; k < F; ++k) {
+    double w = s[k];
+    if (k == F - 1) w *= (1 + (H % 2)) / 2.0;
+    sum += w * w;
+  }
+  const double sigma = 2.0 * std::sqrt(sum) / H;
+  std::vector<float> M((size_t)2 * F * H, 0.f);
+  const double pi = 3.14159265358979323846;
+  for (int k = 0; k < F; ++k)
+    for (int t = 0; t < H; ++t) {
+      const bool nyq = (H % 2 == 0) && (k == F - 1);
+      double re, im = 0.0;
+      if (k == 0) re = s[0] * std::sqrt(2.0);
+      else if (nyq) re = s[k] * std::sqrt(2.0) * std::cos(pi * t);
+      else {
+        re = 2 * s[k] * std::cos(2 * pi * k * t / H);
+        im = -2 * s[k] * std::sin(2 * pi * k * t / H);
+      }
+      M[(size_t)k * H + t] = (float)(re / (H * sigma));
+      M[(size_t)(F + k) * H + t] = (float)(im / (H * sigma));
+    }
+  return M;
+}
+
+int validate(const CeeusConfig& c, std::string& why) {
+  auto bad = [&](const char* m) {
+    why = m;
+    return CEEUS_ERR_INVALID;
+  };
+  if (c.abi_version != CEEUS_ABI_VERSION) return bad("abi_version mismatch");
+  if (c.model_kind != CEEUS_MODEL_GNN && c.model_kind != CEEUS_MODEL_MLP) return bad("model_kind");
+  if (c.ensemble_size < 2 || c.ensemble_size > kMaxEnsemble) return bad("ensemble_size must be in [2,8]");
+  if (c.num_layers < 1 || c.num_layers + 1 > kMaxLayers) return bad("num_layers must be in [1,3]");
+  if (c.hidden_dim != 64 && c.hidden_dim != 128 && c.hidden_dim != 256) return bad("hidden_dim must be 64, 128 or 256");
+  if (c.model_kind == CEEUS_MODEL_GNN) {
+    if (c.hidden_dim == 256) return bad("GNN hidden_dim must be 64 or 128");
+    if (c.n_obj < 2) return bad("GNN needs n_obj >= 2 (gnn_modules.py:190-241: row undefined for one node)");
+    if (c.n_obj * (c.n_obj - 1) > kTileRows) return bad("n_obj too large: N(N-1) must be <= 64");
+    if (c.dyn_dim > 64 || c.agent_dim > 64) return bad("dyn_dim / agent_dim must be <= 64");
+    if (c.agent_dim < 1) return bad("agent_dim must be >= 1 (agent_as_global_node)");
+  } else {
+    const int sd = c.agent_dim + c.n_obj * (c.dyn_dim + c.stat_dim);
+    if (round_up(sd, 64) > c.hidden_dim || sd > 128) return bad("MLP state dim too large for this build");
+  }
+  if (c.num_envs < 1 || c.num_traj < 2 || c.horizon < 1 || c.horizon > 256) return bad("num_envs/num_traj/horizon");
+  if (c.opt_iterations < 1) return bad("opt_iterations");
+  if (c.num_elites < 1 || c.num_elites > 64 || c.num_elites > c.num_traj) return bad("num_elites must be in [1,64] and <= num_traj");
+  if (c.num_kept < 0 || c.num_kept > c.num_elites) return bad("num_kept");
+  if (c.world_size < 1 || c.rank < 0 || c.rank >= c.world_size) return bad("world_size/rank");
+  if (c.world_size * c.num_elites + c.num_kept > 256) return bad("world_size * num_elites too large");
+  if (c.precision != CEEUS_PREC_FP32 && c.precision != CEEUS_PREC_TC) return bad("precision");
+  const bool need_env = !c.curiosity || c.extrinsic_reward;
+  if (need_env && c.env_kind == CEEUS_ENV_NONE) return bad("task cost requested but env_kind is NONE");
+  if (c.env_kind == CEEUS_ENV_CONSTRUCTION && (c.goal_dim != 3 * c.n_obj + 3 || c.dyn_dim < 3 || c.agent_dim < 3))
+    return bad("construction layout: goal_dim must be 3N+3");
+  if (c.env_kind == CEEUS_ENV_PLAYGROUND && (c.goal_dim != 2 * c.n_obj || c.dyn_dim < 2)) return bad("playground layout: goal_dim must be 2N");
+  if (c.cost_along_trajectory != CEEUS_COST_SUM && c.cost_along_trajectory != CEEUS_COST_BEST) return bad("cost_along_trajectory");
+  return CEEUS_OK;
+}
+
+cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace
+
+extern "C" {
+
+int ceeus_abi_version(void) { return CEEUS_ABI_VERSION; }
+
+const char* ceeus_last_error(CeeusHandle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
+  if (!cfg || !out) return fail(nullptr, CEEUS_ERR_INVALID, "null argument");
+  std::string why;
+  if (int rc = validate(*cfg, why)) return fail(nullptr, rc, why);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, CEEUS_ERR_CUDA, "no CUDA device: libceeus_b200 has no CPU fallback");
+  CeeusHandle h = new CeeusHandle_t();
+  h->cfg = *cfg;
+  const CeeusConfig& c = h->cfg;
+  cudaGetDevice(&h->device);
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
+
+  ModelDesc& md = h->md;
+  md.kind = c.model_kind;
+  md.E = c.ensemble_size; md.N = c.n_obj; md.A = c.agent_dim; md.D = c.dyn_dim; md.S = c.stat_dim; md.U = c.action_dim;
+  md.G = c.goal_dim; md.Hd = c.hidden_dim; md.L = c.num_layers;
+  md.act = c.act_fn; md.layer_norm = c.layer_norm; md.aggr_mean = c.aggr_mean;
+  md.sd = c.agent_dim + c.n_obj * (c.dyn_dim + c.stat_dim);
+  md.O = md.sd + c.goal_dim;
+  int off = 0;
+  const bool ln = c.layer_norm != 0;
+  if (c.model_kind == CEEUS_MODEL_GNN) {
+    const int na = c.dyn_dim + c.stat_dim;
+    add_mlp(h, md.mlp[0], 2 * na + c.agent_dim + c.action_dim, c.hidden_dim, c.hidden_dim, c.num_layers, ln, off);
+    add_mlp(h, md.mlp[1], na + c.agent_dim + c.action_dim + c.hidden_dim, c.dyn_dim, c.hidden_dim, c.num_layers, ln, off);
+    add_mlp(h, md.mlp[2], c.agent_dim + c.action_dim + c.hidden_dim, c.agent_dim, c.hidden_dim, c.num_layers, ln, off);
+    int o = 0;
+    md.nrm.in_agent = o; o += 2 * md.A;
+    md.nrm.in_dyn = o; o += 2 * md.D;
+    md.nrm.in_stat = o; o += 2 * md.S;
+    md.nrm.in_action = o; o += 2 * md.U;
+    md.nrm.out_agent = o; o += 2 * md.A;
+    md.nrm.out_dyn = o; o += 2 * md.D;
+    h->norm_floats = o;
+    const GnnTiling tl = make_gnn_tiling(md);
+    if (tl.G < 1 || tl.smem_bytes > 227 * 1024) {
+      delete h;
+      return fail(nullptr, CEEUS_ERR_INVALID, "GNN tiling does not fit shared memory");
+    }
+  } else {
+    add_mlp(h, md.mlp[0], md.sd + c.action_dim, md.sd, c.hidden_dim, c.num_layers, ln, off);
+    md.nrm.in_all = 0;
+    md.nrm.out_all = 2 * (md.sd + md.U);
+    h->norm_floats = 2 * (md.sd + md.U) + 2 * md.sd;
+  }
+  md.member_stride = off;
+
+  CostDesc& cd = h->cd;
+  cd.curiosity = c.curiosity; cd.extrinsic = c.extrinsic_reward; cd.cost_along = c.cost_along_trajectory;
+  cd.env_kind = c.env_kind; cd.cost_case = c.cost_case; cd.sparse = c.sparse; cd.shaped = c.shaped_reward;
+  cd.use_std = c.use_ensemble_cost_std; cd.extrinsic_scale = c.extrinsic_scale; cd.threshold = c.threshold;
+  cd.buffer_threshold = c.buffer_threshold;
+
+  h->F = c.horizon / 2 + 1;
+  auto alloc = [&](float** p, size_t n) { return cudaMalloc(p, (n ? n : 1) * sizeof(float)); };
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = alloc(&h->d_weights, (size_t)md.E * md.member_stride);
+  if (e == cudaSuccess) e = cudaMemset(h->d_weights, 0, (size_t)md.E * md.member_stride * sizeof(float));
+  if (e == cudaSuccess) e = alloc(&h->d_norm, h->norm_floats);
+  if (e == cudaSuccess) e = alloc(&h->d_low, md.U);
+  if (e == cudaSuccess) e = alloc(&h->d_high, md.U);
+  if (e == cudaSuccess) e = alloc(&h->d_goal, (size_t)c.num_envs * (md.G ? md.G : 1));
+  if (e == cudaSuccess) e = cudaMemset(h->d_goal, 0, (size_t)c.num_envs * (md.G ? md.G : 1) * sizeof(float));
+  if (e == cudaSuccess) e = alloc(&h->d_obs, (size_t)c.num_envs * md.O);
+  if (e == cudaSuccess) e = alloc(&h->d_irdft, (size_t)2 * h->F * c.horizon);
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_obs, (size_t)c.num_envs * md.O * sizeof(float));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_action, (size_t)c.num_envs * md.U * sizeof(float));
+  if (e == cudaSuccess) {
+    std::vector<float> M = build_irdft(c.noise_beta, c.horizon);
+    e = cudaMemcpy(h->d_irdft, M.data(), M.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) {
+    std::vector<float> lo(md.U, -1.f), hi(md.U, 1.f);
+    e = cudaMemcpy(h->d_low, lo.data(), md.U * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_high, hi.data(), md.U * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    std::string msg = std::string("allocation failed: ") + cudaGetErrorString(e);
+    ceeus_destroy(h);
+    return fail(nullptr, CEEUS_ERR_CUDA, msg);
+  }
+  *out = h;
+  return CEEUS_OK;
+}
+
+void ceeus_destroy(CeeusHandle h) {
+  if (!h) return;
+  cudaFree(h->d_weights); cudaFree(h->d_norm); cudaFree(h->d_low); cudaFree(h->d_high);
+  cudaFree(h->d_goal); cudaFree(h->d_obs); cudaFree(h->d_irdft);
+  if (h->h_obs) cudaFreeHost(h->h_obs);
+  if (h->h_action) cudaFreeHost(h->h_action);
+  delete h;
+}
+
+int ceeus_num_weight_tensors(CeeusHandle h) { return h ? (int)h->wspec.size() : CEEUS_ERR_INVALID; }
+
+int ceeus_weight_tensor_shape(CeeusHandle h, int i, int32_t* rows, int32_t* cols) {
+  if (!h || i < 0 || i >= (int)h->wspec.size() || !rows || !cols) return fail(h, CEEUS_ERR_INVALID, "weight_tensor_shape: bad index");
+  *rows = h->wspec[i].rows;
+  *cols = h->wspec[i].cols;
+  return CEEUS_OK;
+}
+
+int ceeus_set_weights(CeeusHandle h, const float* const* dev_ptrs, int n, void* stream) {
+  if (!h || !dev_ptrs) return fail(h, CEEUS_ERR_INVALID, "set_weights: null argument");
+  if (n != (int)h->wspec.size()) return fail(h, CEEUS_ERR_INVALID, "set_weights: expected " + std::to_string(h->wspec.size()) + " tensors");
+  for (int i = 0; i < n; ++i) {
+    if (!dev_ptrs[i]) return fail(h, CEEUS_ERR_INVALID, "set_weights: null tensor pointer");
+    const TensorSpec& t = h->wspec[i];
+    LAUNCH(h, launch_repack(dev_ptrs[i], h->d_weights, h->md.E, t.rows, t.cols, h->md.member_stride, t.dst_off, t.dst_ld, S(stream)));
+  }
+  h->weights_set = true;
+  return CEEUS_OK;
+}
+
+int ceeus_set_normalizers(CeeusHandle h, const float* host, int n_floats) {
+  if (!h || !host) return fail(h, CEEUS_ERR_INVALID, "set_normalizers: null argument");
+  if (n_floats != h->norm_floats) return fail(h, CEEUS_ERR_INVALID, "set_normalizers: expected " + std::to_string(h->norm_floats) + " floats");
+  CU_CHECK(h, cudaMemcpy(h->d_norm, host, (size_t)n_floats * sizeof(float), cudaMemcpyHostToDevice));
+  h->norms_set = true;
+  return CEEUS_OK;
+}
+
+int ceeus_set_action_bounds(CeeusHandle h, const float* low_host, const float* high_host) {
+  if (!h || !low_host || !high_host) return fail(h, CEEUS_ERR_INVALID, "set_action_bounds: null argument");
+  CU_CHECK(h, cudaMemcpy(h->d_low, low_host, h->md.U * sizeof(float), cudaMemcpyHostToDevice));
+  CU_CHECK(h, cudaMemcpy(h->d_high, high_host, h->md.U * sizeof(float), cudaMemcpyHostToDevice));
+  return CEEUS_OK;
+}
+
+int ceeus_set_goal(CeeusHandle h, const float* goal_host) {
+  if (!h || !goal_host) return fail(h, CEEUS_ERR_INVALID, "set_goal: null argument");
+  if (h->md.G == 0) return CEEUS_OK;
+  CU_CHECK(h, cudaMemcpy(h->d_goal, goal_host, (size_t)h->cfg.num_envs * h->md.G * sizeof(float), cudaMemcpyHostToDevice));
+  return CEEUS_OK;
+}
+
+int ceeus_bind_buffers(CeeusHandle h, const CeeusBuffers* b) {
+  if (!h || !b) return fail(h, CEEUS_ERR_INVALID, "bind_buffers: null argument");
+  if (!b->mean || !b->std || !b->actions || !b->traj || !b->costs_per_model || !b->costs || !b->elite_actions ||
+      !b->elite_costs || !b->elite_cpm || !b->elite_idx || !b->cand || !b->action_out)
+    return fail(h, CEEUS_ERR_INVALID, "bind_buffers: every buffer must be non-null");
+  h->bufs = *b;
+  h->bound = true;
+  return CEEUS_OK;
+}
+
+int ceeus_cand_record_len(CeeusHandle h) {
+  return h ? 2 + h->cfg.ensemble_size + h->cfg.horizon * h->cfg.action_dim : CEEUS_ERR_INVALID;
+}
+
+static int do_rollout(CeeusHandle h, const float* start_obs_dev, int traj_per_start, const float* actions_dev, int n,
+                      int traj_per_goal, float* traj_dev, cudaStream_t st) {
+  if (!h->weights_set || !h->norms_set) return fail(h, CEEUS_ERR_STATE, "rollout before set_weights / set_normalizers");
+  RolloutArgs ra{};
+  ra.weights = h->d_weights; ra.norm = h->d_norm; ra.start_obs = start_obs_dev; ra.goal = h->d_goal;
+  ra.actions = actions_dev; ra.traj = traj_dev; ra.n = n; ra.H = h->cfg.horizon;
+  ra.traj_per_start = traj_per_start; ra.traj_per_goal = traj_per_goal;
+  if (h->cfg.precision == CEEUS_PREC_TC) return fail(h, CEEUS_ERR_INVALID, "CEEUS_PREC_TC rollout kernel is not part of this build yet");
+  if (h->md.kind == CEEUS_MODEL_GNN) LAUNCH(h, launch_rollout_gnn_simt(h->md, ra, h->num_sms, st));
+  else LAUNCH(h, launch_rollout_mlp_simt(h->md, ra, st));
+  return CEEUS_OK;
+}
+
+int ceeus_rollout(CeeusHandle h, const float* start_obs_dev, int n_start, const float* actions_dev, int n, float* traj_dev,
+                  void* stream) {
+  if (!h || !start_obs_dev || !actions_dev || !traj_dev) return fail(h, CEEUS_ERR_INVALID, "rollout: null argument");
+  if (n < 1 || n_start < 1 || n % n_start != 0 || n % h->cfg.num_envs != 0)
+    return fail(h, CEEUS_ERR_INVALID, "rollout: n must be a multiple of n_start and of num_envs");
+  return do_rollout(h, start_obs_dev, n / n_start, actions_dev, n, n / h->cfg.num_envs, traj_dev, S(stream));
+}
+
+static int do_costs(CeeusHandle h, const float* traj_dev, int n, float* cpm, float* costs, cudaStream_t st) {
+  CostArgs ca{};
+  ca.traj = traj_dev; ca.cpm = cpm; ca.costs = costs; ca.n = n; ca.H = h->cfg.horizon; ca.E = h->md.E; ca.O = h->md.O;
+  ca.N = h->md.N; ca.A = h->md.A; ca.D = h->md.D; ca.S = h->md.S; ca.G = h->md.G; ca.sd = h->md.sd;
+  LAUNCH(h, launch_costs(ca, h->cd, st));
+  return CEEUS_OK;
+}
+
+int ceeus_costs(CeeusHandle h, const float* traj_dev, int n, float* costs_per_model_dev, float* costs_dev, void* stream) {
+  if (!h || !traj_dev || !costs_per_model_dev || !costs_dev || n < 1) return fail(h, CEEUS_ERR_INVALID, "costs: bad argument");
+  return do_costs(h, traj_dev, n, costs_per_model_dev, costs_dev, S(stream));
+}
+
+int ceeus_sample(CeeusHandle h, const float* mean_dev, const float* std_dev, const float* noise_dev, float* gauss_dev,
+                 int write_gauss, uint32_t stream_id, int64_t first_row, int n, float* actions_dev, void* stream) {
+  if (!h || !mean_dev || !std_dev || !actions_dev || n < 1 || n % h->cfg.num_envs != 0)
+    return fail(h, CEEUS_ERR_INVALID, "sample: bad argument");
+  SampleArgs a{};
+  a.mean = mean_dev; a.std = std_dev; a.low = h->d_low; a.high = h->d_high; a.noise = noise_dev; a.gauss = gauss_dev;
+  a.write_gauss = write_gauss; a.irdft = h->d_irdft; a.actions = actions_dev; a.n = n; a.H = h->cfg.horizon;
+  a.U = h->md.U; a.F = h->F; a.rows_per_env = n / h->cfg.num_envs; a.colored = h->cfg.colored_noise;
+  a.seed = h->cfg.seed; a.stream_id = stream_id; a.first_row = first_row;
+  a.global_rows_per_env = (long long)(n / h->cfg.num_envs) * h->cfg.world_size;
+  LAUNCH(h, launch_sample(a, S(stream)));
+  return CEEUS_OK;
+}
+
+static FinishArgs finish_args(CeeusHandle h) {
+  FinishArgs f{};
+  f.mean = h->bufs.mean; f.std = h->bufs.std; f.elite_actions = h->bufs.elite_actions; f.low = h->d_low; f.high = h->d_high;
+  f.action_out = h->bufs.action_out; f.nE = h->cfg.num_envs; f.k = h->cfg.num_elites; f.H = h->cfg.horizon; f.U = h->md.U;
+  f.execute_best = h->cfg.execute_best_elite; f.relative_init = h->cfg.relative_init; f.init_std = h->cfg.init_std;
+  return f;
+}
+
+int ceeus_begin_rollout(CeeusHandle h, void* stream) {
+  if (!h) return CEEUS_ERR_INVALID;
+  if (!h->bound) return fail(h, CEEUS_ERR_STATE, "begin_rollout before bind_buffers");
+  LAUNCH(h, launch_reset_dist(finish_args(h), S(stream)));
+  h->has_elites = false;
+  return CEEUS_OK;
+}
+
+int ceeus_has_elites(CeeusHandle h) { return h && h->has_elites ? 1 : 0; }
+
+int ceeus_plan_iter_local(CeeusHandle h, int iter, const float* obs_dev, const float* noise_dev, const float* shift_noise_dev,
+                          void* stream) {
+  if (!h || !obs_dev) return fail(h, CEEUS_ERR_INVALID, "plan_iter_local: null argument");
+  if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
+  const CeeusConfig& c = h->cfg;
+  if (iter < 0 || iter >= c.opt_iterations) return fail(h, CEEUS_ERR_INVALID, "plan_iter_local: iter out of range");
+  cudaStream_t st = S(stream);
+  const int n = c.num_envs * c.num_traj;
+  const uint32_t streams_per_step = (uint32_t)c.opt_iterations + 1u;
+  const uint32_t base_stream = (uint32_t)(h->step_counter * streams_per_step);
+  // 1. sample_action_sequences (mpc_torch.py:204-236)
+  SampleArgs a{};
+  a.mean = h->bufs.mean; a.std = h->bufs.std; a.low = h->d_low; a.high = h->d_high; a.noise = noise_dev; a.gauss = nullptr;
+  a.write_gauss = 0; a.irdft = h->d_irdft; a.actions = h->bufs.actions; a.n = n; a.H = c.horizon; a.U = h->md.U; a.F = h->F;
+  a.rows_per_env = c.num_traj; a.colored = c.colored_noise; a.seed = c.seed; a.stream_id = base_stream + (uint32_t)iter;
+  a.first_row = (long long)c.rank * c.num_traj; a.global_rows_per_env = (long long)c.num_traj * c.world_size;
+  LAUNCH(h, launch_sample(a, st));
+  // 2. mean-action row + elites shifted over time live at global rows 0..n_kept-1 => rank 0
+  if (c.rank == 0) {
+    FixupArgs f{};
+    f.actions = h->bufs.actions; f.mean = h->bufs.mean; f.std = h->bufs.std; f.low = h->d_low; f.high = h->d_high;
+    f.elite_actions = h->bufs.elite_actions; f.shift_noise = shift_noise_dev; f.irdft = h->d_irdft;
+    f.nE = c.num_envs; f.P = c.num_traj; f.H = c.horizon; f.U = h->md.U; f.F = h->F; f.k = c.num_elites; f.n_kept = c.num_kept;
+    f.colored = c.colored_noise;
+    f.write_mean_row = c.use_mean_actions && iter == c.opt_iterations - 1;
+    f.shift_elites = iter == 0 && c.shift_elites_over_time && h->has_elites && c.num_kept > 0;
+    f.seed = c.seed; f.stream_id = base_stream + (uint32_t)c.opt_iterations;
+    if (f.write_mean_row || f.shift_elites) LAUNCH(h, launch_fixup(f, st));
+  }
+  // 3. predict_n_steps
+  if (int rc = do_rollout(h, obs_dev, c.num_traj, h->bufs.actions, n, c.num_traj, h->bufs.traj, st)) return rc;
+  // 4. trajectory costs
+  if (int rc = do_costs(h, h->bufs.traj, n, h->bufs.costs_per_model, h->bufs.costs, st)) return rc;
+  // 5. this rank's elite candidates
+  TopkArgs t{};
+  t.costs = h->bufs.costs; t.cpm = h->bufs.costs_per_model; t.actions = h->bufs.actions; t.cand = h->bufs.cand;
+  t.nE = c.num_envs; t.P = c.num_traj; t.E = h->md.E; t.HU = c.horizon * h->md.U; t.k = c.num_elites;
+  t.rec = ceeus_cand_record_len(h); t.first_index = (long long)c.rank * c.num_traj;
+  LAUNCH(h, launch_topk(t, st));
+  return CEEUS_OK;
+}
+
+int ceeus_plan_iter_update(CeeusHandle h, int iter, const float* cand_all_dev, void* stream) {
+  if (!h || !cand_all_dev) return fail(h, CEEUS_ERR_INVALID, "plan_iter_update: null argument");
+  if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
+  const CeeusConfig& c = h->cfg;
+  UpdateArgs u{};
+  u.cand_all = cand_all_dev; u.elite_actions = h->bufs.elite_actions; u.elite_costs = h->bufs.elite_costs;
+  u.elite_cpm = h->bufs.elite_cpm; u.elite_idx = h->bufs.elite_idx; u.mean = h->bufs.mean; u.std = h->bufs.std;
+  u.world = c.world_size; u.nE = c.num_envs; u.k = c.num_elites; u.E = h->md.E; u.H = c.horizon; u.U = h->md.U;
+  u.rec = ceeus_cand_record_len(h);
+  u.n_kept_in = (iter > 0 && c.keep_previous_elites) ? c.num_kept : 0;  // mpc_torch.py:319-321
+  u.pop_fresh = (long long)c.num_traj * c.world_size;
+  u.alpha = c.alpha;
+  LAUNCH(h, launch_update(u, S(stream)));
+  return CEEUS_OK;
+}
+
+int ceeus_plan_finish(CeeusHandle h, void* stream) {
+  if (!h) return CEEUS_ERR_INVALID;
+  if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
+  LAUNCH(h, launch_finish(finish_args(h), S(stream)));
+  h->has_elites = true;
+  h->step_counter += 1;
+  return CEEUS_OK;
+}
+
+int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, const float* noise_dev_or_null, void* stream) {
+  if (!h || !obs_host || !action_host) return fail(h, CEEUS_ERR_INVALID, "plan_step: null argument");
+  if (h->cfg.world_size != 1) return fail(h, CEEUS_ERR_INVALID, "plan_step is single-GPU; use plan_iter_local/update with an all-gather");
+  const CeeusConfig& c = h->cfg;
+  cudaStream_t st = S(stream);
+  const size_t ob = (size_t)c.num_envs * h->md.O * sizeof(float);
+  std::memcpy(h->h_obs, obs_host, ob);
+  CU_CHECK(h, cudaMemcpyAsync(h->d_obs, h->h_obs, ob, cudaMemcpyHostToDevice, st));
+  const size_t per_iter = (size_t)c.num_envs * c.num_traj * h->md.U * c.horizon;
+  const size_t per_shift = (size_t)c.num_envs * c.num_kept * h->md.U * c.horizon;
+  const float* np = noise_dev_or_null;
+  for (int i = 0; i < c.opt_iterations; ++i) {
+    const float* ni = np;
+    const float* ns = nullptr;
+    if (np) {
+      np += per_iter;
+      if (i == 0 && c.shift_elites_over_time && h->has_elites && c.num_kept > 0) {
+        ns = np;
+        np += per_shift;
+      }
+    }
+    if (int rc = ceeus_plan_iter_local(h, i, h->d_obs, ni, ns, stream)) return rc;
+    if (int rc = ceeus_plan_iter_update(h, i, h->bufs.cand, stream)) return rc;
+  }
+  if (int rc = ceeus_plan_finish(h, stream)) return rc;
+  const size_t ab = (size_t)c.num_envs * h->md.U * sizeof(float);
+  CU_CHECK(h, cudaMemcpyAsync(h->h_action, h->bufs.action_out, ab, cudaMemcpyDeviceToHost, st));
+  CU_CHECK(h, cudaStreamSynchronize(st));
+  std::memcpy(action_host, h->h_action, ab);
+  return CEEUS_OK;
+}
+
+int64_t ceeus_kernel_launches(CeeusHandle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+"""Drop-in forward models: the inference half of
+
+  * ``GNNForwardEnsembleModel``          (yaml ``forward_model: ParallelGNNDeterministicEnsemble``,
+                                          mbrl/models/gnn_ensemble.py:32-983)
+  * ``ParallelNNDeterministicEnsemble``  (mbrl/models/mlp_ensemble.py:24-641)
+
+behind the same constructor keywords (the yaml ``forward_model_params``), the same ``predict_n_steps`` /
+``predict`` / ``reset`` / ``load`` / ``state_dict`` surface and the same checkpoint format; the rollout itself is ONE
+launch of the CUDA kernel in cee-us_b200/csrc.  Training stays with the reference (out of scope):
+after ``train()`` hand the new weights over with ``load_state_dict`` / ``sync_from``.
+"""
+import numpy as np
+import torch
+
+from .engine import Engine
+from .rollout_buffer import RolloutView
+
+
+def _np(x):
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+class _B200Ensemble:
+    model_kind = None
+    _norm_groups = ()
+
+    def __init__(self, *, env, model_params, train_params=None, target_is_delta=True, use_input_normalization=True,
+                 use_output_normalization=True, normalize_w_running_stats=True, agent_as_global_node=True,
+                 backend_params=None, **kwargs):
+        if not target_is_delta:
+            raise NotImplementedError("target_is_delta=False is not used by any shipped setting and is unsupported")
+        if not agent_as_global_node:
+            raise NotImplementedError("HomogeneousGraphNeuralNetworkEnsemble is not implemented (SURVEY.md 8f rank 1)")
+        self.env = env
+        self.train_params = dict(train_params or {})
+        self.target_is_delta = target_is_delta
+        self.use_input_normalization = use_input_normalization
+        self.use_output_normalization = use_output_normalization
+        self.normalize_w_running_stats = normalize_w_running_stats
+        self.backend_params = dict(backend_params or {})
+        self._parse_model_params(**model_params)
+        self.num_simulated_trajectories = None
+        self.horizon = None
+        self.memory_is_preallocated = False
+        self._state = None          # state_dict (reference key names) of torch tensors
+        self._normalizers = None    # name -> (mean, std) numpy
+        self.weights_version = 0
+        self._engines = {}
+        self._reset_normalizers()
+
+    # -- parameters ---------------------------------------------------------------------------------------
+    def _reset_normalizers(self):
+        self._normalizers = {k: (np.zeros(d, np.float32), np.ones(d, np.float32)) for k, d in self._norm_dims().items()}
+
+    def load_state_dict(self, state_dict):
+        self._state = {k: torch.as_tensor(v).detach().clone().float() for k, v in state_dict.items()}
+        self.weights_version += 1
+
+    def state_dict(self):
+        if self._state is None:
+            raise RuntimeError("no weights loaded")
+        return self._state
+
+    def set_normalizers(self, normalizers):
+        """normalizers: name -> (mean, std); names as in ``_norm_groups``.  Disabled normalisation == identity."""
+        for k, (m, s) in normalizers.items():
+            if k not in self._normalizers:
+                raise KeyError(k)
+            m, s = _np(m).astype(np.float32).reshape(-1), _np(s).astype(np.float32).reshape(-1)
+            want = self._normalizers[k][0].shape[0]
+            if m.size == 1 and want != 1:  # an un-updated running Normalizer holds scalars (torch_helpers.py:812-816)
+                m, s = np.full(want, m[0], np.float32), np.full(want, s[0], np.float32)
+            assert m.shape[0] == want and s.shape[0] == want, (k, m.shape, want)
+            self._normalizers[k] = (m, s)
+        self.weights_version += 1
+
+    def _normalizer_list(self):
+        out = []
+        for k in self._norm_groups:
+            m, s = self._normalizers[k]
+            is_input = k.startswith("in")
+            if (is_input and not self.use_input_normalization) or (not is_input and not self.use_output_normalization):
+                m, s = np.zeros_like(m), np.ones_like(s)
+            out.append((m, s))
+        return out
+
+    def sync_from(self, reference_model):
+        """Weight hand-off from a live reference model object (after its ``train()`` / ``load()``)."""
+        self.load_state_dict(reference_model.model.state_dict())
+        self.set_normalizers(self._read_reference_normalizers(reference_model))
+
+    @staticmethod
+    def _nz(n):
+        if hasattr(n, "mean_tensor"):  # Normalizer (running stats), torch_helpers.py:804-883
+            return _np(n.mean_tensor), _np(n.std_tensor)
+        return _np(n.mean), _np(n.std)  # Normalizer_v2, :767-801
+
+    # -- planner-facing surface (base_types.py:61-118) -----------------------------------------------------
+    def preallocate_memory(self):
+        self.memory_is_preallocated = True
+
+    def got_actual_observation_and_env_state(self, *, observation, env_state=None, model_state=None):
+        return None
+
+    def engine_kwargs(self):
+        return dict(env=self.env, model_kind=self.model_kind, ensemble_size=self.ensemble_size,
+                    hidden_dim=self.hidden_dim, num_layers=self.num_layers, act_fn=self.act_fn,
+                    layer_norm=self.layer_norm, aggr_fn=getattr(self, "aggr_fn", "mean"),
+                    precision=self.backend_params.get("precision", "fp32"))
+
+    def push_to(self, engine):
+        """(Re)uploads weights, normalisers if ``engine`` holds an older version."""
+        if engine.weights_version != self.weights_version:
+            engine.set_weights(self.state_dict())
+            engine.set_normalizers(self._normalizer_list())
+            engine.weights_version = self.weights_version
+
+    def _rollout_engine(self, n, horizon):
+        key = (n, horizon)
+        if key not in self._engines:
+            if len(self._engines) > 4:
+                self._engines.pop(next(iter(self._engines))).close()
+            self._engines[key] = Engine(horizon=horizon, num_traj=max(n, 2), **self.engine_kwargs())
+        eng = self._engines[key]
+        self.push_to(eng)
+        eng.set_goal(np.asarray(self.env.goal, np.float32))
+        return eng
+
+    @torch.no_grad()
+    def predict_n_steps(self, *, start_observations, start_states=None, policy, horizon):
+        """-> (buffer with observations / next_observations / actions [P,E,H,*], None)   gnn_ensemble.py:946-983"""
+        acts = getattr(policy, "action_sequences", None)
+        if acts is None:
+            raise NotImplementedError("only open-loop policies (OpenLoopPolicy.action_sequences [P,H,U]) are supported")
+        acts = torch.as_tensor(acts)
+        if start_observations.ndim != 2:
+            raise AttributeError("call predict_n_steps with a batch of observations [P, obs_dim]")
+        eng = self._rollout_engine(acts.shape[0], horizon)
+        start = torch.as_tensor(start_observations).to(eng.device, torch.float32)
+        acts = acts.to(eng.device, torch.float32).contiguous()
+        traj = eng.rollout(start.contiguous(), acts)
+        return RolloutView.from_device_buffers(traj, acts), None
+
+    @torch.no_grad()
+    def predict(self, *, observations, states=None, actions):
+        """One model step for every member: observations [E,B,O] (or [O]), actions [E,B,U] -> (next_obs, None, None)."""
+        obs = torch.as_tensor(observations, dtype=torch.float32)
+        act = torch.as_tensor(actions, dtype=torch.float32)
+        if obs.ndim == 1:
+            obs, act = obs[None, None].expand(self.ensemble_size, 1, -1), act[None, None].expand(self.ensemble_size, 1, -1)
+        E, B, O = obs.shape
+        # member e must start from its own state: run E*B single-step rollouts and take the diagonal blocks
+        eng = self._rollout_engine(E * B, 1)
+        start = obs.reshape(E * B, O).to(eng.device).contiguous()
+        a = act.reshape(E * B, 1, -1).to(eng.device).contiguous()
+        traj = eng.rollout(start, a)  # [2,E,E*B,O]
+        nxt = traj[1].view(E, E, B, O)
+        idx = torch.arange(E, device=nxt.device)
+        return nxt[idx, idx], None, None
+
+    def train(self, *a, **k):
+        raise NotImplementedError("model training stays with the reference implementation (SURVEY.md section 2 #18); "
+                                  "train there and call sync_from(reference_model)")
+
+
+class B200GNNEnsemble(_B200Ensemble):
+    """yaml key ``ParallelGNNDeterministicEnsembleB200``."""
+
+    model_kind = "gnn"
+    _norm_groups = ("in_agent", "in_dyn", "in_stat", "in_action", "out_agent", "out_dyn")
+
+    def _parse_model_params(self, *, n, hidden_dim, act_fn="relu", output_act_fn="none", num_layers=1,
+                            ignore_agent_object=True, num_message_passing=1, aggr_fn="mean", layer_norm=True,
+                            embedding_dim=None, embedding=False):
+        if output_act_fn not in ("none", None):
+            raise NotImplementedError("output_act_fn other than 'none'")
+        if not ignore_agent_object or num_message_passing != 1:
+            raise NotImplementedError("ignore_agent_object=False / num_message_passing>1 (SURVEY.md 8f rank 1)")
+        self.ensemble_size, self.hidden_dim, self.act_fn, self.num_layers = n, hidden_dim, act_fn, num_layers
+        self.layer_norm, self.aggr_fn = layer_norm, aggr_fn
+
+    def _norm_dims(self):
+        e = self.env
+        return {"in_agent": e.agent_dim, "in_dyn": e.object_dyn_dim, "in_stat": e.object_stat_dim,
+                "in_action": e.action_space.shape[0], "out_agent": e.agent_dim, "out_dyn": e.object_dyn_dim}
+
+    def _read_reference_normalizers(self, m):
+        return {"in_agent": self._nz(m.input_normalizer_agent), "in_dyn": self._nz(m.input_normalizer_obj_dyn),
+                "in_stat": self._nz(m.input_normalizer_obj_stat), "in_action": self._nz(m.action_normalizer),
+                "out_agent": self._nz(m.output_agent_normalizer), "out_dyn": self._nz(m.output_obj_normalizer)}
+
+    _CKPT = {"in_agent": "input_normalizer_agent", "in_dyn": "input_normalizer_obj_dyn",
+             "in_stat": "input_normalizer_obj_stat", "in_action": "action_normalizer",
+             "out_agent": "output_agent_normalizer", "out_dyn": "output_obj_normalizer"}
+
+    def reset(self, obs):
+        return {"obs": torch.as_tensor(np.asarray(obs), dtype=torch.float32)}  # gnn_ensemble.py:810-830
+
+    def load(self, path, for_training=True):
+        """Reads a checkpoint written by GNNForwardEnsembleModel.save (gnn_ensemble.py:756-808)."""
+        sd = torch.load(path, map_location="cpu", weights_only=False)
+        self.load_state_dict(sd["model"])
+        self.set_normalizers({k: (sd[v]["mean"], sd[v]["std"]) for k, v in self._CKPT.items() if v in sd})
+
+    def save(self, path):
+        out = {"model": {k: v.cpu() for k, v in self.state_dict().items()}}
+        for k, v in self._CKPT.items():
+            m, s = self._normalizers[k]
+            out[v] = {"mean": m.reshape(1, -1), "std": s.reshape(1, -1)}
+        torch.save(out, path)
+
+
+class B200MLPEnsemble(_B200Ensemble):
+    """yaml key ``ParallelNNDeterministicEnsembleB200``."""
+
+    model_kind = "mlp"
+    _norm_groups = ("in", "out")
+
+    def _parse_model_params(self, *, n, hidden_dim, act_fn="silu", output_act_fn="none", num_layers=1, layer_norm=False,
+                            spectral_norm=False, weight_initializer="torch_truncated_normal",
+                            bias_initializer="constant_zero", l1_reg=0, l2_reg=0):
+        if output_act_fn not in ("none", None) or spectral_norm:
+            raise NotImplementedError("output_act_fn / spectral_norm")
+        self.ensemble_size, self.hidden_dim, self.act_fn, self.num_layers = n, hidden_dim, act_fn, num_layers
+        self.layer_norm = layer_norm
+
+    def _norm_dims(self):
+        sd = self.env.observation_space_size_preproc
+        return {"in": sd + self.env.action_space.shape[0], "out": sd}
+
+    def _read_reference_normalizers(self, m):
+        return {"in": self._nz(m.input_normalizer), "out": self._nz(m.output_normalizer)}
+
+    def reset(self, observation):
+        return None  # mlp_ensemble.py:640-641
+
+    def load(self, path, for_training=True):
+        sd = torch.load(path, map_location="cpu", weights_only=False)  # mlp_ensemble.py:625-638
+        self.load_state_dict(sd["nn_state"])
+        self.set_normalizers({"in": (sd["input_normalizer"]["mean"], sd["input_normalizer"]["std"]),
+                              "out": (sd["output_normalizer"]["mean"], sd["output_normalizer"]["std"])})
+
+    def save(self, path):
+        torch.save({"nn_state": {k: v.cpu() for k, v in self.state_dict().items()},
+                    "input_normalizer": dict(zip(("mean", "std"), self._normalizers["in"])),
+                    "output_normalizer": dict(zip(("mean", "std"), self._normalizers["out"]))}, path)

@@ -1,0 +1,198 @@
+/*
+ * ceeus_b200.h -- C ABI of libceeus_b200.so: the B200 (sm_100a) implementation of the CEE-US iCEM planning
+ * hot path (martius-lab/cee-us).  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * The reference has no native boundary for this path (it is pure Python + torch eager), so every entry point
+ * below names the reference *Python* interface it stands behind (paths relative to the reference root):
+ *
+ *   ceeus_create / ceeus_destroy      TorchMpcICem.__init__ + preallocate_memory  mbrl/controllers/mpc_torch.py:20-110
+ *                                     GNNForwardEnsembleModel.__init__            mbrl/models/gnn_ensemble.py:37-141
+ *   ceeus_set_weights                 model.model.load_state_dict / state_dict()  mbrl/models/gnn_ensemble.py:793-808,
+ *                                                                                 mbrl/models/mlp_ensemble.py:625-638
+ *   ceeus_set_normalizers             Normalizer_v2 / Normalizer (mean, std)      mbrl/torch_helpers.py:767-883
+ *   ceeus_set_goal                    env.goal read by env.obs_postproc           mbrl/environments/fpp_construction_env.py:133-138
+ *   ceeus_rollout                     ForwardModel.predict_n_steps                mbrl/models/gnn_ensemble.py:946-983,
+ *                                                                                 mbrl/models/mlp_ensemble.py:575-611
+ *   ceeus_costs                       trajectory_cost_fn + ensemble mean/std      mbrl/controllers/mpc_torch.py:116-137,323-332
+ *                                                                                 mbrl/controllers/mpc_torch_curiosity.py:45-80
+ *                                     env.cost_fn                                 mbrl/environments/fpp_construction_env.py:404-511,
+ *                                                                                 mbrl/environments/playground_env_wgoals.py:108-157
+ *   ceeus_sample                      sample_action_sequences + colored noise     mbrl/controllers/mpc_torch.py:204-247,
+ *                                                                                 mbrl/controllers/colored_noise.py:115-218
+ *   ceeus_begin_rollout               beginning_of_rollout (reset mean/std/elites) mbrl/controllers/mpc_torch.py:159-202
+ *   ceeus_plan_iter_local /           one iCEM iteration of get_action            mbrl/controllers/mpc_torch.py:300-359
+ *   ceeus_plan_iter_update            update_distributions (top-k, refit)         mbrl/controllers/mpc_torch.py:445-478
+ *   ceeus_plan_finish                 action pick + shift-initialisation          mbrl/controllers/mpc_torch.py:383-421
+ *   ceeus_plan_step                   TorchMpcICem.get_action (single GPU)        mbrl/controllers/mpc_torch.py:282-439
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative CEEUS_ERR_* code; ceeus_last_error() gives the text.
+ *   - "dev" pointers are device pointers owned by the caller (PyTorch); the library borrows them for work
+ *     enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - "host" pointers are plain host memory read/written synchronously.
+ *   - all floating point data is IEEE float32, all index data int32.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef CEEUS_B200_H
+#define CEEUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CEEUS_ABI_VERSION 1
+
+enum {
+  CEEUS_OK = 0,
+  CEEUS_ERR_INVALID = -1, /* bad argument / unsupported configuration */
+  CEEUS_ERR_CUDA = -2,    /* a CUDA runtime call failed */
+  CEEUS_ERR_STATE = -3,   /* call order violated (e.g. plan before set_weights) */
+};
+
+enum { CEEUS_MODEL_GNN = 0, CEEUS_MODEL_MLP = 1 };
+enum { CEEUS_ACT_NONE = 0, CEEUS_ACT_RELU = 1, CEEUS_ACT_SILU = 2, CEEUS_ACT_TANH = 3 };
+/* arithmetic of the rollout GEMMs: fp32 FMA (parity 1e-5) or tcgen05 tensor cores with 10-bit-mantissa
+ * operands and fp32 accumulation (parity 1e-3). */
+enum { CEEUS_PREC_FP32 = 0, CEEUS_PREC_TC = 1 };
+enum { CEEUS_ENV_NONE = 0, CEEUS_ENV_CONSTRUCTION = 1, CEEUS_ENV_PLAYGROUND = 2 };
+/* construction cost branches, fpp_construction_env.py:475-508 */
+enum { CEEUS_CASE_TOWER = 0 /* "*tower*" and "Pyramid" */, CEEUS_CASE_PICKANDPLACE = 1 /* every other non Flip/Slide case */ };
+enum { CEEUS_COST_SUM = 0, CEEUS_COST_BEST = 1 }; /* cost_along_trajectory */
+
+typedef struct CeeusConfig {
+  int32_t abi_version; /* = CEEUS_ABI_VERSION */
+  /* ---- dynamics model ---- */
+  int32_t model_kind;    /* CEEUS_MODEL_* */
+  int32_t ensemble_size; /* E */
+  int32_t n_obj;         /* N (GNN: >= 2) */
+  int32_t agent_dim;     /* A */
+  int32_t dyn_dim;       /* D */
+  int32_t stat_dim;      /* S */
+  int32_t action_dim;    /* U */
+  int32_t goal_dim;      /* G; observation = [agent | N x dyn | N x stat | goal] */
+  int32_t hidden_dim;    /* Hd */
+  int32_t num_layers;    /* hidden layers per MLP (GNN: 2, dense MLP: 3) */
+  int32_t act_fn;        /* CEEUS_ACT_* */
+  int32_t layer_norm;    /* 0/1 */
+  int32_t aggr_mean;     /* 1 = mean aggregation, 0 = sum */
+  int32_t precision;     /* CEEUS_PREC_* */
+  /* ---- iCEM planner (yaml controller_params / action_sampler_params) ---- */
+  int32_t num_envs;      /* independent planning problems batched together (1 for the reference semantics) */
+  int32_t num_traj;      /* P: trajectories per env simulated on THIS rank */
+  int32_t horizon;       /* H */
+  int32_t opt_iterations;
+  int32_t num_elites;    /* min(elites_size, P_total / 2), >= 2 */
+  int32_t num_kept;      /* int(num_elites * fraction_elites_reused) */
+  int32_t relative_init;
+  int32_t use_mean_actions;
+  int32_t keep_previous_elites;
+  int32_t shift_elites_over_time;
+  int32_t execute_best_elite;
+  int32_t use_ensemble_cost_std;
+  int32_t colored_noise;
+  int32_t cost_along_trajectory; /* CEEUS_COST_* */
+  int32_t curiosity;             /* 1: TorchCuriosityMpcICem (ensemble disagreement), 0: TorchMpcICem (task cost) */
+  int32_t extrinsic_reward;      /* curiosity only: add extrinsic_scale * env cost */
+  float alpha;
+  float init_std;
+  float noise_beta;
+  float extrinsic_scale;
+  /* ---- task cost ---- */
+  int32_t env_kind;      /* CEEUS_ENV_* */
+  int32_t cost_case;     /* CEEUS_CASE_* (construction) */
+  int32_t sparse;
+  int32_t shaped_reward;
+  float threshold;
+  float buffer_threshold;
+  /* ---- multi GPU: trajectories are sharded, rank r owns global indices [r*P, (r+1)*P) of every env ---- */
+  int32_t world_size;
+  int32_t rank;
+  uint64_t seed;         /* Philox key of the on-device noise sampler */
+} CeeusConfig;
+
+/* Caller-owned device buffers the planner reads and writes (bound once, may be rebound). Shapes use
+ * P = num_traj, Pk = P_total_pop = P*world_size + num_kept (population incl. kept elites), k = num_elites,
+ * nE = num_envs, O = A + N(D+S) + G.  The reference attributes they mirror are given on the right. */
+typedef struct CeeusBuffers {
+  float* mean;            /* [nE,H,U]            TorchMpcICem.mean_ */
+  float* std;             /* [nE,H,U]            TorchMpcICem.std_ */
+  float* actions;         /* [nE*P,H,U]          action_sequences of the current iteration (this rank) */
+  float* traj;            /* [H+1,E,nE*P,O]      traj[:-1] = observations, traj[1:] = next_observations */
+  float* costs_per_model; /* [nE,P,E]            costs_per_model_ (this rank's fresh samples) */
+  float* costs;           /* [nE,P]              costs_ (this rank's fresh samples) */
+  float* elite_actions;   /* [nE,k,H,U]          elite_samples["actions"][:,0] */
+  float* elite_costs;     /* [nE,k]              costs_ of the elites, ascending */
+  float* elite_cpm;       /* [nE,k,E]            costs_per_model_ of the elites */
+  int32_t* elite_idx;     /* [nE,k]              index into the global population of the last iteration */
+  float* cand;            /* [nE,k,rec]          this rank's top-k candidate records, rec = ceeus_cand_record_len() */
+  float* action_out;      /* [nE,U]              executed action */
+} CeeusBuffers;
+
+typedef struct CeeusHandle_t* CeeusHandle;
+
+int ceeus_abi_version(void);
+const char* ceeus_last_error(CeeusHandle h); /* h may be NULL: error of the last failed ceeus_create */
+int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out);
+void ceeus_destroy(CeeusHandle h);
+
+/* number of float32 tensors ceeus_set_weights expects and, for i in [0,n), their (rows, cols) per member:
+ * GNN order: for mlp in (edge, node, global): for l in 0..L: weight[in,out], bias[1,out], then if l<L and
+ * layer_norm: gamma[1,out], beta[1,out].  Dense MLP: for l in 0..L: weight, bias (+ gamma, beta). */
+int ceeus_num_weight_tensors(CeeusHandle h);
+int ceeus_weight_tensor_shape(CeeusHandle h, int i, int32_t* rows, int32_t* cols);
+/* dev_ptrs[i] -> contiguous float32 [E, rows_i, cols_i] in device memory (the reference's x @ W layout).
+ * The library repacks into its own resident layout; pointers are not retained. */
+int ceeus_set_weights(CeeusHandle h, const float* const* dev_ptrs, int n, void* stream);
+/* host array: for each normaliser group, mean[dim] then std[dim].
+ * GNN groups: in_agent(A) in_dyn(D) in_stat(S) in_action(U) out_agent(A) out_dyn(D); MLP: in(sd+U) out(sd). */
+int ceeus_set_normalizers(CeeusHandle h, const float* host, int n_floats);
+int ceeus_set_action_bounds(CeeusHandle h, const float* low_host, const float* high_host);
+int ceeus_set_goal(CeeusHandle h, const float* goal_host /* [nE,G] */);
+int ceeus_bind_buffers(CeeusHandle h, const CeeusBuffers* bufs);
+int ceeus_cand_record_len(CeeusHandle h); /* floats per candidate record: 2 + E + H*U */
+
+/* ---- stand-alone stages (predict_n_steps / trajectory_cost_fn / sample_action_sequences) ---- */
+/* start_obs_dev [n_start,O] (n_start = 1 broadcast per env block, or = num_traj_total one per trajectory),
+ * actions_dev [n,H,U], traj_dev [H+1,E,n,O]; trajectories [i*n/nE,(i+1)*n/nE) use goal i. */
+int ceeus_rollout(CeeusHandle h, const float* start_obs_dev, int n_start, const float* actions_dev, int n,
+                  float* traj_dev, void* stream);
+/* traj_dev [H+1,E,n,O] -> costs_per_model_dev [n,E], costs_dev [n] (ensemble mean (+ std)). */
+int ceeus_costs(CeeusHandle h, const float* traj_dev, int n, float* costs_per_model_dev, float* costs_dev,
+                void* stream);
+/* actions_dev [n,H,U] = clip(y*std + mean, low, high), row r uses mean/std of env r / (n/nE).
+ * noise_dev != NULL: y = noise_dev [n,U,H] (the torch_powerlaw_psd_gaussian boundary);
+ * else y is drawn on device: Philox4x32-10(seed; stream, global row = first_row + r) -> Box-Muller -> irDFT.
+ * If gauss_dev != NULL it receives/provides the standard normals [n,U,2F] (testing hook: write_gauss=1 stores the
+ * drawn normals, write_gauss=0 uses them instead of Philox). */
+int ceeus_sample(CeeusHandle h, const float* mean_dev, const float* std_dev, const float* noise_dev,
+                 float* gauss_dev, int write_gauss, uint32_t stream_id, int64_t first_row, int n,
+                 float* actions_dev, void* stream);
+
+/* ---- planner ---- */
+int ceeus_begin_rollout(CeeusHandle h, void* stream);
+/* One iCEM iteration on this rank: sample (+ mean-action / shifted-elite insertion), rollout, costs, local top-k
+ * into bufs.cand.  obs_dev [nE,O].  noise_dev: NULL (device RNG) or [nE*P,U,H]; shift_noise_dev: NULL or [nE*n_kept,U,H]
+ * (only read in iteration 0 when elites are shifted over time). */
+int ceeus_plan_iter_local(CeeusHandle h, int iter, const float* obs_dev, const float* noise_dev,
+                          const float* shift_noise_dev, void* stream);
+/* Merge candidate records of all ranks (cand_all_dev [world,nE,k,rec]; world=1: pass bufs.cand) with the kept elites,
+ * select the global top-k (ties: lower global index first), refit mean/std. Identical result on every rank. */
+int ceeus_plan_iter_update(CeeusHandle h, int iter, const float* cand_all_dev, void* stream);
+/* executed action -> bufs.action_out, shift mean by one step, reset std. */
+int ceeus_plan_finish(CeeusHandle h, void* stream);
+/* Whole MPC step on one GPU: H2D obs, opt_iterations x (local, update), finish, D2H action (synchronises `stream`).
+ * noise_host_or_null: concatenation in the reference's draw order: iter0 [nE*P,U,H], shift [nE*n_kept,U,H] (only if
+ * elites are being shifted), iter1, iter2, ... ; NULL = device RNG. */
+int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, const float* noise_dev_or_null,
+                    void* stream);
+/* counters for bench.py: kernels launched by this handle since creation */
+int64_t ceeus_kernel_launches(CeeusHandle h);
+/* 1 once elites from a previous MPC step exist (controls whether shift noise is consumed) */
+int ceeus_has_elites(CeeusHandle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CEEUS_B200_H */

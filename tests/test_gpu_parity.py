@@ -1,0 +1,169 @@
+"""GPU (B200): the CUDA path, called through the drop-in classes -> C ABI, against
+  (1) the fixtures the REFERENCE produced (tests/golden), and
+  (2) the CPU oracle on fresh seeded inputs,
+with the fp32-mode bar of BASELINE.json: states / costs within 1e-5 relative, elite indices exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import icem_oracle as orc
+from cases import CASES
+from helpers import (GOLD, SeededNoise, build_inputs, oracle_model, oracle_params, product_controller, product_env,
+                     product_model, rel_err, rollout_actions, step_noise)
+
+pytestmark = pytest.mark.gpu
+TOL_FP32 = 1e-5  # BASELINE.json north_star: "1e-5 in fp32 mode" (relative, denominators floored at 1e-3)
+DEV = "cuda:0"
+
+
+class _Policy:  # OpenLoopPolicy stand-in (abstract_controller.py:178-220): carries action_sequences [P,H,U]
+    def __init__(self, a):
+        self.action_sequences = a
+
+
+@pytest.mark.parametrize("name", [k for k, c in CASES.items() if c["kind"] == "rollout"])
+def test_rollout_matches_reference_fixture(name):
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    model = product_model(c, env, weights, norms)
+    acts = torch.from_numpy(rollout_actions(c, spec)).to(DEV)
+    start = torch.from_numpy(obs).view(1, -1).expand(c["P"], -1).contiguous().to(DEV)
+    buf, _ = model.predict_n_steps(start_observations=start, start_states=[None] * c["P"], policy=_Policy(acts),
+                                   horizon=c["H"])
+    nxt = buf.as_array("next_observations").cpu().numpy()
+    assert nxt.shape == g["next_observations"].shape
+    assert rel_err(nxt, g["next_observations"]) < TOL_FP32
+    np.testing.assert_array_equal(buf.as_array("observations")[:, :, 0].cpu().numpy(), g["first_observation"])
+    assert tuple(buf.as_array("actions").shape) == (c["P"], 5, c["H"], spec.action_dim)
+    # costs on the device from the same trajectories
+    eng = model._rollout_engine(c["P"], c["H"])
+    traj = eng.traj_
+    bonus = g["disagreement_bonus"]  # [P,H]
+    cpm, costs = eng.costs(traj)  # engine default: curiosity, "sum"
+    want = -bonus.sum(-1)
+    assert rel_err(cpm.cpu().numpy(), np.repeat(want[:, None], 5, 1)) < 5e-5
+    assert rel_err(costs.cpu().numpy(), want) < 5e-5
+
+
+@pytest.mark.parametrize("name", [k for k, c in CASES.items() if c["kind"] == "rollout"])
+@pytest.mark.parametrize("mode", ["task_sum", "task_best", "extr_best"])
+def test_task_costs_match_reference_fixture(name, mode):
+    import ceeus_b200
+
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    model = product_model(c, env, weights, norms)
+    eng = ceeus_b200.Engine(horizon=c["H"], num_traj=c["P"], curiosity=mode.startswith("extr"),
+                            extrinsic_reward=mode.startswith("extr"), extrinsic_reward_scale=0.7,
+                            cost_along_trajectory="best" if mode.endswith("best") else "sum", **model.engine_kwargs())
+    model.push_to(eng)
+    eng.set_goal(goal)
+    acts = torch.from_numpy(rollout_actions(c, spec)).to(DEV)
+    start = torch.from_numpy(obs).view(1, -1).to(DEV)
+    traj = eng.rollout(start, acts)
+    cpm, costs = eng.costs(traj)
+    envc = g["env_cost"].astype(np.float32)  # [P,E,H]
+    path = envc if mode.startswith("task") else (-g["disagreement_bonus"][:, None, :] + np.float32(0.7) * envc)
+    want = path[..., 1:].min(-1) if mode.endswith("best") else path.sum(-1)
+    assert rel_err(cpm.cpu().numpy(), want) < 5e-5
+    assert rel_err(costs.cpu().numpy(), want.mean(-1)) < 5e-5
+
+
+@pytest.mark.parametrize("name", [k for k, c in CASES.items() if c["kind"] == "mpc"])
+def test_mpc_steps_match_reference_fixture(name):
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    model = product_model(c, env, weights, norms)
+    ctrl = product_controller(c, env, model)
+    noise = SeededNoise(c["nseed"], 3.5)
+    ctrl.beginning_of_rollout(observation=g["s0_obs"], state=None, mode="train")
+    e = ctrl.engine
+    n_iter = ctrl.opt_iter
+    for s in range(c["steps"]):
+        flat, _ = step_noise(noise, c, spec, e.has_elites(), e.n_kept, DEV)
+        a = ctrl.get_action(g[f"s{s}_obs"], None, noise=flat)
+        i = n_iter - 1  # state after the last iteration is observable from outside
+        np.testing.assert_array_equal(e.elite_idx_[0].cpu().numpy(), g[f"s{s}_i{i}_elite_idx"])
+        k = e.k
+        want_costs = np.sort(g[f"s{s}_i{i}_costs"], kind="stable")[:k]
+        assert rel_err(e.elite_costs_[0].cpu().numpy(), want_costs) < 5e-5
+        assert rel_err(e.elite_actions_[0].cpu().numpy(), g[f"s{s}_i{i}_elite_actions"]) < TOL_FP32
+        P = c["P"]
+        assert rel_err(ctrl.costs_.cpu().numpy(), g[f"s{s}_i{i}_costs"][:P]) < 5e-5
+        np.testing.assert_allclose(a, g[f"s{s}_action"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ctrl.mean_.cpu().numpy(), g[f"s{s}_mean_after"], rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("env_kind,n_obj,model,hidden,P,H", [
+    ("construction", 2, "gnn", 128, 300, 12), ("construction", 4, "gnn", 128, 130, 7),
+    ("construction", 6, "gnn", 128, 77, 9), ("construction", 3, "gnn", 64, 64, 5),
+    ("playground", 4, "gnn", 64, 200, 10), ("playground", 2, "gnn", 128, 33, 4),
+    ("construction", 4, "mlp", 256, 257, 8), ("construction", 2, "mlp", 128, 70, 6)])
+def test_rollout_matches_oracle_fresh_inputs(env_kind, n_obj, model, hidden, P, H):
+    """Ragged sizes (P not a multiple of any tile), every supported N / hidden width, non-identity normalisers."""
+    c = dict(kind="rollout", env=env_kind, n_obj=n_obj, model=model, hidden=hidden, layers=2 if model == "gnn" else 3,
+             P=P, H=H, wseed=1000 + n_obj + hidden, identity_norm=False, running=False, oseed=77 + P)
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    pm = product_model(c, env, weights, norms)
+    om = oracle_model(c, spec, weights, norms)
+    acts = rollout_actions(c, spec)
+    rs = np.random.RandomState(5)
+    starts = np.tile(obs, (P, 1))
+    starts[:, :spec.state_dim] += (0.05 * rs.standard_normal((P, spec.state_dim))).astype(np.float32)
+    want = orc.rollout(om, torch.from_numpy(starts), torch.from_numpy(acts), torch.from_numpy(goal)).numpy()
+    buf, _ = pm.predict_n_steps(start_observations=torch.from_numpy(starts).to(DEV), start_states=None,
+                                policy=_Policy(torch.from_numpy(acts).to(DEV)), horizon=H)
+    got = pm._rollout_engine(P, H).traj_.cpu().numpy()
+    assert got.shape == want.shape
+    assert rel_err(got, want) < TOL_FP32
+
+
+def test_predict_single_step_matches_oracle():
+    c = CASES["rollout_gnn_pg4"]
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    pm, om = product_model(c, env, weights, norms), oracle_model(c, spec, weights, norms)
+    rs = np.random.RandomState(0)
+    E, B = 5, 6
+    o = np.tile(obs, (E, B, 1)) + (0.05 * rs.standard_normal((E, B, spec.obs_dim))).astype(np.float32)
+    o[..., spec.state_dim:] = goal
+    a = rs.uniform(-1, 1, (E, B, spec.action_dim)).astype(np.float32)
+    nxt, _, _ = pm.predict(observations=torch.from_numpy(o), states=None, actions=torch.from_numpy(a))
+    want = om.predict(torch.from_numpy(o[..., :spec.state_dim]), torch.from_numpy(a)).numpy()
+    assert rel_err(nxt[..., :spec.state_dim].cpu().numpy(), want) < TOL_FP32
+    np.testing.assert_array_equal(nxt[..., spec.state_dim:].cpu().numpy(), np.broadcast_to(goal, (E, B, goal.size)))
+
+
+def test_mpc_matches_oracle_larger_population():
+    """P = 1024, H = 30 (config-2 model, a quarter of its population): 2 MPC steps against the oracle."""
+    c = dict(kind="mpc", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=1024, H=30, wseed=5,
+             identity_norm=True, running=False, oseed=1, nseed=9, steps=2, curiosity=True, cost="sum", sampler={})
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    ctrl = product_controller(c, env, product_model(c, env, weights, norms))
+    noise = SeededNoise(c["nseed"], 3.5)
+    feed = {}
+    oc = orc.ICEMOracle(oracle_model(c, spec, weights, norms), oracle_params(c), lambda size: feed["replay"](size))
+    oc.set_goal(goal)
+    oc.beginning_of_rollout()
+    ctrl.beginning_of_rollout(observation=obs, state=None, mode="train")
+    e = ctrl.engine
+    for s in range(c["steps"]):
+        flat, feed["replay"] = step_noise(noise, c, spec, e.has_elites(), e.n_kept, DEV)
+        a = ctrl.get_action(obs, None, noise=flat)
+        want = oc.get_action(obs)
+        it = oc.trace[-1]["iters"][-1]
+        np.testing.assert_array_equal(e.elite_idx_[0].cpu().numpy(), it["elite_idx"].numpy())
+        assert rel_err(ctrl.costs_.cpu().numpy(), it["costs"].numpy()[: c["P"]]) < 5e-5
+        np.testing.assert_allclose(a, want, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ctrl.mean_.cpu().numpy(), oc.mean_.numpy(), rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(ctrl.std_.cpu().numpy(), oc.std_.numpy(), rtol=1e-5, atol=2e-6)
