@@ -96,5 +96,21 @@ def step_noise(noise_fn, c, spec, has_elites, n_kept, device):
 
 
 def rel_err(a, b):
+    """Relative error used by the parity bars (1e-5 fp32 mode, 1e-3 tensor-core mode): the worse of
+      * rel-L2 of the whole tensor, and
+      * max_i |a_i - b_i| / (|b_i| + s_i), s_i = largest magnitude the same feature takes anywhere in b
+        (last axis = feature for tensors with >= 3 axes, the whole tensor otherwise).
+    An element-wise ratio without s_i is meaningless for features that pass through zero (velocities, deltas):
+    fp32 rounding of state + delta is relative to the state's magnitude, not the element's."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-3)))
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if b.size == 0:
+        return 0.0
+    if b.ndim >= 3:
+        scale = np.max(np.abs(b).reshape(-1, b.shape[-1]), axis=0)
+    else:
+        scale = np.max(np.abs(b))
+    scale = np.maximum(scale, 1e-30)
+    elem = float(np.max(np.abs(a - b) / (np.abs(b) + scale)))
+    l2 = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+    return max(elem, l2)
