@@ -1,0 +1,136 @@
+// Self-test of the tcgen05 building blocks the tensor-core rollout kernel is made of: one D = A * B^T tile with the
+// same shared-memory layout, descriptors, TMEM access pattern, commit/mbarrier protocol (1-CTA and 2-CTA pair).
+// Exposed through the C ABI as ceeus_selftest_umma so the GPU tests can pin every piece against a plain GEMM.
+#include <cuda_fp16.h>
+
+#include <string>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ceeus {
+namespace {
+
+using namespace tc;
+
+// A [rows_total][K] fp16 row-major, Bt [N][K] fp16 row-major (= W^T), D [rows_total][N] fp32.
+// CG = 1: one CTA, rows_total = 128.  CG = 2: cluster of 2, rows_total = 256, each CTA holds half of the N rows of Bt.
+template <int CG>
+__global__ void __launch_bounds__(160, 1) umma_probe_kernel(const __half* __restrict__ A, const __half* __restrict__ Bt,
+                                                            float* __restrict__ D, int K, int N, int variant, int* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  const int nloc = N / CG;           // B rows held by this CTA
+  const int kc = K / 8;              // 16-byte K chunks
+  uint8_t* sA = smem;                // [kc][128][16B]
+  uint8_t* sB = sA + (size_t)kc * 128 * 16;  // [kc][nloc][16B]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + (size_t)kc * nloc * 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+
+  for (int idx = tid; idx < 128 * kc; idx += blockDim.x) {
+    const int r = idx % 128, c = idx / 128;
+    *reinterpret_cast<uint4*>(sA + (size_t)c * 2048 + r * 16) =
+        *reinterpret_cast<const uint4*>(A + (size_t)(rank * 128 + r) * K + c * 8);
+  }
+  for (int idx = tid; idx < nloc * kc; idx += blockDim.x) {
+    const int n = idx % nloc, c = idx / nloc;
+    *reinterpret_cast<uint4*>(sB + (size_t)c * nloc * 16 + n * 16) =
+        *reinterpret_cast<const uint4*>(Bt + (size_t)(rank * nloc + n) * K + c * 8);
+  }
+  fence_proxy_async();
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<CG>(tmem_slot, ncols);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4 && lane == 0 && rank == 0) {
+    uint32_t lbo_a = 2048, sbo_a = 128, lbo_b = nloc * 16, sbo_b = 128;
+    if (variant & 1) {
+      uint32_t t = lbo_a; lbo_a = sbo_a; sbo_a = t;
+      t = lbo_b; lbo_b = sbo_b; sbo_b = t;
+    }
+    const uint32_t idesc = make_idesc_f16(128 * CG, N);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint64_t da = make_smem_desc(smem_u32(sA) + ks * 2 * 2048, lbo_a, sbo_a);
+      const uint64_t db = make_smem_desc(smem_u32(sB) + ks * 2 * nloc * 16, lbo_b, sbo_b);
+      umma_f16_ss<CG>(tmem_base, da, db, idesc, ks > 0 ? 1u : 0u);
+    }
+    if (CG == 1) umma_commit_cg1(bar);
+    else umma_commit_cg2_mc(bar, 0x3);
+  }
+  if (warp < 4) {
+    const bool ok = mbar_wait(bar, 0, status, 100 + (int)rank);
+    tc_fence_after();
+    if (ok) {
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tmem_wait_ld();
+        float* out = D + (size_t)(rank * 128 + warp * 32 + lane) * N + c0;
+        for (int j = 0; j < 32 && c0 + j < N; ++j) out[j] = __uint_as_float(v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync();
+  if (warp == 4) tmem_dealloc<CG>(tmem_base, ncols);
+}
+
+}  // namespace
+}  // namespace ceeus
+
+extern "C" int ceeus_selftest_umma(int cta_group, const void* a_dev, const void* bt_dev, float* d_dev, int K, int N,
+                                   int variant, int* status_host) {
+  using namespace ceeus;
+  if (!a_dev || !bt_dev || !d_dev || !status_host) return CEEUS_ERR_INVALID;
+  if ((cta_group != 1 && cta_group != 2) || K % 16 != 0 || K < 16 || K > 256 || N % 16 != 0 || N < 16 || N > 256)
+    return CEEUS_ERR_INVALID;
+  int* d_status = nullptr;
+  if (cudaMalloc(&d_status, sizeof(int)) != cudaSuccess) return CEEUS_ERR_CUDA;
+  cudaMemset(d_status, 0, sizeof(int));
+  const size_t smem = (size_t)(K / 8) * 128 * 16 + (size_t)(K / 8) * (N / cta_group) * 16 + 64;
+  cudaError_t e;
+  if (cta_group == 1) {
+    e = cudaFuncSetAttribute(umma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      umma_probe_kernel<1><<<1, 160, smem>>>((const __half*)a_dev, (const __half*)bt_dev, d_dev, K, N, variant, d_status);
+      e = cudaGetLastError();
+    }
+  } else {
+    e = cudaFuncSetAttribute(umma_probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2);
+      cfg.blockDim = dim3(160);
+      cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, umma_probe_kernel<2>, (const __half*)a_dev, (const __half*)bt_dev, d_dev, K, N, variant, d_status);
+    }
+  }
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  int st = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&st, d_status, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_status);
+  *status_host = e == cudaSuccess ? st : -(int)e;
+  return e == cudaSuccess ? CEEUS_OK : CEEUS_ERR_CUDA;
+}

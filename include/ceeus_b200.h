@@ -192,6 +192,12 @@ int64_t ceeus_kernel_launches(CeeusHandle h);
 /* 1 once elites from a previous MPC step exist (controls whether shift noise is consumed) */
 int ceeus_has_elites(CeeusHandle h);
 
+/* Diagnostic: one D[128*cta_group, N] = A[.,K] * Bt[N,K]^T tile (fp16 in, fp32 out) through exactly the tcgen05 / TMEM /
+ * mbarrier building blocks of the CEEUS_PREC_TC rollout kernel (cta_group 1 = single CTA, 2 = CTA pair).  Synchronous.
+ * status_host: 0 ok, >0 a bounded barrier wait expired, <0 CUDA error.  No reference counterpart (test hook). */
+int ceeus_selftest_umma(int cta_group, const void* a_dev, const void* bt_dev, float* d_dev, int K, int N, int variant,
+                        int* status_host);
+
 #ifdef __cplusplus
 }
 #endif
