@@ -35,6 +35,10 @@ struct CeeusHandle_t {
   float* h_obs = nullptr;     // pinned staging
   float* h_action = nullptr;  // pinned staging
   int norm_floats = 0;
+  TcLayout tc{};             // CEEUS_PREC_TC only
+  uint8_t* d_wimg = nullptr;
+  float* d_wpar = nullptr;
+  int* d_tc_err = nullptr;
   CeeusBuffers bufs{};
   bool bound = false, weights_set = false, norms_set = false;
   bool has_elites = false;
@@ -236,6 +240,17 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
   if (e == cudaSuccess) e = alloc(&h->d_irdft, (size_t)2 * h->F * c.horizon);
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_obs, (size_t)c.num_envs * md.O * sizeof(float));
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_action, (size_t)c.num_envs * md.U * sizeof(float));
+  if (e == cudaSuccess && c.precision == CEEUS_PREC_TC) {
+    if (c.model_kind != CEEUS_MODEL_GNN || !make_tc_layout(md, h->num_sms, &h->tc)) {
+      ceeus_destroy(h);
+      return fail(nullptr, CEEUS_ERR_INVALID,
+                  "CEEUS_PREC_TC supports the GNN ensemble with hidden_dim 64/128, 2 hidden layers, dyn/agent dim <= 16");
+    }
+    e = cudaMalloc(&h->d_wimg, (size_t)md.E * 2 * h->tc.image_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_wpar, (size_t)md.E * h->tc.par_floats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_tc_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->d_tc_err, 0, sizeof(int));
+  }
   if (e == cudaSuccess) {
     std::vector<float> M = build_irdft(c.noise_beta, c.horizon);
     e = cudaMemcpy(h->d_irdft, M.data(), M.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -258,6 +273,7 @@ void ceeus_destroy(CeeusHandle h) {
   if (!h) return;
   cudaFree(h->d_weights); cudaFree(h->d_norm); cudaFree(h->d_low); cudaFree(h->d_high);
   cudaFree(h->d_goal); cudaFree(h->d_obs); cudaFree(h->d_irdft);
+  cudaFree(h->d_wimg); cudaFree(h->d_wpar); cudaFree(h->d_tc_err);
   if (h->h_obs) cudaFreeHost(h->h_obs);
   if (h->h_action) cudaFreeHost(h->h_action);
   delete h;
@@ -280,6 +296,8 @@ int ceeus_set_weights(CeeusHandle h, const float* const* dev_ptrs, int n, void* 
     const TensorSpec& t = h->wspec[i];
     LAUNCH(h, launch_repack(dev_ptrs[i], h->d_weights, h->md.E, t.rows, t.cols, h->md.member_stride, t.dst_off, t.dst_ld, S(stream)));
   }
+  if (h->cfg.precision == CEEUS_PREC_TC)
+    LAUNCH(h, launch_tc_pack(h->d_weights, h->md, h->tc, h->d_wimg, h->d_wpar, S(stream)));
   h->weights_set = true;
   return CEEUS_OK;
 }
@@ -327,8 +345,9 @@ static int do_rollout(CeeusHandle h, const float* start_obs_dev, int traj_per_st
   ra.weights = h->d_weights; ra.norm = h->d_norm; ra.start_obs = start_obs_dev; ra.goal = h->d_goal;
   ra.actions = actions_dev; ra.traj = traj_dev; ra.n = n; ra.H = h->cfg.horizon;
   ra.traj_per_start = traj_per_start; ra.traj_per_goal = traj_per_goal;
-  if (h->cfg.precision == CEEUS_PREC_TC) return fail(h, CEEUS_ERR_INVALID, "CEEUS_PREC_TC rollout kernel is not part of this build yet");
-  if (h->md.kind == CEEUS_MODEL_GNN) LAUNCH(h, launch_rollout_gnn_simt(h->md, ra, h->num_sms, st));
+  if (h->cfg.precision == CEEUS_PREC_TC)
+    LAUNCH(h, launch_rollout_gnn_tc(h->md, ra, h->tc, h->d_wimg, h->d_wpar, h->d_tc_err, st));
+  else if (h->md.kind == CEEUS_MODEL_GNN) LAUNCH(h, launch_rollout_gnn_simt(h->md, ra, h->num_sms, st));
   else LAUNCH(h, launch_rollout_mlp_simt(h->md, ra, st));
   return CEEUS_OK;
 }
@@ -481,10 +500,22 @@ int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, co
   const size_t ab = (size_t)c.num_envs * h->md.U * sizeof(float);
   CU_CHECK(h, cudaMemcpyAsync(h->h_action, h->bufs.action_out, ab, cudaMemcpyDeviceToHost, st));
   CU_CHECK(h, cudaStreamSynchronize(st));
+  if (h->d_tc_err) {
+    const int tcs = ceeus_tc_status(h);
+    if (tcs != 0) return fail(h, CEEUS_ERR_CUDA, "tensor-core rollout kernel reported protocol error " + std::to_string(tcs));
+  }
   std::memcpy(action_host, h->h_action, ab);
   return CEEUS_OK;
 }
 
 int64_t ceeus_kernel_launches(CeeusHandle h) { return h ? h->launches : 0; }
+
+int ceeus_tc_status(CeeusHandle h) {
+  if (!h) return CEEUS_ERR_INVALID;
+  if (!h->d_tc_err) return 0;
+  int st = 0;
+  if (cudaMemcpy(&st, h->d_tc_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return CEEUS_ERR_CUDA;
+  return st;
+}
 
 }  // extern "C"

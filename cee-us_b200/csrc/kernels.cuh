@@ -28,6 +28,25 @@ GnnTiling make_gnn_tiling(const ModelDesc& md);
 cudaError_t launch_rollout_gnn_simt(const ModelDesc& md, const RolloutArgs& ra, int num_sms, cudaStream_t st);
 cudaError_t launch_rollout_mlp_simt(const ModelDesc& md, const RolloutArgs& ra, cudaStream_t st);
 
+// ---- tensor-core rollout (rollout_tc.cu) ----
+struct TcMat {      // one B operand (fp16, K-major 8x16B core matrices, split by output column between the CTA pair)
+  int K, N, nloc;   // padded K, total output columns, columns held per CTA
+  int off;          // byte offset inside the per-(member, rank) weight image
+  int src_mlp, src_layer;
+  int seg_tc[2], seg_len[2], seg_src[2];  // K permutation: tile-K range [seg_tc, +len) <- source rows [seg_src, +len)
+};
+struct TcLayout {
+  int HD, KE1, KX, T_r, ppm;  // ppm: CTA pairs per ensemble member
+  TcMat mat[9];               // E1 E2 E3 N1 N2 N3 G1 G2 G3
+  int image_bytes;            // per (member, rank)
+  int par_off[9][3], par_len[9], par_floats;  // fp32 bias / gamma / beta blocks per member
+  int sm_w, sm_slot[2], sm_par, sm_state[2], sm_bar, sraw_bytes, smem_bytes;
+};
+bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out);
+cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, uint8_t* wimg, float* wpar, cudaStream_t st);
+cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
+                                  const float* wpar, int* err_flag, cudaStream_t st);
+
 // ---- iCEM kernels (icem_kernels.cu) ----
 struct SampleArgs {
   const float* mean;   // [nE,H,U]

@@ -228,5 +228,8 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ceeus_plan_finish(self.handle, _stream()), self.handle)
 
+    def tc_status(self):
+        return int(self.lib.ceeus_tc_status(self.handle))
+
     def kernel_launches(self):
         return int(self.lib.ceeus_kernel_launches(self.handle))

@@ -189,6 +189,8 @@ int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, co
                     void* stream);
 /* counters for bench.py: kernels launched by this handle since creation */
 int64_t ceeus_kernel_launches(CeeusHandle h);
+/* CEEUS_PREC_TC only: 0 = the tensor-core kernel's mbarrier protocol never timed out; synchronises the device. */
+int ceeus_tc_status(CeeusHandle h);
 /* 1 once elites from a previous MPC step exist (controls whether shift noise is consumed) */
 int ceeus_has_elites(CeeusHandle h);
 
