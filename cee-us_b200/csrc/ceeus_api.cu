@@ -39,6 +39,7 @@ struct CeeusHandle_t {
   uint8_t* d_wimg = nullptr;
   float* d_wpar = nullptr;
   int* d_tc_err = nullptr;
+  long long* d_tc_dbg = nullptr;  // optional timeline of one warpgroup (ceeus_tc_debug_timeline)
   CeeusBuffers bufs{};
   bool bound = false, weights_set = false, norms_set = false;
   bool has_elites = false;
@@ -273,7 +274,7 @@ void ceeus_destroy(CeeusHandle h) {
   if (!h) return;
   cudaFree(h->d_weights); cudaFree(h->d_norm); cudaFree(h->d_low); cudaFree(h->d_high);
   cudaFree(h->d_goal); cudaFree(h->d_obs); cudaFree(h->d_irdft);
-  cudaFree(h->d_wimg); cudaFree(h->d_wpar); cudaFree(h->d_tc_err);
+  cudaFree(h->d_wimg); cudaFree(h->d_wpar); cudaFree(h->d_tc_err); cudaFree(h->d_tc_dbg);
   if (h->h_obs) cudaFreeHost(h->h_obs);
   if (h->h_action) cudaFreeHost(h->h_action);
   delete h;
@@ -346,7 +347,7 @@ static int do_rollout(CeeusHandle h, const float* start_obs_dev, int traj_per_st
   ra.actions = actions_dev; ra.traj = traj_dev; ra.n = n; ra.H = h->cfg.horizon;
   ra.traj_per_start = traj_per_start; ra.traj_per_goal = traj_per_goal;
   if (h->cfg.precision == CEEUS_PREC_TC)
-    LAUNCH(h, launch_rollout_gnn_tc(h->md, ra, h->tc, h->d_wimg, h->d_wpar, h->d_tc_err, st));
+    LAUNCH(h, launch_rollout_gnn_tc(h->md, ra, h->tc, h->d_wimg, h->d_wpar, h->d_tc_err, h->d_tc_dbg, st));
   else if (h->md.kind == CEEUS_MODEL_GNN) LAUNCH(h, launch_rollout_gnn_simt(h->md, ra, h->num_sms, st));
   else LAUNCH(h, launch_rollout_mlp_simt(h->md, ra, st));
   return CEEUS_OK;
@@ -509,6 +510,24 @@ int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, co
 }
 
 int64_t ceeus_kernel_launches(CeeusHandle h) { return h ? h->launches : 0; }
+
+int ceeus_tc_debug_timeline(CeeusHandle h, int enable, long long* out_host, int n_pairs) {
+  if (!h || h->cfg.precision != CEEUS_PREC_TC) return CEEUS_ERR_INVALID;
+  if (enable && !h->d_tc_dbg) {
+    if (cudaMalloc(&h->d_tc_dbg, 512 * sizeof(long long)) != cudaSuccess) return CEEUS_ERR_CUDA;
+    cudaMemset(h->d_tc_dbg, 0, 512 * sizeof(long long));
+  }
+  if (out_host && h->d_tc_dbg) {
+    if (n_pairs > 256) n_pairs = 256;
+    if (cudaMemcpy(out_host, h->d_tc_dbg, (size_t)n_pairs * 2 * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+      return CEEUS_ERR_CUDA;
+  }
+  if (!enable && h->d_tc_dbg) {
+    cudaFree(h->d_tc_dbg);
+    h->d_tc_dbg = nullptr;
+  }
+  return CEEUS_OK;
+}
 
 int ceeus_tc_status(CeeusHandle h) {
   if (!h) return CEEUS_ERR_INVALID;

@@ -40,12 +40,12 @@ struct TcLayout {
   TcMat mat[9];               // E1 E2 E3 N1 N2 N3 G1 G2 G3
   int image_bytes;            // per (member, rank)
   int par_off[9][3], par_len[9], par_floats;  // fp32 bias / gamma / beta blocks per member
-  int sm_w, sm_slot[2], sm_par, sm_state[2], sm_bar, sraw_bytes, smem_bytes;
+  int sm_w, sm_slot[2], sm_par, sm_state[2], sm_rinfo, sm_bar, sraw_bytes, smem_bytes;
 };
 bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out);
 cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, uint8_t* wimg, float* wpar, cudaStream_t st);
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
-                                  const float* wpar, int* err_flag, cudaStream_t st);
+                                  const float* wpar, int* err_flag, long long* dbg, cudaStream_t st);
 
 // ---- iCEM kernels (icem_kernels.cu) ----
 struct SampleArgs {

@@ -28,7 +28,7 @@ namespace ceeus {
 namespace {
 using namespace tc;
 
-constexpr int kTcThreads = 288;  // 2 warpgroups + control warp
+constexpr int kTcThreads = 320;  // 2 epilogue warpgroups + 2 MMA-issuer warps (warp 8 also does the set-up)
 constexpr uint32_t FULL = 0xffffffffu;
 
 __device__ __forceinline__ void wg_sync(int s) { asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory"); }
@@ -54,7 +54,7 @@ struct Ctx {
 
 __device__ __forceinline__ bool wait_bar(const Ctx& cx, uint64_t* bar, uint32_t parity, int code) {
   for (uint32_t it = 0; it < (1u << 26); ++it) {
-    if (mbar_try_wait_cluster(bar, parity)) return true;
+    if (mbar_try_wait(bar, parity)) return true;
     if ((it & 1023u) == 1023u && *cx.abort) return false;
   }
   *cx.abort = 1;
@@ -88,16 +88,23 @@ __device__ __forceinline__ void finish_row(float (&x)[HD], const float* __restri
     x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
   }
   if (ln) {
-    float s = 0.f;
+    float s4[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < HD; ++j) s += x[j];
-    const float mean = s * (1.f / HD);
-    float v = 0.f;
+    for (int j = 0; j < HD; j += 8) {
 #pragma unroll
-    for (int j = 0; j < HD; ++j) {
-      x[j] -= mean;
-      v = fmaf(x[j], x[j], v);
+      for (int t = 0; t < 8; ++t) s4[t] += x[j + t];
     }
+    const float mean = (((s4[0] + s4[1]) + (s4[2] + s4[3])) + ((s4[4] + s4[5]) + (s4[6] + s4[7]))) * (1.f / HD);
+    float v4[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < HD; j += 8) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        x[j + t] -= mean;
+        v4[t] = fmaf(x[j + t], x[j + t], v4[t]);
+      }
+    }
+    const float v = ((v4[0] + v4[1]) + (v4[2] + v4[3])) + ((v4[4] + v4[5]) + (v4[6] + v4[7]));
     const float rstd = rsqrtf(v * (1.f / HD) + 1e-5f);
 #pragma unroll
     for (int j = 0; j < HD; j += 4) {
@@ -126,7 +133,7 @@ __device__ __forceinline__ void finish_row(float (&x)[HD], const float* __restri
 template <int HD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     rollout_gnn_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcLayout tl, const uint8_t* __restrict__ wimg,
-                          const float* __restrict__ wpar, int* __restrict__ err) {
+                          const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -184,57 +191,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   const int n_iter = (n_groups + 3) / 4;  // 4 workers per pair, lock-step
   const int total_stages = n_iter * ra.H * 6;
 
-  if (warp == 8) {
-    // =========================== MMA issuer (leader CTA, one thread) ===========================
+  if (warp >= 8) {
+    // =========================== MMA issuers (leader CTA): warp 8 -> slot 0, warp 9 -> slot 1 ===========================
+    // One thread per slot, each blocking on its own barrier: mbarrier.try_wait suspends the thread for a
+    // system-defined time, so a single thread polling both slots alternately stalled every stage of one slot
+    // behind the other's time-out (first version: ~10 us per stage).
     if (rank == 0 && lane == 0) {
+      const int s = warp - 8;
       const uint32_t idesc_h = make_idesc_f16(256, HD);
       const uint32_t idesc_o = make_idesc_f16(256, 16);
       const uint32_t wbase = smem_u32(sW);
-      int stage[2] = {0, 0};
-      uint32_t ph[2] = {0, 0};
-      uint32_t idle = 0;
-      auto issue = [&](uint32_t d, uint32_t a_addr, int a_chunk0, const TcMat& m, uint32_t idesc) {
+      const uint32_t a_addr = smem_u32(smem + tl.sm_slot[s]);
+      const uint32_t d0 = cx.tmem_base + (uint32_t)(s * 2 * HD);
+      const uint32_t d1 = d0 + HD;
+      auto issue = [&](uint32_t d, const TcMat& m, uint32_t idesc) {
         const uint32_t lbo_b = (uint32_t)m.nloc * 16;
 #pragma unroll 1
         for (int ks = 0; ks < m.K / 16; ++ks) {
-          const uint64_t da = make_smem_desc(a_addr + (uint32_t)(a_chunk0 + 2 * ks) * 2048, 2048, 128);
+          const uint64_t da = make_smem_desc(a_addr + (uint32_t)(2 * ks) * 2048, 2048, 128);
           const uint64_t db = make_smem_desc(wbase + (uint32_t)m.off + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
           umma_f16_ss<2>(d, da, db, idesc, ks > 0 ? 1u : 0u);
         }
       };
-      while (stage[0] < total_stages || stage[1] < total_stages) {
-        bool progressed = false;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (stage[s] >= total_stages) continue;
-          if (!mbar_try_wait_cluster(&a_ready[s], ph[s])) continue;
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + tl.sm_slot[s]);
-          const uint32_t d0 = cx.tmem_base + (uint32_t)(s * 2 * HD);
-          const uint32_t d1 = d0 + HD;
-          switch (stage[s] % 6) {
-            case 0: issue(d0, a_addr, 0, tl.mat[0], idesc_h); break;
-            case 1: issue(d0, a_addr, 0, tl.mat[1], idesc_h); break;
-            case 2: issue(d0, a_addr, 0, tl.mat[2], idesc_h); break;
-            case 3: issue(d0, a_addr, 0, tl.mat[3], idesc_h); issue(d1, a_addr, 0, tl.mat[6], idesc_h); break;
-            case 4: issue(d0, a_addr, 0, tl.mat[4], idesc_h); issue(d1, a_addr, 0, tl.mat[7], idesc_h); break;
-            default: issue(d0, a_addr, 0, tl.mat[5], idesc_o); issue(d1, a_addr, 0, tl.mat[8], idesc_o); break;
-          }
-          umma_commit_cg2_mc(&d_ready[s], 0x3);
-          stage[s] += 1;
-          ph[s] ^= 1u;
-          progressed = true;
+      uint32_t ph = 0;
+#pragma unroll 1
+      for (int stage = 0; stage < total_stages; ++stage) {
+        if (!wait_bar(cx, &a_ready[s], ph, 2)) break;
+        ph ^= 1u;
+        tc_fence_after();
+        switch (stage % 6) {
+          case 0: issue(d0, tl.mat[0], idesc_h); break;
+          case 1: issue(d0, tl.mat[1], idesc_h); break;
+          case 2: issue(d0, tl.mat[2], idesc_h); break;
+          case 3: issue(d0, tl.mat[3], idesc_h); issue(d1, tl.mat[6], idesc_h); break;
+          case 4: issue(d0, tl.mat[4], idesc_h); issue(d1, tl.mat[7], idesc_h); break;
+          default: issue(d0, tl.mat[5], idesc_o); issue(d1, tl.mat[8], idesc_o); break;
         }
-        if (progressed) {
-          idle = 0;
-        } else if (++idle > (1u << 26) || ((idle & 1023u) == 0 && *abort_flag)) {
-          *abort_flag = 1;
-          atomicExch(err, 2);
-          break;
-        }
+        umma_commit_cg2_mc(&d_ready[s], 0x3);
       }
     }
-  } else {
+  } else if (warp < 8) {
     // =========================== warpgroup: tile builder + epilogue ===========================
     const int s = warp >> 2;       // slot
     const int q = warp & 3;        // TMEM lane quadrant
@@ -252,6 +248,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     const uint32_t tm_row = cx.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 2 * HD);
     uint32_t dph = 0;
     auto par = [&](int m, int which) { return sPar + tl.par_off[m][which]; };
+    // combined row r = b*(N+1)+i  ->  (first message row, number of messages): node i<N: its N-1 outgoing edges,
+    // i==N (global row): all N(N-1) edges of trajectory b
+    int dbg_n = 0;
+    const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    auto stamp = [&](int tag) {
+      if (dbg_on && dbg_n < 250) { dbg[2 * dbg_n] = tag; dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
+    };
+    int2* rinfo = reinterpret_cast<int2*>(smem + tl.sm_rinfo) + s * 128;
+    {
+      const int b = row / N1, i = row % N1;
+      rinfo[row] = make_int2(b * NE + (i < N ? i * (N - 1) : 0), i < N ? N - 1 : NE);
+    }
 
     for (int it = 0; it < n_iter; ++it) {
       const int g = it * 4 + worker;
@@ -271,6 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       wg_sync(s);
 
       for (int h = 0; h < ra.H; ++h) {
+        stamp(100);
         // ---- normalise state + action (gnn_ensemble.py:190-243) -> fp16 ----
         for (int idx = row; idx < Gc * SN; idx += 128) {
           const int b = idx / SN, c = idx % SN;
@@ -292,6 +301,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
           snrm[idx] = __float2half_rn(v);
         }
         wg_sync(s);
+        stamp(101);
         // ---- edge tile, layer-1 input [x_i | x_j | agent | action | 0] (gnn_modules.py:194-211) ----
         if (row < rows_e) {
           const int b = row / NE, qq = row % NE;
@@ -313,160 +323,153 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
             *reinterpret_cast<uint4*>(tile + (size_t)c * 2048 + row * 16) = *reinterpret_cast<const uint4*>(tmp);
           }
         }
+        stamp(102);
         signal_a(cx, s, lane);
+        stamp(103);
 
-        // ---- edge MLP: two hidden layers, output layer -> messages (fp16) at chunks [KXc, KXc + HD/8) ----
-        const bool warp_live_e = q * 32 < rows_e;
-#pragma unroll 1
-        for (int l = 0; l < 3; ++l) {
-          wait_bar(cx, &d_ready[s], dph, 10 + l);
-          dph ^= 1u;
-          tc_fence_after();
-          if (warp_live_e) {
-            float x[HD];
-            load_acc<HD>(tm_row, x);
-            tmem_wait_ld();
-            if (l < 2) finish_row<HD>(x, par(l, 0), par(l, 1), par(l, 2), ln, act, tile, 0, row, row < rows_e);
-            else finish_row<HD>(x, par(2, 0), nullptr, nullptr, false, CEEUS_ACT_NONE, tile, KXc, row, row < rows_e);
-          }
-          if (l < 2) signal_a(cx, s, lane);
-        }
-        // ---- aggregation (models/utils.py:42-51): read every message chunk this thread needs, then write ----
-        tc_fence_before();
-        wg_sync(s);
-        {
-          constexpr int CH = HD / 8;
-          constexpr int MAXI = CH;  // rows_c <= 128  =>  rows_c * CH / 128 <= CH items per thread
-          uint4 out[MAXI];
-          const int n_items = rows_c * CH;
-#pragma unroll
-          for (int t = 0; t < MAXI; ++t) {
-            const int item = row + t * 128;
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (item < n_items) {
-              const int c = item / rows_c, r = item % rows_c;
-              const int b = r / N1, i = r % N1;
-              const int first = b * NE + (i < N ? i * (N - 1) : 0);
-              const int cnt = i < N ? N - 1 : NE;
-              const uint8_t* src = tile + (size_t)(KXc + c) * 2048 + (size_t)first * 16;
-              for (int e2 = 0; e2 < cnt; ++e2) {
-                const uint4 m = *reinterpret_cast<const uint4*>(src + e2 * 16);
-                const __half2* hp = reinterpret_cast<const __half2*>(&m);
-#pragma unroll
-                for (int t2 = 0; t2 < 4; ++t2) {
-                  const float2 f = __half22float2(hp[t2]);
-                  acc[2 * t2] += f.x;
-                  acc[2 * t2 + 1] += f.y;
-                }
-              }
-              const float sc = i < N ? inv_node : inv_glob;
-#pragma unroll
-              for (int t2 = 0; t2 < 8; ++t2) acc[t2] *= sc;
-            }
-            out[t].x = pack_half2(acc[0], acc[1]);
-            out[t].y = pack_half2(acc[2], acc[3]);
-            out[t].z = pack_half2(acc[4], acc[5]);
-            out[t].w = pack_half2(acc[6], acc[7]);
-          }
-          wg_sync(s);
-#pragma unroll
-          for (int t = 0; t < MAXI; ++t) {
-            const int item = row + t * 128;
-            if (item < n_items) {
-              const int c = item / rows_c, r = item % rows_c;
-              *reinterpret_cast<uint4*>(tile + (size_t)(KXc + c) * 2048 + r * 16) = out[t];
-            }
-          }
-        }
-        // ---- combined tile, [x_i | agent | action | 0] part (global rows: x_i = 0)  gnn_modules.py:213-223,250-254 ----
+        // ---- six MMA stages of this step: E1 E2 E3 (edge MLP) C1 C2 C3 (node + global MLP on the combined tile) ----
+        // One copy of the row epilogue serves all hidden stages: code size matters (the first version unrolled it five
+        // times into 350 KB of SASS and stalled on instruction fetch).
         const int cb = row / N1, ci = row % N1;
         const bool is_glob = ci == N;
-        if (row < rows_c) {
-          const __half* sb = snrm + cb * SN;
-          for (int c = 0; c < KXc; ++c) {
-            __align__(16) __half tmp[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const int k = c * 8 + t;
-              __half v = __float2half_rn(0.f);
-              if (k < NA) { if (!is_glob) v = sb[A + U + ci * NA + k]; }
-              else if (k < NA + A) v = sb[k - NA];
-              else if (k < NA + A + U) v = sb[A + (k - NA - A)];
-              tmp[t] = v;
-            }
-            *reinterpret_cast<uint4*>(tile + (size_t)c * 2048 + row * 16) = *reinterpret_cast<const uint4*>(tmp);
-          }
-        }
-        signal_a(cx, s, lane);
-
-        // ---- node MLP (rows b*(N+1)+i, i<N) and global MLP (rows b*(N+1)+N) on the same tile ----
-        const bool live = row < rows_c;
-        const bool has_n = __any_sync(FULL, live && !is_glob);
-        const bool has_g = __any_sync(FULL, live && is_glob);
-        const int mo = is_glob ? 6 : 3;  // parameter block of this row's MLP
+        const bool live_c = row < rows_c, live_e = row < rows_e;
+        const bool has_n = __any_sync(FULL, live_c && !is_glob);
+        const bool has_g = __any_sync(FULL, live_c && is_glob);
+        const bool warp_live_e = q * 32 < rows_e;
 #pragma unroll 1
-        for (int l = 0; l < 2; ++l) {
-          wait_bar(cx, &d_ready[s], dph, 20 + l);
+        for (int st = 0; st < 6; ++st) {
+          stamp(10 + st);
+          wait_bar(cx, &d_ready[s], dph, 10 + st);
           dph ^= 1u;
           tc_fence_after();
-          if (has_n || has_g) {
-            float x[HD];
-            if (has_n) load_acc<HD>(tm_row, x);
-            else load_acc<HD>(tm_row + HD, x);
-            tmem_wait_ld();
-            if (has_n && has_g) {
+          stamp(20 + st);
+          const bool cstage = st >= 3;
+          const bool warp_on = cstage ? (has_n || has_g) : warp_live_e;
+          if (st < 5) {
+            if (warp_on) {
+              float x[HD];
+              const bool from_g = cstage && !has_n;  // warp holds only global rows
+              load_acc<HD>(tm_row + (from_g ? HD : 0), x);
+              tmem_wait_ld();
+              if (cstage && has_n && has_g) {  // mixed warp: global rows take the second accumulator
 #pragma unroll
-              for (int c0 = 0; c0 < HD; c0 += 32) {
-                uint32_t t32[32];
-                tmem_ld32(tm_row + HD + c0, t32);
-                tmem_wait_ld();
+                for (int c0 = 0; c0 < HD; c0 += 32) {
+                  uint32_t t32[32];
+                  tmem_ld32(tm_row + HD + c0, t32);
+                  tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (is_glob) x[c0 + j] = __uint_as_float(t32[j]);
+                  for (int j = 0; j < 32; ++j)
+                    if (is_glob) x[c0 + j] = __uint_as_float(t32[j]);
+                }
+              }
+              const int m = cstage ? (is_glob ? 6 : 3) + (st - 3) : st;
+              const bool hidden = st != 2;
+              finish_row<HD>(x, par(m, 0), par(m, hidden ? 1 : 0), par(m, hidden ? 2 : 0), ln && hidden,
+                             hidden ? act : CEEUS_ACT_NONE, tile, st == 2 ? KXc : 0, row, cstage ? live_c : live_e);
+            }
+            stamp(30 + st);
+            if (st == 2) {
+              // ---- aggregation (models/utils.py:42-51): read every message chunk this thread needs, then write ----
+              tc_fence_before();
+              wg_sync(s);
+              constexpr int CH = HD / 8;
+              uint4 outv[CH];  // rows_c <= 128  =>  at most CH items per thread
+              const int n_items = rows_c * CH;
+              {
+                int c = 0, r = row;  // item = c * rows_c + r, advanced by 128 per slot without divisions
+                if (rows_c > 0) { c = row / rows_c; r = row % rows_c; }
+                const int dq = rows_c > 0 ? 128 / rows_c : 0, dr = rows_c > 0 ? 128 % rows_c : 0;
+#pragma unroll
+                for (int t = 0; t < CH; ++t) {
+                  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                  if (row + t * 128 < n_items) {
+                    const int2 info = rinfo[r];  // (first message row, message count) of combined row r
+                    const uint8_t* src = tile + (size_t)(KXc + c) * 2048 + (size_t)info.x * 16;
+                    for (int e2 = 0; e2 < info.y; ++e2) {
+                      const uint4 mm = *reinterpret_cast<const uint4*>(src + e2 * 16);
+                      const __half2* hp = reinterpret_cast<const __half2*>(&mm);
+#pragma unroll
+                      for (int t2 = 0; t2 < 4; ++t2) {
+                        const float2 f = __half22float2(hp[t2]);
+                        acc[2 * t2] += f.x;
+                        acc[2 * t2 + 1] += f.y;
+                      }
+                    }
+                    const float sc = info.y == NE ? inv_glob : inv_node;  // N-1 != N(N-1) for every N >= 2
+#pragma unroll
+                    for (int t2 = 0; t2 < 8; ++t2) acc[t2] *= sc;
+                  }
+                  outv[t].x = pack_half2(acc[0], acc[1]);
+                  outv[t].y = pack_half2(acc[2], acc[3]);
+                  outv[t].z = pack_half2(acc[4], acc[5]);
+                  outv[t].w = pack_half2(acc[6], acc[7]);
+                  c += dq; r += dr;
+                  if (r >= rows_c && rows_c > 0) { r -= rows_c; c += 1; }
+                }
+              }
+              wg_sync(s);
+              {
+                int c = 0, r = row;
+                if (rows_c > 0) { c = row / rows_c; r = row % rows_c; }
+                const int dq = rows_c > 0 ? 128 / rows_c : 0, dr = rows_c > 0 ? 128 % rows_c : 0;
+#pragma unroll
+                for (int t = 0; t < CH; ++t) {
+                  if (row + t * 128 < n_items) *reinterpret_cast<uint4*>(tile + (size_t)(KXc + c) * 2048 + r * 16) = outv[t];
+                  c += dq; r += dr;
+                  if (r >= rows_c && rows_c > 0) { r -= rows_c; c += 1; }
+                }
+              }
+              // ---- combined tile, [x_i | agent | action | 0] part (global rows: x_i = 0)  gnn_modules.py:213-223,250-254 ----
+              if (live_c) {
+                const __half* sb = snrm + cb * SN;
+                for (int c = 0; c < KXc; ++c) {
+                  __align__(16) __half tmp[8];
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) {
+                    const int k = c * 8 + t;
+                    __half v = __float2half_rn(0.f);
+                    if (k < NA) { if (!is_glob) v = sb[A + U + ci * NA + k]; }
+                    else if (k < NA + A) v = sb[k - NA];
+                    else if (k < NA + A + U) v = sb[A + (k - NA - A)];
+                    tmp[t] = v;
+                  }
+                  *reinterpret_cast<uint4*>(tile + (size_t)c * 2048 + row * 16) = *reinterpret_cast<const uint4*>(tmp);
+                }
               }
             }
-            finish_row<HD>(x, par(mo + l, 0), par(mo + l, 1), par(mo + l, 2), ln, act, tile, 0, row, live);
-          }
-          signal_a(cx, s, lane);
-        }
-        // ---- output layers: deltas -> de-normalise, residual update (gnn_ensemble.py:302-334, 935-939) ----
-        wait_bar(cx, &d_ready[s], dph, 30);
-        dph ^= 1u;
-        tc_fence_after();
-        if (has_n || has_g) {
-          uint32_t v[16];
-          if (has_n) tmem_ld16(tm_row, v);
-          else tmem_ld16(tm_row + HD, v);
-          tmem_wait_ld();
-          if (has_n && has_g) {
-            uint32_t w[16];
-            tmem_ld16(tm_row + HD, w);
+            stamp(40 + st);
+            signal_a(cx, s, lane);
+            stamp(50 + st);
+          } else if (warp_on) {
+            // ---- output layers: deltas -> de-normalise, residual update (gnn_ensemble.py:302-334, 935-939) ----
+            uint32_t v[16];
+            tmem_ld16(tm_row + (has_n ? 0 : HD), v);
             tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (is_glob) v[j] = w[j];
-          }
-          if (live) {
-            const float* pb = par(is_glob ? 8 : 5, 0);
-            if (is_glob) {
+            if (has_n && has_g) {
+              uint32_t w[16];
+              tmem_ld16(tm_row + HD, w);
+              tmem_wait_ld();
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (j < A) {
-                  const float dl = __uint_as_float(v[j]) + pb[j];
-                  sraw[cb * sd + j] += fmaf(__ldg(nrm + md.nrm.out_agent + A + j), dl, __ldg(nrm + md.nrm.out_agent + j));
-                }
-            } else {
+                if (is_glob) v[j] = w[j];
+            }
+            if (live_c) {
+              const float* pb = par(is_glob ? 8 : 5, 0);
+              const int nout = is_glob ? A : D;
+              const int so = is_glob ? md.nrm.out_agent : md.nrm.out_dyn;
+              float* dst = sraw + cb * sd + (is_glob ? 0 : A + ci * D);
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (j < D) {
+                if (j < nout) {
                   const float dl = __uint_as_float(v[j]) + pb[j];
-                  sraw[cb * sd + A + ci * D + j] += fmaf(__ldg(nrm + md.nrm.out_dyn + D + j), dl, __ldg(nrm + md.nrm.out_dyn + j));
+                  dst[j] += fmaf(__ldg(nrm + so + nout + j), dl, __ldg(nrm + so + j));
                 }
             }
           }
         }
         tc_fence_before();
         wg_sync(s);
+        stamp(60);
         // ---- emit traj[h+1] = [state | goal] (env.obs_postproc) ----
         {
           float* outp = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
@@ -589,6 +592,7 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out) {
   const int snrm_bytes = round_up(t.T_r * (md.A + md.U + md.N * NA) * 2, 16);
   t.sm_state[0] = sm; sm += t.sraw_bytes + snrm_bytes;
   t.sm_state[1] = sm; sm += t.sraw_bytes + snrm_bytes;
+  t.sm_rinfo = sm; sm += 2 * 128 * 8;
   t.sm_bar = sm; sm += 64;
   t.smem_bytes = sm;
   if (t.smem_bytes > 227 * 1024) return false;
@@ -606,17 +610,17 @@ cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout
 }
 
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
-                                  const float* wpar, int* err_flag, cudaStream_t st) {
+                                  const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
   cudaError_t e;
   const dim3 grid(2 * tl.ppm * md.E);
   if (md.Hd == 128) {
     e = cudaFuncSetAttribute(rollout_gnn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
     if (e != cudaSuccess) return e;
-    rollout_gnn_tc_kernel<128><<<grid, kTcThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag);
+    rollout_gnn_tc_kernel<128><<<grid, kTcThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
   } else {
     e = cudaFuncSetAttribute(rollout_gnn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
     if (e != cudaSuccess) return e;
-    rollout_gnn_tc_kernel<64><<<grid, kTcThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag);
+    rollout_gnn_tc_kernel<64><<<grid, kTcThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
   }
   return cudaGetLastError();
 }

@@ -191,6 +191,9 @@ int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, co
 int64_t ceeus_kernel_launches(CeeusHandle h);
 /* CEEUS_PREC_TC only: 0 = the tensor-core kernel's mbarrier protocol never timed out; synchronises the device. */
 int ceeus_tc_status(CeeusHandle h);
+/* CEEUS_PREC_TC profiling aid: enable=1 makes thread 0 of CTA 0 record (tag, clock64) pairs at every pipeline stage of
+ * the next rollouts; out_host (nullable) receives the first n_pairs pairs.  enable=0 releases the buffer. */
+int ceeus_tc_debug_timeline(CeeusHandle h, int enable, long long* out_host, int n_pairs);
 /* 1 once elites from a previous MPC step exist (controls whether shift noise is consumed) */
 int ceeus_has_elites(CeeusHandle h);
 

@@ -114,3 +114,20 @@ def rel_err(a, b):
     elem = float(np.max(np.abs(a - b) / (np.abs(b) + scale)))
     l2 = float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
     return max(elem, l2)
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def elites_consistent(idx, ref_costs, k, rel_tol):
+    """Tolerance-aware elite comparison: every reference candidate that beats the k-th best cost by more
+    than the precision-mode tolerance must be selected, none that is worse by more than it may be."""
+    ref_costs = np.asarray(ref_costs, np.float64)
+    kth = np.sort(ref_costs)[k - 1]
+    margin = rel_tol * max(abs(kth), float(np.max(np.abs(ref_costs))) * 0.1)
+    sure_in = set(np.nonzero(ref_costs < kth - margin)[0].tolist())
+    sure_out = set(np.nonzero(ref_costs > kth + margin)[0].tolist())
+    sel = set(int(i) for i in idx)
+    return sure_in <= sel and not (sel & sure_out)

