@@ -38,6 +38,8 @@ struct CeeusHandle_t {
   TcLayout tc{};             // CEEUS_PREC_TC only
   uint8_t* d_wimg = nullptr;
   float* d_wpar = nullptr;
+  int* d_kmap = nullptr;         // K permutation / folding map of every stage matrix
+  float* d_tc_scratch = nullptr; // logical fp32 stage matrices (pack-time only)
   int* d_tc_err = nullptr;
   long long* d_tc_dbg = nullptr;  // optional timeline of one warpgroup (ceeus_tc_debug_timeline)
   CeeusBuffers bufs{};
@@ -242,13 +244,18 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_obs, (size_t)c.num_envs * md.O * sizeof(float));
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_action, (size_t)c.num_envs * md.U * sizeof(float));
   if (e == cudaSuccess && c.precision == CEEUS_PREC_TC) {
-    if (c.model_kind != CEEUS_MODEL_GNN || !make_tc_layout(md, h->num_sms, &h->tc)) {
+    std::vector<int> kmap(4096, -1);
+    if (c.model_kind != CEEUS_MODEL_GNN || !make_tc_layout(md, h->num_sms, &h->tc, kmap.data())) {
       ceeus_destroy(h);
       return fail(nullptr, CEEUS_ERR_INVALID,
-                  "CEEUS_PREC_TC supports the GNN ensemble with hidden_dim 64/128, 2 hidden layers, dyn/agent dim <= 16");
+                  "CEEUS_PREC_TC supports the GNN ensemble with hidden_dim 64/128, 2 hidden layers, dyn/agent dim <= 16, "
+                  "action dim <= 8 and a trajectory group that fits shared memory");
     }
     e = cudaMalloc(&h->d_wimg, (size_t)md.E * 2 * h->tc.image_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_wpar, (size_t)md.E * h->tc.par_floats * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_kmap, (size_t)h->tc.kmap_len * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_kmap, kmap.data(), (size_t)h->tc.kmap_len * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_tc_scratch, (size_t)md.E * h->tc.scratch_floats * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&h->d_tc_err, sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(h->d_tc_err, 0, sizeof(int));
   }
@@ -274,7 +281,7 @@ void ceeus_destroy(CeeusHandle h) {
   if (!h) return;
   cudaFree(h->d_weights); cudaFree(h->d_norm); cudaFree(h->d_low); cudaFree(h->d_high);
   cudaFree(h->d_goal); cudaFree(h->d_obs); cudaFree(h->d_irdft);
-  cudaFree(h->d_wimg); cudaFree(h->d_wpar); cudaFree(h->d_tc_err); cudaFree(h->d_tc_dbg);
+  cudaFree(h->d_wimg); cudaFree(h->d_wpar); cudaFree(h->d_kmap); cudaFree(h->d_tc_scratch); cudaFree(h->d_tc_err); cudaFree(h->d_tc_dbg);
   if (h->h_obs) cudaFreeHost(h->h_obs);
   if (h->h_action) cudaFreeHost(h->h_action);
   delete h;
@@ -298,7 +305,7 @@ int ceeus_set_weights(CeeusHandle h, const float* const* dev_ptrs, int n, void* 
     LAUNCH(h, launch_repack(dev_ptrs[i], h->d_weights, h->md.E, t.rows, t.cols, h->md.member_stride, t.dst_off, t.dst_ld, S(stream)));
   }
   if (h->cfg.precision == CEEUS_PREC_TC)
-    LAUNCH(h, launch_tc_pack(h->d_weights, h->md, h->tc, h->d_wimg, h->d_wpar, S(stream)));
+    LAUNCH(h, launch_tc_pack(h->d_weights, h->md, h->tc, h->d_kmap, h->d_tc_scratch, h->d_wimg, h->d_wpar, S(stream)));
   h->weights_set = true;
   return CEEUS_OK;
 }

@@ -29,21 +29,34 @@ cudaError_t launch_rollout_gnn_simt(const ModelDesc& md, const RolloutArgs& ra, 
 cudaError_t launch_rollout_mlp_simt(const ModelDesc& md, const RolloutArgs& ra, cudaStream_t st);
 
 // ---- tensor-core rollout (rollout_tc.cu) ----
+// Stage matrices of one model step, in issue order per edge pass / node tile / global tile.
+enum { TC_E1 = 0, TC_E2, TC_N1, TC_N2, TC_N3, TC_G1, TC_G2, TC_G3, TC_NMAT };
 struct TcMat {      // one B operand (fp16, K-major 8x16B core matrices, split by output column between the CTA pair)
-  int K, N, nloc;   // padded K, total output columns, columns held per CTA
+  int K, N, nloc;   // padded K, output columns, columns held per CTA
   int off;          // byte offset inside the per-(member, rank) weight image
-  int src_mlp, src_layer;
-  int seg_tc[2], seg_len[2], seg_src[2];  // K permutation: tile-K range [seg_tc, +len) <- source rows [seg_src, +len)
+  int kx;           // leading K range fed from the "x part" of the A operand (R1); the rest comes from R2 (aggregate)
+  int ln;           // LayerNorm follows (weights are centred over the output columns at pack time)
+  int par_bias, par_gamma, par_beta;  // float offsets in the per-member parameter block (-1: none / folded into K)
+  int kmap_off;     // offset of this matrix' K map in the kmap buffer
 };
 struct TcLayout {
-  int HD, KE1, KX, T_r, ppm;  // ppm: CTA pairs per ensemble member
-  TcMat mat[9];               // E1 E2 E3 N1 N2 N3 G1 G2 G3
-  int image_bytes;            // per (member, rank)
-  int par_off[9][3], par_len[9], par_floats;  // fp32 bias / gamma / beta blocks per member
-  int sm_w, sm_slot[2], sm_par, sm_state[2], sm_rinfo, sm_bar, sraw_bytes, smem_bytes;
+  int HD;
+  int AUp, NAp, SNs;       // halves: header [agent|action|1|0..], node block [dyn|stat|0..], per-trajectory snrm row
+  int KE1, KXn, KXg;       // padded K of the edge input, node x-part, global x-part
+  int Te, Tmax, n_pass_max, q_n;  // trajectories per edge pass, per group; node-tile lanes per warp and pass
+  int tail;                // N*S + G floats behind the dynamic part of an observation
+  TcMat mat[TC_NMAT];
+  int image_bytes;         // per (member, rank)
+  int par_floats;          // per member
+  int kmap_len;
+  int sm_w, sm_par, sm_nrm, nrm_floats, sm_slot[2], sm_bar, smem_bytes;
+  int so_h2, so_agg, so_glob, so_snrm, so_tail;  // offsets inside a slot region
+  int pairs;               // CTA pairs in the grid
+  int scratch_floats;      // per member: logical fp32 matrices built by the pack kernels
 };
-bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out);
-cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, uint8_t* wimg, float* wpar, cudaStream_t st);
+bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_host /* [kmap_len] or null */);
+cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, const int* kmap_dev, float* scratch,
+                           uint8_t* wimg, float* wpar, cudaStream_t st);
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                   const float* wpar, int* err_flag, long long* dbg, cudaStream_t st);
 

@@ -1,21 +1,25 @@
 // CEEUS_PREC_TC: tensor-core (tcgen05) GNN rollout -- the whole horizon of GNNForwardEnsembleModel.predict_n_steps
 // (mbrl/models/gnn_ensemble.py:876-983, gnn_modules.py:173-278) in one persistent launch.
 //
-// Execution model (see DESIGN.md "rollout_gnn_tc_kernel"):
-//   * grid = CTA PAIRS (cluster of 2, tcgen05 cta_group::2).  A pair owns one ensemble member and a contiguous chunk of
-//     trajectories.  Every linear layer of the member's three MLPs is resident in shared memory for the whole kernel as
-//     fp16, split by output column between the two CTAs (each CTA holds N/2 columns of every B operand) -> 114 KB per
-//     CTA instead of 224 KB, which is what makes residency possible at all.
-//   * per CTA two warpgroups (WG0 = warps 0-3, WG1 = warps 4-7), each with its own A-operand tile in shared memory
-//     ("slot") and its own 2 x HD TMEM accumulator columns.  WG s of CTA 0 and WG s of CTA 1 form one M = 256 MMA tile.
-//     Warp 8 lane 0 of the leader CTA issues every tcgen05.mma; completion is multicast-committed to both CTAs.
-//   * a WG runs groups of T_r trajectories through all H steps.  Per step: edge tile (T_r * N(N-1) rows) through the
-//     3-layer edge MLP, on-chip aggregation (mean over the N-1 edges of each source node, mean over all edges), then ONE
-//     combined tile whose rows are the T_r * N node rows and the T_r global rows; that tile is multiplied by both the
-//     node-MLP and the global-MLP weights (two accumulators) and every row keeps the result of its own MLP.
-//   * thread == tile row == TMEM lane in every epilogue: bias + LayerNorm + ReLU run on the 128 fp32 accumulator
-//     values of the row held in registers; the fp16 result is written straight back as the next layer's A operand.
-//   * operands are fp16 (10-bit mantissa, like TF32) with fp32 accumulation; states, residual update, normalisers and
+// Execution model (DESIGN.md "rollout_gnn_tc_kernel"):
+//   * grid = CTA PAIRS (cluster of 2, tcgen05 cta_group::2, M = 256).  A pair owns one ensemble member; every B operand
+//     of the member (8 fp16 matrices, 96 KB per CTA thanks to the split by output column) is resident in shared memory
+//     for the whole kernel, staged by one bulk TMA copy.
+//   * per CTA two warpgroups ("slots"), each owning 2*HD TMEM columns: the fp32 accumulator (HD columns) and two fp16
+//     A-operand regions R1, R2 (HD/2 columns each).  The A operand of EVERY MMA comes from TMEM (tcgen05.mma "TS" form):
+//     the epilogue threads write the next layer's input with tcgen05.st, so activations never touch shared memory.
+//     Thread == tile row == TMEM lane in every epilogue.  Warps 8/9 lane 0 of the leader CTA issue the MMAs of slot 0/1;
+//     completion is multicast-committed to both CTAs.
+//   * a warpgroup takes a group of T trajectories through all H steps.  Per step: edge rows in passes of Te trajectories
+//     (E1, E2), aggregation of the hidden edge activations, node tile (N1, N2, N3), global tile (G1, G2, G3).
+//   * algebra done at pack time (tc_logical_kernel): the edge output layer has no LayerNorm / activation and the
+//     aggregation is linear, so  aggr_j(h2_j W3 + b3) W_agg = aggr_j(h2_j) (W3 W_agg) + b3 W_agg  -- W3 is folded into the
+//     first node / global layer and the E3 stage disappears; mean-aggregation scales are folded too.  Weights feeding a
+//     LayerNorm are centred over the output columns, so the MMA result already has zero row mean and the epilogue only
+//     needs the second moment.  First-layer biases ride in a constant-one K column.
+//   * fp32 object states live in REGISTERS of the row-owner threads (node row: D dynamic features, global row: agent);
+//     shared memory only holds the normalised fp16 copy the A tiles are built from.
+//   * operands are fp16 (10-bit mantissa, TF32 class) with fp32 accumulation; states, residual update, normalisers and
 //     LayerNorm statistics stay fp32.  Parity bar: 1e-3 (BASELINE.json north_star, tf32/bf16 mode).
 #include <cuda_fp16.h>
 
@@ -30,6 +34,7 @@ using namespace tc;
 
 constexpr int kTcThreads = 320;  // 2 epilogue warpgroups + 2 MMA-issuer warps (warp 8 also does the set-up)
 constexpr uint32_t FULL = 0xffffffffu;
+constexpr int kFold = 100000;    // kmap code >= kFold: folded aggregate row (index code - kFold)
 
 __device__ __forceinline__ void wg_sync(int s) { asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory"); }
 
@@ -43,12 +48,8 @@ __device__ __forceinline__ float act_fn(float x, int act) {
 }
 
 struct Ctx {
-  uint8_t* smem;
-  uint64_t* a_ready;   // [2] (used in the leader CTA)
-  uint64_t* d_ready;   // [2]
-  volatile int* abort; // per CTA
-  int* err;            // global
-  uint32_t tmem_base;
+  volatile int* abort;  // per CTA
+  int* err;             // global
   uint32_t a_ready_leader[2];  // cluster addresses of the leader's a_ready barriers
 };
 
@@ -62,13 +63,14 @@ __device__ __forceinline__ bool wait_bar(const Ctx& cx, uint64_t* bar, uint32_t 
   return false;
 }
 
-// A-operand tile of this WG is complete: make the generic-proxy writes visible to the tensor core, order prior TMEM
-// loads, one arrival per warp on the leader's barrier.
+// The A operand of this warpgroup's next MMA stage is complete in TMEM: retire the tcgen05.st, order them (and the
+// earlier tcgen05.ld of the accumulator) before the barrier, one arrival per warp on the leader's barrier.
 __device__ __forceinline__ void signal_a(const Ctx& cx, int s, int lane) {
-  fence_proxy_async();
+  tmem_wait_st();
   tc_fence_before();
+  __threadfence_block();  // shared-memory staging written by this thread is read by CTA-local threads behind the barrier chain
   __syncwarp();
-  if (lane == 0) mbar_arrive_cluster(cx.a_ready_leader[s]);
+  if (lane == 0) mbar_arrive_cluster_relaxed(cx.a_ready_leader[s]);
 }
 
 template <int HD>
@@ -77,56 +79,75 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, float (&x)[HD]) {
   for (int c0 = 0; c0 < HD; c0 += 32) tmem_ld32(taddr + c0, *reinterpret_cast<uint32_t(*)[32]>(&x[c0]));
 }
 
-// bias + LayerNorm + activation on the row held in x[], fp16 result -> A tile chunks [chunk0, chunk0 + HD/8) of `row`
+// HD/2 packed fp16 pairs -> TMEM columns [taddr, taddr + HD/2)
 template <int HD>
-__device__ __forceinline__ void finish_row(float (&x)[HD], const float* __restrict__ pb, const float* __restrict__ pg,
-                                           const float* __restrict__ pbe, bool ln, int act, uint8_t* tile, int chunk0,
-                                           int row, bool store) {
+__device__ __forceinline__ void store_hidden(uint32_t taddr, const uint32_t (&h)[HD / 2]) {
 #pragma unroll
-  for (int j = 0; j < HD; j += 4) {
-    const float4 b = *reinterpret_cast<const float4*>(pb + j);
-    x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
-  }
-  if (ln) {
-    float s4[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < HD; j += 8) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) s4[t] += x[j + t];
-    }
-    const float mean = (((s4[0] + s4[1]) + (s4[2] + s4[3])) + ((s4[4] + s4[5]) + (s4[6] + s4[7]))) * (1.f / HD);
-    float v4[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < HD; j += 8) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        x[j + t] -= mean;
-        v4[t] = fmaf(x[j + t], x[j + t], v4[t]);
-      }
-    }
-    const float v = ((v4[0] + v4[1]) + (v4[2] + v4[3])) + ((v4[4] + v4[5]) + (v4[6] + v4[7]));
-    const float rstd = rsqrtf(v * (1.f / HD) + 1e-5f);
+  for (int c0 = 0; c0 < HD / 2; c0 += 32) tmem_st32(taddr + c0, *reinterpret_cast<const uint32_t(*)[32]>(&h[c0]));
+}
+
+// bias + LayerNorm (second moment only: the weights are centred) + activation on the accumulator row -> packed fp16
+template <int HD>
+__device__ __forceinline__ void epi_hidden(uint32_t tacc, const float* __restrict__ pb, const float* __restrict__ pg,
+                                           const float* __restrict__ pbe, bool ln, int act, uint32_t (&h)[HD / 2]) {
+  float x[HD];
+  load_acc<HD>(tacc, x);
+  tmem_wait_ld();
+  if (pb != nullptr) {
 #pragma unroll
     for (int j = 0; j < HD; j += 4) {
-      const float4 g = *reinterpret_cast<const float4*>(pg + j);
-      const float4 be = *reinterpret_cast<const float4*>(pbe + j);
-      x[j] = fmaf(x[j] * rstd, g.x, be.x);
-      x[j + 1] = fmaf(x[j + 1] * rstd, g.y, be.y);
-      x[j + 2] = fmaf(x[j + 2] * rstd, g.z, be.z);
-      x[j + 3] = fmaf(x[j + 3] * rstd, g.w, be.w);
+      const float4 b = *reinterpret_cast<const float4*>(pb + j);
+      x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
     }
   }
-  if (store) {
+  if (ln) {
+    float v8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < HD / 8; ++c) {
-      uint4 o;
-      o.x = pack_half2(act_fn(x[8 * c + 0], act), act_fn(x[8 * c + 1], act));
-      o.y = pack_half2(act_fn(x[8 * c + 2], act), act_fn(x[8 * c + 3], act));
-      o.z = pack_half2(act_fn(x[8 * c + 4], act), act_fn(x[8 * c + 5], act));
-      o.w = pack_half2(act_fn(x[8 * c + 6], act), act_fn(x[8 * c + 7], act));
-      *reinterpret_cast<uint4*>(tile + (size_t)(chunk0 + c) * 2048 + row * 16) = o;
+    for (int j = 0; j < HD; j += 8) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v8[t] = fmaf(x[j + t], x[j + t], v8[t]);
     }
+    const float v = ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
+    const float rstd = rsqrtf(v * (1.f / HD) + 1e-5f);
+    if (act == CEEUS_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < HD; j += 4) {
+        const float4 g = *reinterpret_cast<const float4*>(pg + j);
+        const float4 be = *reinterpret_cast<const float4*>(pbe + j);
+        h[j / 2] = pack_half2_relu(fmaf(x[j] * rstd, g.x, be.x), fmaf(x[j + 1] * rstd, g.y, be.y));
+        h[j / 2 + 1] = pack_half2_relu(fmaf(x[j + 2] * rstd, g.z, be.z), fmaf(x[j + 3] * rstd, g.w, be.w));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < HD; j += 4) {
+        const float4 g = *reinterpret_cast<const float4*>(pg + j);
+        const float4 be = *reinterpret_cast<const float4*>(pbe + j);
+        h[j / 2] = pack_half2(act_fn(fmaf(x[j] * rstd, g.x, be.x), act), act_fn(fmaf(x[j + 1] * rstd, g.y, be.y), act));
+        h[j / 2 + 1] = pack_half2(act_fn(fmaf(x[j + 2] * rstd, g.z, be.z), act), act_fn(fmaf(x[j + 3] * rstd, g.w, be.w), act));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < HD; j += 2) h[j / 2] = pack_half2(act_fn(x[j], act), act_fn(x[j + 1], act));
   }
+}
+
+__device__ __forceinline__ void add8(float (&acc)[8], const uint4& m) {
+  const __half2* hp = reinterpret_cast<const __half2*>(&m);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __half22float2(hp[t]);
+    acc[2 * t] += f.x;
+    acc[2 * t + 1] += f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&acc)[8]) {
+  uint4 o;
+  o.x = pack_half2(acc[0], acc[1]);
+  o.y = pack_half2(acc[2], acc[3]);
+  o.z = pack_half2(acc[4], acc[5]);
+  o.w = pack_half2(acc[6], acc[7]);
+  return o;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -135,21 +156,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     rollout_gnn_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcLayout tl, const uint8_t* __restrict__ wimg,
                           const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int CH = HD / 8;  // 16-byte chunks per hidden row
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
-  const int e = pair / tl.ppm;
-  const int chunk_id = pair % tl.ppm;
   const int N = md.N, A = md.A, D = md.D, S = md.S, U = md.U, sd = md.sd, O = md.O;
-  const int NA = D + S, NE = N * (N - 1), N1 = N + 1;
-  const int T_r = tl.T_r;
-  const int KXc = tl.KX / 8;  // chunks of the [x|g|u] part of the combined tile
+  const int NE = N * (N - 1);
+
+  // ---- member / trajectory range of this pair: pairs are dealt to members as evenly as the count allows ----
+  int e, lp, np;
+  {
+    const int base = tl.pairs / md.E, rem = tl.pairs % md.E;
+    if (pair < rem * (base + 1)) { e = pair / (base + 1); lp = pair % (base + 1); np = base + 1; }
+    else { const int q = pair - rem * (base + 1); e = rem + q / base; lp = q % base; np = base; }
+  }
+  const int per_worker = (ra.n + 4 * np - 1) / (4 * np);
+  const int rounds = (per_worker + tl.Tmax - 1) / tl.Tmax;
+  const int T = (per_worker + rounds - 1) / rounds;  // trajectories per group, <= Tmax
+  const int Te = tl.Te;
+  const int n_pass = (T + Te - 1) / Te;
+  const int n_stage = 2 * n_pass + 6;
 
   uint8_t* sW = smem + tl.sm_w;
   float* sPar = reinterpret_cast<float*>(smem + tl.sm_par);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tl.sm_bar);
   uint64_t* wbar = bars;        // weights landed
-  uint64_t* a_ready = bars + 1; // [2]
+  uint64_t* a_ready = bars + 1; // [2] (used in the leader CTA)
   uint64_t* d_ready = bars + 3; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
@@ -172,312 +204,357 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     tmem_relinquish<2>();
   }
   for (int i = tid; i < tl.par_floats; i += kTcThreads) sPar[i] = __ldg(wpar + (size_t)e * tl.par_floats + i);
+  // normalisers -> shared memory; the std of the INPUT groups is stored as its reciprocal (x_n = (x - mean) * inv_std)
+  float* sNrm = reinterpret_cast<float*>(smem + tl.sm_nrm);
+  for (int i = tid; i < tl.nrm_floats; i += kTcThreads) {
+    const float v = __ldg(ra.norm + i);
+    const bool inv = (i >= md.nrm.in_agent + md.A && i < md.nrm.in_dyn) || (i >= md.nrm.in_dyn + md.D && i < md.nrm.in_stat) ||
+                     (i >= md.nrm.in_stat + md.S && i < md.nrm.in_action) || (i >= md.nrm.in_action + md.U && i < md.nrm.out_agent);
+    sNrm[i] = inv ? 1.f / v : v;
+  }
   tc_fence_before();
   __syncthreads();
   Ctx cx;
-  cx.smem = smem; cx.a_ready = a_ready; cx.d_ready = d_ready; cx.abort = abort_flag; cx.err = err;
+  cx.abort = abort_flag; cx.err = err;
   if (warp == 8 && lane == 0) wait_bar(cx, wbar, 0, 1);  // this CTA's weight image has landed
   __syncthreads();
   cluster_sync();  // both CTAs: barriers initialised, TMEM allocated, weights resident
   tc_fence_after();
-  cx.tmem_base = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
   cx.a_ready_leader[0] = mapa(smem_u32(&a_ready[0]), 0);
   cx.a_ready_leader[1] = mapa(smem_u32(&a_ready[1]), 0);
 
-  // trajectories of this pair
-  const int chunk = (ra.n + tl.ppm - 1) / tl.ppm;
-  const int c_lo = min(ra.n, chunk_id * chunk), c_hi = min(ra.n, c_lo + chunk);
-  const int n_groups = (c_hi - c_lo + T_r - 1) / T_r;
-  const int n_iter = (n_groups + 3) / 4;  // 4 workers per pair, lock-step
-  const int total_stages = n_iter * ra.H * 6;
-
   if (warp >= 8) {
     // =========================== MMA issuers (leader CTA): warp 8 -> slot 0, warp 9 -> slot 1 ===========================
-    // One thread per slot, each blocking on its own barrier: mbarrier.try_wait suspends the thread for a
-    // system-defined time, so a single thread polling both slots alternately stalled every stage of one slot
-    // behind the other's time-out (first version: ~10 us per stage).
     if (rank == 0 && lane == 0) {
       const int s = warp - 8;
       const uint32_t idesc_h = make_idesc_f16(256, HD);
       const uint32_t idesc_o = make_idesc_f16(256, 16);
       const uint32_t wbase = smem_u32(sW);
-      const uint32_t a_addr = smem_u32(smem + tl.sm_slot[s]);
-      const uint32_t d0 = cx.tmem_base + (uint32_t)(s * 2 * HD);
-      const uint32_t d1 = d0 + HD;
-      auto issue = [&](uint32_t d, const TcMat& m, uint32_t idesc) {
+      const uint32_t acc = tmem_base + (uint32_t)(s * 2 * HD);
+      const uint32_t r1 = acc + HD, r2 = r1 + HD / 2;
+      // K steps [k0, k1) of matrix m with the A operand at TMEM columns a_col + 8 * (ks - k0)
+      auto issue = [&](const TcMat& m, int k0, int k1, uint32_t a_col, uint32_t idesc, bool first) {
         const uint32_t lbo_b = (uint32_t)m.nloc * 16;
 #pragma unroll 1
-        for (int ks = 0; ks < m.K / 16; ++ks) {
-          const uint64_t da = make_smem_desc(a_addr + (uint32_t)(2 * ks) * 2048, 2048, 128);
+        for (int ks = k0; ks < k1; ++ks) {
           const uint64_t db = make_smem_desc(wbase + (uint32_t)m.off + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
-          umma_f16_ss<2>(d, da, db, idesc, ks > 0 ? 1u : 0u);
+          umma_f16_ts<2>(acc, a_col + (uint32_t)(8 * (ks - k0)), db, idesc, (first && ks == k0) ? 0u : 1u);
         }
       };
       uint32_t ph = 0;
+      const int total = rounds * ra.H;
 #pragma unroll 1
-      for (int stage = 0; stage < total_stages; ++stage) {
-        if (!wait_bar(cx, &a_ready[s], ph, 2)) break;
-        ph ^= 1u;
-        tc_fence_after();
-        switch (stage % 6) {
-          case 0: issue(d0, tl.mat[0], idesc_h); break;
-          case 1: issue(d0, tl.mat[1], idesc_h); break;
-          case 2: issue(d0, tl.mat[2], idesc_h); break;
-          case 3: issue(d0, tl.mat[3], idesc_h); issue(d1, tl.mat[6], idesc_h); break;
-          case 4: issue(d0, tl.mat[4], idesc_h); issue(d1, tl.mat[7], idesc_h); break;
-          default: issue(d0, tl.mat[5], idesc_o); issue(d1, tl.mat[8], idesc_o); break;
+      for (int it = 0; it < total; ++it) {
+#pragma unroll 1
+        for (int st = 0; st < n_stage; ++st) {
+          if (!wait_bar(cx, &a_ready[s], ph, 2)) { it = total; break; }
+          ph ^= 1u;
+          tc_fence_after();
+          const int kind = st < 2 * n_pass ? (st & 1) : 2 + (st - 2 * n_pass);
+          const TcMat& m = tl.mat[kind];
+          const int kx = m.kx / 16, kall = m.K / 16;
+          const uint32_t idesc = (kind == TC_N3 || kind == TC_G3) ? idesc_o : idesc_h;
+          issue(m, 0, kx, r1, idesc, true);
+          if (kall > kx) issue(m, kx, kall, r2, idesc, kx == 0);
+          umma_commit_cg2_mc(&d_ready[s], 0x3);
         }
-        umma_commit_cg2_mc(&d_ready[s], 0x3);
       }
     }
-  } else if (warp < 8) {
+  } else {
     // =========================== warpgroup: tile builder + epilogue ===========================
     const int s = warp >> 2;       // slot
     const int q = warp & 3;        // TMEM lane quadrant
     const int row = tid & 127;     // tile row == TMEM lane
-    const int worker = (int)rank * 2 + s;
-    uint8_t* tile = smem + tl.sm_slot[s];
-    float* sraw = reinterpret_cast<float*>(smem + tl.sm_state[s]);
-    __half* snrm = reinterpret_cast<__half*>(smem + tl.sm_state[s] + tl.sraw_bytes);
-    const int SN = A + U + N * NA;  // normalised [agent | action | nodes]
-    const float* __restrict__ nrm = ra.norm;
+    const int worker = (lp * 2 + (int)rank) * 2 + s;
+    uint8_t* slot = smem + tl.sm_slot[s];
+    uint8_t* s_h2 = slot + tl.so_h2;      // [128][HD] fp16, 16-byte chunks swizzled by (row & 7)
+    uint8_t* s_agg = slot + tl.so_agg;    // [Te*N][HD] fp16 sums over the N-1 outgoing edges (N >= 3)
+    uint8_t* s_glob = slot + tl.so_glob;  // [T][HD] fp16 sums over all edges
+    __half* snrm = reinterpret_cast<__half*>(slot + tl.so_snrm);  // [T][SNs] normalised [hdr | node blocks]
+    float* s_tail = reinterpret_cast<float*>(slot + tl.so_tail);  // [T][tail] static features + goal (fp32)
+    const int SNs = tl.SNs, AUp = tl.AUp, NAp = tl.NAp, tail = tl.tail;
+    const float* __restrict__ nrm = sNrm;
     const bool ln = md.layer_norm != 0;
     const int act = md.act;
-    const float inv_node = md.aggr_mean ? 1.f / fmaxf((float)(N - 1), 1.f) : 1.f;
-    const float inv_glob = md.aggr_mean ? 1.f / fmaxf((float)NE, 1.f) : 1.f;
-    const uint32_t tm_row = cx.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 2 * HD);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 2 * HD);
+    const uint32_t t_acc = lane_base, t_r1 = lane_base + HD, t_r2 = lane_base + HD + HD / 2;
     uint32_t dph = 0;
-    auto par = [&](int m, int which) { return sPar + tl.par_off[m][which]; };
-    // combined row r = b*(N+1)+i  ->  (first message row, number of messages): node i<N: its N-1 outgoing edges,
-    // i==N (global row): all N(N-1) edges of trajectory b
+    auto parp = [&](int off) -> const float* { return off >= 0 ? sPar + off : nullptr; };
     int dbg_n = 0;
     const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && tid == 0;
     auto stamp = [&](int tag) {
       if (dbg_on && dbg_n < 250) { dbg[2 * dbg_n] = tag; dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
     };
-    int2* rinfo = reinterpret_cast<int2*>(smem + tl.sm_rinfo) + s * 128;
-    {
-      const int b = row / N1, i = row % N1;
-      rinfo[row] = make_int2(b * NE + (i < N ? i * (N - 1) : 0), i < N ? N - 1 : NE);
-    }
 
-    for (int it = 0; it < n_iter; ++it) {
-      const int g = it * 4 + worker;
-      const int p0 = c_lo + g * T_r;
-      const int Gc = g < n_groups ? min(T_r, c_hi - p0) : 0;  // live trajectories of this group (0: pure lock-step filler)
-      const int rows_e = Gc * NE, rows_c = Gc * N1;
+    // ---- static row roles ----
+    // edge row (pass-local): trajectory bl, source node ei, target node ej
+    const int e_bl = row / NE, e_q = row % NE;
+    const int e_i = e_q / (N - 1), e_jj = e_q % (N - 1);
+    const int e_j = e_jj + (e_jj >= e_i ? 1 : 0);
+    // node row: pass n_p, pass-local aggregate row n_a = bl * N + i.  N == 2: node row == edge row (one edge per node);
+    // N >= 3: each pass's rows are dealt over the four warps so that the aggregation owners are spread.
+    int n_p, n_a;
+    if (N == 2) { n_p = 0; n_a = row; }
+    else { n_p = lane / tl.q_n; n_a = (lane % tl.q_n) * 4 + q; }
+    const bool n_valid = n_a < Te * N && n_p < n_pass;
+    const int n_b = n_p * Te + n_a / N, n_i = n_a % N;  // group-local trajectory, node
+    // global row: trajectory == row
+
+    float dyn[16], agent[16], act_next[8];
+
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int w_lo = min(ra.n, worker * per_worker), w_hi = min(ra.n, w_lo + per_worker);
+      const int p0 = w_lo + rd * T;
+      const int Gc = max(0, min(T, w_hi - p0));  // live trajectories of this group (0: pure lock-step filler)
+      const bool live_n = n_valid && n_b < Gc;
+      const bool live_g = row < Gc;
       wg_sync(s);
-      // ---- start observation -> raw state, traj[0] ----
-      for (int idx = row; idx < Gc * sd; idx += 128) {
-        const int b = idx / sd, c = idx % sd;
-        sraw[idx] = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
-      }
+      // ---- group init: start observation -> registers, snrm, tail cache, traj[0] ----
+      for (int idx = row; idx < (T * SNs) / 8; idx += 128) reinterpret_cast<uint4*>(snrm)[idx] = make_uint4(0u, 0u, 0u, 0u);
       for (int idx = row; idx < Gc * O; idx += 128) {
         const int b = idx / O, c = idx % O;
-        ra.traj[((size_t)e * ra.n + p0 + b) * O + c] = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
+        const float v = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
+        ra.traj[((size_t)e * ra.n + p0 + b) * O + c] = v;
+      }
+      for (int idx = row; idx < Gc * tail; idx += 128) {
+        const int b = idx / tail, c = idx % tail;
+        s_tail[idx] = c < N * S ? __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + A + N * D + c)
+                                : __ldg(ra.goal + (size_t)((p0 + b) / ra.traj_per_goal) * md.G + (c - N * S));
       }
       wg_sync(s);
+      if (live_n) {
+        const float* so = ra.start_obs + (size_t)((p0 + n_b) / ra.traj_per_start) * O;
+        __half* dst = snrm + n_b * SNs + AUp + n_i * NAp;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < D) {
+            dyn[j] = __ldg(so + A + n_i * D + j);
+            dst[j] = __float2half_rn((dyn[j] - nrm[md.nrm.in_dyn + j]) * nrm[md.nrm.in_dyn + D + j]);
+          }
+        for (int j = 0; j < S; ++j)
+          dst[D + j] = __float2half_rn((__ldg(so + A + N * D + n_i * S + j) - nrm[md.nrm.in_stat + j]) * nrm[md.nrm.in_stat + S + j]);
+      }
+      if (live_g) {
+        const float* so = ra.start_obs + (size_t)((p0 + row) / ra.traj_per_start) * O;
+        __half* dst = snrm + row * SNs;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < A) {
+            agent[j] = __ldg(so + j);
+            dst[j] = __float2half_rn((agent[j] - nrm[md.nrm.in_agent + j]) * nrm[md.nrm.in_agent + A + j]);
+          }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < U) {
+            const float a0 = __ldg(ra.actions + ((size_t)(p0 + row) * ra.H) * U + j);
+            dst[A + j] = __float2half_rn((a0 - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]);
+          }
+        dst[A + U] = __float2half_rn(1.f);
+      }
+      wg_sync(s);
+
+      // A operand of an edge pass: [hdr | x_i | x_j] of this thread's edge row -> R1
+      auto build_edge = [&](int p) {
+        const int b = min(p * Te + e_bl, T - 1);
+        const uint4* sb = reinterpret_cast<const uint4*>(snrm + b * SNs);
+        int col = 0;
+        for (int c = 0; c < AUp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[c]);
+        for (int c = 0; c < NAp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[(AUp + e_i * NAp) / 8 + c]);
+        for (int c = 0; c < NAp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[(AUp + e_j * NAp) / 8 + c]);
+        for (; col < tl.KE1 / 2; col += 4) tmem_st4(t_r1 + col, make_uint4(0u, 0u, 0u, 0u));
+      };
 
       for (int h = 0; h < ra.H; ++h) {
         stamp(100);
-        // ---- normalise state + action (gnn_ensemble.py:190-243) -> fp16 ----
-        for (int idx = row; idx < Gc * SN; idx += 128) {
-          const int b = idx / SN, c = idx % SN;
-          float v;
-          if (c < A) {
-            v = (sraw[b * sd + c] - __ldg(nrm + md.nrm.in_agent + c)) / __ldg(nrm + md.nrm.in_agent + A + c);
-          } else if (c < A + U) {
-            const int u = c - A;
-            const float a = __ldg(ra.actions + ((size_t)(p0 + b) * ra.H + h) * U + u);
-            v = (a - __ldg(nrm + md.nrm.in_action + u)) / __ldg(nrm + md.nrm.in_action + U + u);
-          } else {
-            const int qq = c - A - U, i = qq / NA, f = qq % NA;
-            if (f < D)
-              v = (sraw[b * sd + A + i * D + f] - __ldg(nrm + md.nrm.in_dyn + f)) / __ldg(nrm + md.nrm.in_dyn + D + f);
-            else
-              v = (sraw[b * sd + A + N * D + i * S + (f - D)] - __ldg(nrm + md.nrm.in_stat + (f - D))) /
-                  __ldg(nrm + md.nrm.in_stat + S + (f - D));
-          }
-          snrm[idx] = __float2half_rn(v);
-        }
-        wg_sync(s);
-        stamp(101);
-        // ---- edge tile, layer-1 input [x_i | x_j | agent | action | 0] (gnn_modules.py:194-211) ----
-        if (row < rows_e) {
-          const int b = row / NE, qq = row % NE;
-          const int i = qq / (N - 1), jj = qq % (N - 1);
-          const int j = jj + (jj >= i ? 1 : 0);
-          const __half* sb = snrm + b * SN;
-          for (int c = 0; c < tl.KE1 / 8; ++c) {
-            __align__(16) __half tmp[8];
+        if (live_g && h + 1 < ra.H) {  // prefetch the next step's action; consumed in the G3 epilogue
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              const int k = c * 8 + t;
-              __half v = __float2half_rn(0.f);
-              if (k < NA) v = sb[A + U + i * NA + k];
-              else if (k < 2 * NA) v = sb[A + U + j * NA + (k - NA)];
-              else if (k < 2 * NA + A) v = sb[k - 2 * NA];
-              else if (k < 2 * NA + A + U) v = sb[A + (k - 2 * NA - A)];
-              tmp[t] = v;
-            }
-            *reinterpret_cast<uint4*>(tile + (size_t)c * 2048 + row * 16) = *reinterpret_cast<const uint4*>(tmp);
-          }
+          for (int j = 0; j < 8; ++j)
+            if (j < U) act_next[j] = __ldg(ra.actions + ((size_t)(p0 + row) * ra.H + h + 1) * U + j);
         }
-        stamp(102);
+        build_edge(0);
         signal_a(cx, s, lane);
-        stamp(103);
+        float* outp = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
 
-        // ---- six MMA stages of this step: E1 E2 E3 (edge MLP) C1 C2 C3 (node + global MLP on the combined tile) ----
-        // One copy of the row epilogue serves all hidden stages: code size matters (the first version unrolled it five
-        // times into 350 KB of SASS and stalled on instruction fetch).
-        const int cb = row / N1, ci = row % N1;
-        const bool is_glob = ci == N;
-        const bool live_c = row < rows_c, live_e = row < rows_e;
-        const bool has_n = __any_sync(FULL, live_c && !is_glob);
-        const bool has_g = __any_sync(FULL, live_c && is_glob);
-        const bool warp_live_e = q * 32 < rows_e;
 #pragma unroll 1
-        for (int st = 0; st < 6; ++st) {
-          stamp(10 + st);
-          wait_bar(cx, &d_ready[s], dph, 10 + st);
+        for (int st = 0; st < n_stage; ++st) {
+          const int kind = st < 2 * n_pass ? (st & 1) : 2 + (st - 2 * n_pass);
+          const int p = st >> 1;  // edge pass (kinds E1 / E2)
+          stamp(10 + kind);
+          wait_bar(cx, &d_ready[s], dph, 10 + kind);
           dph ^= 1u;
           tc_fence_after();
-          stamp(20 + st);
-          const bool cstage = st >= 3;
-          const bool warp_on = cstage ? (has_n || has_g) : warp_live_e;
-          if (st < 5) {
-            if (warp_on) {
-              float x[HD];
-              const bool from_g = cstage && !has_n;  // warp holds only global rows
-              load_acc<HD>(tm_row + (from_g ? HD : 0), x);
-              tmem_wait_ld();
-              if (cstage && has_n && has_g) {  // mixed warp: global rows take the second accumulator
+          stamp(20 + kind);
+          const TcMat& m = tl.mat[kind];
+          if (kind != TC_N3 && kind != TC_G3) {
+            // ------------------ hidden layer: LayerNorm + activation -> fp16 ------------------
+            const bool live = kind <= TC_E2 ? (e_bl < Te && p * Te + e_bl < Gc) : kind <= TC_N2 ? live_n : live_g;
+            const bool warp_on = __any_sync(FULL, live);
+            uint32_t hreg[HD / 2];
+            if (warp_on) epi_hidden<HD>(t_acc, parp(m.par_bias), parp(m.par_gamma), parp(m.par_beta), ln && m.ln, act, hreg);
+            stamp(30 + kind);
+            if (kind != TC_E2) {
+              if (warp_on) store_hidden<HD>(t_r1, hreg);
+            } else {
+              // ---------- aggregation of the hidden edge activations (models/utils.py:42-51; W3 folded) ----------
+              if (N == 2) {
+                // one outgoing edge per node: the node aggregate is this thread's own row; the global aggregate is the
+                // sum of the two rows of a trajectory (adjacent lanes)
+                if (warp_on) {
+                  store_hidden<HD>(t_r2, hreg);
 #pragma unroll
-                for (int c0 = 0; c0 < HD; c0 += 32) {
-                  uint32_t t32[32];
-                  tmem_ld32(tm_row + HD + c0, t32);
-                  tmem_wait_ld();
+                  for (int j = 0; j < HD / 2; ++j) {
+                    const uint32_t o = __shfl_xor_sync(FULL, hreg[j], 1);
+                    const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&hreg[j]), *reinterpret_cast<const __half2*>(&o));
+                    hreg[j] = *reinterpret_cast<const uint32_t*>(&sum);
+                  }
+                  if (live && (row & 1) == 0) {
+                    const int b = row >> 1;
 #pragma unroll
-                  for (int j = 0; j < 32; ++j)
-                    if (is_glob) x[c0 + j] = __uint_as_float(t32[j]);
+                    for (int c = 0; c < CH; ++c)
+                      *reinterpret_cast<uint4*>(s_glob + (size_t)b * (HD * 2) + ((c ^ (b & 7)) * 16)) =
+                          make_uint4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
+                  }
                 }
-              }
-              const int m = cstage ? (is_glob ? 6 : 3) + (st - 3) : st;
-              const bool hidden = st != 2;
-              finish_row<HD>(x, par(m, 0), par(m, hidden ? 1 : 0), par(m, hidden ? 2 : 0), ln && hidden,
-                             hidden ? act : CEEUS_ACT_NONE, tile, st == 2 ? KXc : 0, row, cstage ? live_c : live_e);
-            }
-            stamp(30 + st);
-            if (st == 2) {
-              // ---- aggregation (models/utils.py:42-51): read every message chunk this thread needs, then write ----
-              tc_fence_before();
-              wg_sync(s);
-              constexpr int CH = HD / 8;
-              uint4 outv[CH];  // rows_c <= 128  =>  at most CH items per thread
-              const int n_items = rows_c * CH;
-              {
-                int c = 0, r = row;  // item = c * rows_c + r, advanced by 128 per slot without divisions
-                if (rows_c > 0) { c = row / rows_c; r = row % rows_c; }
-                const int dq = rows_c > 0 ? 128 / rows_c : 0, dr = rows_c > 0 ? 128 % rows_c : 0;
+              } else {
+                if (warp_on) {
 #pragma unroll
-                for (int t = 0; t < CH; ++t) {
-                  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                  if (row + t * 128 < n_items) {
-                    const int2 info = rinfo[r];  // (first message row, message count) of combined row r
-                    const uint8_t* src = tile + (size_t)(KXc + c) * 2048 + (size_t)info.x * 16;
-                    for (int e2 = 0; e2 < info.y; ++e2) {
-                      const uint4 mm = *reinterpret_cast<const uint4*>(src + e2 * 16);
-                      const __half2* hp = reinterpret_cast<const __half2*>(&mm);
+                  for (int c = 0; c < CH; ++c)
+                    *reinterpret_cast<uint4*>(s_h2 + (size_t)row * (HD * 2) + ((c ^ (row & 7)) * 16)) =
+                        make_uint4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
+                }
+                wg_sync(s);
+                const int live_tr = max(0, min(Te, Gc - p * Te));  // live trajectories of this pass
+                // phase 1: sums over the N-1 outgoing edges of every node of the pass
+                for (int t = row; t < live_tr * N * CH; t += 128) {
+                  const int a = t / CH, c = t % CH;
+                  const int first = (a / N) * NE + (a % N) * (N - 1);
+                  float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                  for (int e2 = 0; e2 < N - 1; ++e2) {
+                    const int r = first + e2;
+                    add8(acc8, *reinterpret_cast<const uint4*>(s_h2 + (size_t)r * (HD * 2) + ((c ^ (r & 7)) * 16)));
+                  }
+                  *reinterpret_cast<uint4*>(s_agg + (size_t)a * (HD * 2) + ((c ^ (a & 7)) * 16)) = pack8(acc8);
+                }
+                wg_sync(s);
+                // phase 2a: the owner of a node row moves its aggregate into the node tile's A operand (R2)
+                if (__any_sync(FULL, n_p == p && live_n)) {
+                  if (n_p == p) {
+                    const int a = min(n_a, Te * N - 1);
 #pragma unroll
-                      for (int t2 = 0; t2 < 4; ++t2) {
-                        const float2 f = __half22float2(hp[t2]);
-                        acc[2 * t2] += f.x;
-                        acc[2 * t2 + 1] += f.y;
-                      }
+                    for (int c = 0; c < CH; ++c) {
+                      const uint4 v = *reinterpret_cast<const uint4*>(s_agg + (size_t)a * (HD * 2) + ((c ^ (a & 7)) * 16));
+                      hreg[4 * c] = v.x; hreg[4 * c + 1] = v.y; hreg[4 * c + 2] = v.z; hreg[4 * c + 3] = v.w;
                     }
-                    const float sc = info.y == NE ? inv_glob : inv_node;  // N-1 != N(N-1) for every N >= 2
-#pragma unroll
-                    for (int t2 = 0; t2 < 8; ++t2) acc[t2] *= sc;
                   }
-                  outv[t].x = pack_half2(acc[0], acc[1]);
-                  outv[t].y = pack_half2(acc[2], acc[3]);
-                  outv[t].z = pack_half2(acc[4], acc[5]);
-                  outv[t].w = pack_half2(acc[6], acc[7]);
-                  c += dq; r += dr;
-                  if (r >= rows_c && rows_c > 0) { r -= rows_c; c += 1; }
+                  // tcgen05.st is warp wide: lanes that belong to other passes re-write what R2 already holds
+                  uint32_t cur[HD / 2];
+#pragma unroll
+                  for (int c0 = 0; c0 < HD / 2; c0 += 32) tmem_ld32(t_r2 + c0, *reinterpret_cast<uint32_t(*)[32]>(&cur[c0]));
+                  tmem_wait_ld();
+                  if (n_p != p) {
+#pragma unroll
+                    for (int j = 0; j < HD / 2; ++j) hreg[j] = cur[j];
+                  }
+                  store_hidden<HD>(t_r2, hreg);
+                }
+                // phase 2b: sum over all edges of a trajectory = sum of its node sums
+                for (int t = row; t < live_tr * CH; t += 128) {
+                  const int bl = t / CH, c = t % CH;
+                  float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                  for (int i2 = 0; i2 < N; ++i2) {
+                    const int a = bl * N + i2;
+                    add8(acc8, *reinterpret_cast<const uint4*>(s_agg + (size_t)a * (HD * 2) + ((c ^ (a & 7)) * 16)));
+                  }
+                  const int b = p * Te + bl;
+                  *reinterpret_cast<uint4*>(s_glob + (size_t)b * (HD * 2) + ((c ^ (b & 7)) * 16)) = pack8(acc8);
                 }
               }
-              wg_sync(s);
-              {
-                int c = 0, r = row;
-                if (rows_c > 0) { c = row / rows_c; r = row % rows_c; }
-                const int dq = rows_c > 0 ? 128 / rows_c : 0, dr = rows_c > 0 ? 128 % rows_c : 0;
-#pragma unroll
-                for (int t = 0; t < CH; ++t) {
-                  if (row + t * 128 < n_items) *reinterpret_cast<uint4*>(tile + (size_t)(KXc + c) * 2048 + r * 16) = outv[t];
-                  c += dq; r += dr;
-                  if (r >= rows_c && rows_c > 0) { r -= rows_c; c += 1; }
-                }
-              }
-              // ---- combined tile, [x_i | agent | action | 0] part (global rows: x_i = 0)  gnn_modules.py:213-223,250-254 ----
-              if (live_c) {
-                const __half* sb = snrm + cb * SN;
-                for (int c = 0; c < KXc; ++c) {
-                  __align__(16) __half tmp[8];
-#pragma unroll
-                  for (int t = 0; t < 8; ++t) {
-                    const int k = c * 8 + t;
-                    __half v = __float2half_rn(0.f);
-                    if (k < NA) { if (!is_glob) v = sb[A + U + ci * NA + k]; }
-                    else if (k < NA + A) v = sb[k - NA];
-                    else if (k < NA + A + U) v = sb[A + (k - NA - A)];
-                    tmp[t] = v;
-                  }
-                  *reinterpret_cast<uint4*>(tile + (size_t)c * 2048 + row * 16) = *reinterpret_cast<const uint4*>(tmp);
-                }
+              stamp(40 + kind);
+              // next A operand: the following edge pass, or the x part of the node tile
+              if (p + 1 < n_pass) {
+                build_edge(p + 1);
+              } else {
+                const uint4* sb = reinterpret_cast<const uint4*>(snrm + min(n_b, T - 1) * SNs);
+                int col = 0;
+                for (int c = 0; c < AUp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[c]);
+                for (int c = 0; c < NAp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[(AUp + n_i * NAp) / 8 + c]);
+                for (; col < tl.KXn / 2; col += 4) tmem_st4(t_r1 + col, make_uint4(0u, 0u, 0u, 0u));
               }
             }
-            stamp(40 + st);
             signal_a(cx, s, lane);
-            stamp(50 + st);
-          } else if (warp_on) {
-            // ---- output layers: deltas -> de-normalise, residual update (gnn_ensemble.py:302-334, 935-939) ----
-            uint32_t v[16];
-            tmem_ld16(tm_row + (has_n ? 0 : HD), v);
-            tmem_wait_ld();
-            if (has_n && has_g) {
-              uint32_t w[16];
-              tmem_ld16(tm_row + HD, w);
+          } else if (kind == TC_N3) {
+            // ------------------ node output: delta -> de-normalise, residual update (gnn_ensemble.py:302-334, 935-939) ------------------
+            if (__any_sync(FULL, live_n)) {
+              uint32_t v[16];
+              tmem_ld16(t_acc, v);
               tmem_wait_ld();
+              if (live_n) {
+                const float* pb = sPar + m.par_bias;
+                __half* dst = snrm + n_b * SNs + AUp + n_i * NAp;
+                float* og = outp + (size_t)n_b * O + A + n_i * D;
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (is_glob) v[j] = w[j];
+                for (int j = 0; j < 16; ++j)
+                  if (j < D) {
+                    const float dl = __uint_as_float(v[j]) + pb[j];
+                    dyn[j] += fmaf(nrm[md.nrm.out_dyn + D + j], dl, nrm[md.nrm.out_dyn + j]);
+                    og[j] = dyn[j];
+                    dst[j] = __float2half_rn((dyn[j] - nrm[md.nrm.in_dyn + j]) * nrm[md.nrm.in_dyn + D + j]);
+                  }
+              }
             }
-            if (live_c) {
-              const float* pb = par(is_glob ? 8 : 5, 0);
-              const int nout = is_glob ? A : D;
-              const int so = is_glob ? md.nrm.out_agent : md.nrm.out_dyn;
-              float* dst = sraw + cb * sd + (is_glob ? 0 : A + ci * D);
+            // A operand of the global tile: [hdr | 0] -> R1, sum over all edges -> R2
+            {
+              const int b = min(row, T - 1);
+              const uint4* sb = reinterpret_cast<const uint4*>(snrm + b * SNs);
+              int col = 0;
+              for (int c = 0; c < AUp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[c]);
+              for (; col < tl.KXg / 2; col += 4) tmem_st4(t_r1 + col, make_uint4(0u, 0u, 0u, 0u));
+              uint32_t hreg[HD / 2];
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < nout) {
-                  const float dl = __uint_as_float(v[j]) + pb[j];
-                  dst[j] += fmaf(__ldg(nrm + so + nout + j), dl, __ldg(nrm + so + j));
+              for (int c = 0; c < CH; ++c) {
+                const uint4 g4 = *reinterpret_cast<const uint4*>(s_glob + (size_t)b * (HD * 2) + ((c ^ (b & 7)) * 16));
+                hreg[4 * c] = g4.x; hreg[4 * c + 1] = g4.y; hreg[4 * c + 2] = g4.z; hreg[4 * c + 3] = g4.w;
+              }
+              store_hidden<HD>(t_r2, hreg);
+            }
+            signal_a(cx, s, lane);
+          } else {
+            // ------------------ global output: agent delta, next action, trailing observation part ------------------
+            if (__any_sync(FULL, live_g)) {
+              uint32_t v[16];
+              tmem_ld16(t_acc, v);
+              tmem_wait_ld();
+              if (live_g) {
+                const float* pb = sPar + m.par_bias;
+                __half* dst = snrm + row * SNs;
+                float* og = outp + (size_t)row * O;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (j < A) {
+                    const float dl = __uint_as_float(v[j]) + pb[j];
+                    agent[j] += fmaf(nrm[md.nrm.out_agent + A + j], dl, nrm[md.nrm.out_agent + j]);
+                    og[j] = agent[j];
+                    dst[j] = __float2half_rn((agent[j] - nrm[md.nrm.in_agent + j]) * nrm[md.nrm.in_agent + A + j]);
+                  }
+                if (h + 1 < ra.H) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (j < U)
+                      dst[A + j] = __float2half_rn((act_next[j] - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]);
                 }
+              }
             }
+            tc_fence_before();
           }
         }
-        tc_fence_before();
-        wg_sync(s);
+        // trailing part of the observation (static features + goal, env.obs_postproc): constant along the horizon
+        for (int idx = row; idx < Gc * tail; idx += 128) {
+          const int b = idx / tail, c = idx % tail;
+          outp[(size_t)b * O + (sd - N * S) + c] = s_tail[idx];
+        }
+        wg_sync(s);  // snrm of the next step is complete
         stamp(60);
-        // ---- emit traj[h+1] = [state | goal] (env.obs_postproc) ----
-        {
-          float* outp = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
-          for (int idx = row; idx < Gc * O; idx += 128) {
-            const int b = idx / O, c = idx % O;
-            outp[idx] = c < sd ? sraw[b * sd + c] : __ldg(ra.goal + (size_t)((p0 + b) / ra.traj_per_goal) * md.G + (c - sd));
-          }
-        }
       }
     }
   }
@@ -485,134 +562,243 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   tc_fence_before();
   __syncthreads();
   cluster_sync();
-  if (warp == 8) tmem_dealloc<2>(cx.tmem_base, 512);
+  if (warp == 8) tmem_dealloc<2>(tmem_base, 512);
 }
 
-// fp32 packed weights (SIMT layout) -> fp16 B-operand images + fp32 parameter blocks
-__global__ void tc_pack_kernel(const float* __restrict__ w32, const ModelDesc md, const TcLayout tl, uint8_t* __restrict__ wimg,
-                               float* __restrict__ wpar) {
+// ---- weight packing ------------------------------------------------------------------------------------------
+__device__ __forceinline__ const LayerDesc& mat_layer(const ModelDesc& md, int m) {
+  switch (m) {
+    case TC_E1: return md.mlp[0].layer[0];
+    case TC_E2: return md.mlp[0].layer[1];
+    case TC_N1: return md.mlp[1].layer[0];
+    case TC_N2: return md.mlp[1].layer[1];
+    case TC_N3: return md.mlp[1].layer[2];
+    case TC_G1: return md.mlp[2].layer[0];
+    case TC_G2: return md.mlp[2].layer[1];
+    default: return md.mlp[2].layer[2];
+  }
+}
+
+// scratch[e][m][k][n] (fp32): the logical B matrix of every stage in tile-K order, with the edge output layer folded into
+// the aggregate rows of N1 / G1, mean-aggregation scales applied and first-layer biases placed in the constant-one row.
+__global__ void tc_logical_kernel(const float* __restrict__ w32, const ModelDesc md, const TcLayout tl, const int* __restrict__ kmap,
+                                  float* __restrict__ scratch) {
   const int e = blockIdx.y;
   const float* wm = w32 + (size_t)e * md.member_stride;
-  const int halves = tl.image_bytes / 2;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * halves; idx += gridDim.x * blockDim.x) {
-    const int rank = idx / halves;
-    const int off_b = (idx % halves) * 2;
-    int m = 0;
-    for (int t = 1; t < 9; ++t)
-      if (off_b >= tl.mat[t].off) m = t;
+  float* out = scratch + (size_t)e * tl.scratch_floats;
+  const LayerDesc& e3 = md.mlp[0].layer[2];
+  const int NE = md.N * (md.N - 1);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tl.scratch_floats; idx += gridDim.x * blockDim.x) {
+    int m = 0, base = 0;
+    for (int t = 0; t < TC_NMAT; ++t) {
+      if (idx >= base + tl.mat[t].K * tl.mat[t].N) base += tl.mat[t].K * tl.mat[t].N;
+      else { m = t; break; }
+    }
     const TcMat& M = tl.mat[m];
-    const int el = (off_b - M.off) / 2;
-    const int c = el / (M.nloc * 8), rem = el % (M.nloc * 8);
-    const int nl = rem / 8, j = rem % 8;
-    const int k = c * 8 + j;
-    const int n = rank * M.nloc + nl;
+    const int k = (idx - base) / M.N, n = (idx - base) % M.N;
+    const LayerDesc& ld = mat_layer(md, m);
+    const int code = kmap[M.kmap_off + k];
+    const bool node = m == TC_N1;
+    const int agg_off = node ? (md.D + md.S + md.A + md.U) : (md.A + md.U);  // first aggregate row of the layer input
+    const float cnt = node ? (float)(md.N - 1) : (float)NE;
     float v = 0.f;
-    const LayerDesc& ld = md.mlp[M.src_mlp].layer[M.src_layer];
-    int ks = -1;
-    if (k >= M.seg_tc[0] && k < M.seg_tc[0] + M.seg_len[0]) ks = M.seg_src[0] + (k - M.seg_tc[0]);
-    else if (k >= M.seg_tc[1] && k < M.seg_tc[1] + M.seg_len[1]) ks = M.seg_src[1] + (k - M.seg_tc[1]);
-    if (ks >= 0 && ks < ld.K && n < ld.N) v = wm[ld.w_off + (size_t)ks * ld.Npad + n];
-    reinterpret_cast<__half*>(wimg + ((size_t)e * 2 + rank) * tl.image_bytes)[off_b / 2] = __float2half_rn(v);
-  }
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tl.par_floats; idx += gridDim.x * blockDim.x) {
-    float v = 0.f;
-    for (int m = 0; m < 9; ++m) {
-      const LayerDesc& ld = md.mlp[tl.mat[m].src_mlp].layer[tl.mat[m].src_layer];
-      for (int w = 0; w < 3; ++w) {
-        const int o = tl.par_off[m][w];
-        if (o >= 0 && idx >= o && idx < o + tl.par_len[m]) {
-          const int j = idx - o;
-          if (j < ld.N) v = wm[(w == 0 ? ld.b_off : w == 1 ? ld.g_off : ld.be_off) + j];
+    if (n < ld.N) {
+      if (code >= kFold) {
+        const int a = code - kFold;
+        float acc = 0.f;
+        for (int c = 0; c < md.Hd; ++c) acc = fmaf(wm[e3.w_off + (size_t)a * e3.Npad + c], wm[ld.w_off + (size_t)(agg_off + c) * ld.Npad + n], acc);
+        v = md.aggr_mean ? acc / cnt : acc;
+      } else if (code == -2) {
+        v = wm[ld.b_off + n];
+        if (m == TC_N1 || m == TC_G1) {
+          float acc = 0.f;
+          for (int c = 0; c < md.Hd; ++c) acc = fmaf(wm[e3.b_off + c], wm[ld.w_off + (size_t)(agg_off + c) * ld.Npad + n], acc);
+          v += md.aggr_mean ? acc : acc * cnt;
         }
+      } else if (code >= 0) {
+        v = wm[ld.w_off + (size_t)code * ld.Npad + n];
       }
     }
-    wpar[(size_t)e * tl.par_floats + idx] = v;
+    out[idx] = v;
+  }
+}
+
+// logical fp32 matrices -> centred (LayerNorm layers) fp16 B-operand images + fp32 parameter blocks
+__global__ void tc_image_kernel(const float* __restrict__ w32, const ModelDesc md, const TcLayout tl, const float* __restrict__ scratch,
+                                uint8_t* __restrict__ wimg, float* __restrict__ wpar) {
+  const int e = blockIdx.y;
+  const float* wm = w32 + (size_t)e * md.member_stride;
+  const float* L = scratch + (size_t)e * tl.scratch_floats;
+  int rows_total = 0;
+  for (int t = 0; t < TC_NMAT; ++t) rows_total += tl.mat[t].K;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < rows_total; idx += gridDim.x * blockDim.x) {
+    int m = 0, rbase = 0, fbase = 0;
+    for (int t = 0; t < TC_NMAT; ++t) {
+      if (idx >= rbase + tl.mat[t].K) { rbase += tl.mat[t].K; fbase += tl.mat[t].K * tl.mat[t].N; }
+      else { m = t; break; }
+    }
+    const TcMat& M = tl.mat[m];
+    const int k = idx - rbase;
+    const float* rowp = L + fbase + (size_t)k * M.N;
+    const int nreal = mat_layer(md, m).N;
+    float mean = 0.f;
+    if (M.ln && md.layer_norm) {
+      for (int n = 0; n < nreal; ++n) mean += rowp[n];
+      mean /= (float)nreal;
+    }
+    for (int n = 0; n < M.N; ++n) {
+      const float v = n < nreal ? rowp[n] - mean : 0.f;
+      const int rk = n / M.nloc, nl = n % M.nloc;
+      uint8_t* img = wimg + ((size_t)e * 2 + rk) * tl.image_bytes;
+      reinterpret_cast<__half*>(img + M.off)[((size_t)(k / 8) * M.nloc + nl) * 8 + (k % 8)] = __float2half_rn(v);
+    }
+  }
+  // parameter block
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < TC_NMAT * 3 * 128; idx += gridDim.x * blockDim.x) {
+    const int m = idx / (3 * 128), w = (idx / 128) % 3, j = idx % 128;
+    const TcMat& M = tl.mat[m];
+    const LayerDesc& ld = mat_layer(md, m);
+    const int off = w == 0 ? M.par_bias : w == 1 ? M.par_gamma : M.par_beta;
+    const int len = (m == TC_N3 || m == TC_G3) ? 16 : tl.HD;
+    if (off < 0 || j >= len) continue;
+    float v = 0.f;
+    if (j < ld.N) {
+      if (w == 0) {
+        v = wm[ld.b_off + j];
+        if (M.ln && md.layer_norm) {
+          float mean = 0.f;
+          for (int n = 0; n < ld.N; ++n) mean += wm[ld.b_off + n];
+          v -= mean / (float)ld.N;
+        }
+      } else {
+        v = wm[(w == 1 ? ld.g_off : ld.be_off) + j];
+      }
+    }
+    wpar[(size_t)e * tl.par_floats + off + j] = v;
   }
 }
 
 }  // namespace
 
-bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out) {
+bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_host) {
   TcLayout t{};
   if (md.kind != CEEUS_MODEL_GNN || (md.Hd != 64 && md.Hd != 128) || md.L != 2) return false;
-  if (md.D > 16 || md.A > 16) return false;
-  const int NA = md.D + md.S, NE = md.N * (md.N - 1);
-  t.HD = md.Hd;
-  t.KE1 = round_up(2 * NA + md.A + md.U, 16);
-  t.KX = round_up(NA + md.A + md.U, 16);
-  if (t.KE1 > md.Hd) return false;  // the edge tile's layer-1 input shares the K = HD chunk range
-  const int Hd = md.Hd;
-  t.T_r = 128 / NE < 128 / (md.N + 1) ? 128 / NE : 128 / (md.N + 1);
-  if (t.T_r < 1) return false;
-  auto mat = [&](int m, int K, int N, int mlp, int layer) {
-    t.mat[m].K = K; t.mat[m].N = N; t.mat[m].nloc = N / 2; t.mat[m].src_mlp = mlp; t.mat[m].src_layer = layer;
-    t.mat[m].seg_tc[0] = 0; t.mat[m].seg_len[0] = K; t.mat[m].seg_src[0] = 0;
-    t.mat[m].seg_tc[1] = 0; t.mat[m].seg_len[1] = 0; t.mat[m].seg_src[1] = 0;
+  if (md.D > 16 || md.A > 16 || md.U > 8 || md.N < 2) return false;
+  const int N = md.N, NA = md.D + md.S, NE = N * (N - 1), Hd = md.Hd;
+  t.HD = Hd;
+  t.AUp = round_up(md.A + md.U + 1, 8);
+  t.NAp = round_up(NA, 8);
+  t.SNs = t.AUp + N * t.NAp;
+  t.KE1 = round_up(t.AUp + 2 * t.NAp, 16);
+  t.KXn = round_up(t.AUp + t.NAp, 16);
+  t.KXg = round_up(t.AUp, 16);
+  if (t.KE1 > Hd || NE > 128) return false;  // R1 holds the edge input (KE1/2 columns) and the hidden row (Hd/2)
+  t.Te = 128 / NE;
+  if (N == 2) {
+    t.q_n = 32; t.n_pass_max = 1; t.Tmax = t.Te;
+  } else {
+    t.q_n = (t.Te * N + 3) / 4;
+    t.n_pass_max = 32 / t.q_n;
+    if (t.n_pass_max < 1) return false;
+    t.Tmax = t.n_pass_max * t.Te;
+  }
+  if (t.Tmax > 128) t.Tmax = 128;
+  t.tail = N * md.S + md.G;
+  auto mat = [&](int m, int kx, int kagg, int n, int lnf) {
+    t.mat[m].K = kx + kagg; t.mat[m].kx = kx; t.mat[m].N = n; t.mat[m].nloc = n / 2; t.mat[m].ln = lnf;
   };
-  mat(0, t.KE1, Hd, 0, 0); t.mat[0].seg_len[0] = 2 * NA + md.A + md.U;
-  mat(1, Hd, Hd, 0, 1);
-  mat(2, Hd, Hd, 0, 2);
-  mat(3, t.KX + Hd, Hd, 1, 0);
-  t.mat[3].seg_len[0] = NA + md.A + md.U;
-  t.mat[3].seg_tc[1] = t.KX; t.mat[3].seg_len[1] = Hd; t.mat[3].seg_src[1] = NA + md.A + md.U;
-  mat(4, Hd, Hd, 1, 1);
-  mat(5, Hd, 16, 1, 2);
-  mat(6, t.KX + Hd, Hd, 2, 0);
-  t.mat[6].seg_tc[0] = NA; t.mat[6].seg_len[0] = md.A + md.U; t.mat[6].seg_src[0] = 0;
-  t.mat[6].seg_tc[1] = t.KX; t.mat[6].seg_len[1] = Hd; t.mat[6].seg_src[1] = md.A + md.U;
-  mat(7, Hd, Hd, 2, 1);
-  mat(8, Hd, 16, 2, 2);
-  int off = 0;
-  for (int m = 0; m < 9; ++m) {
-    t.mat[m].off = off;
-    off += (t.mat[m].K / 8) * t.mat[m].nloc * 16;
+  mat(TC_E1, t.KE1, 0, Hd, 1);
+  mat(TC_E2, Hd, 0, Hd, 1);
+  mat(TC_N1, t.KXn, Hd, Hd, 1);
+  mat(TC_N2, Hd, 0, Hd, 1);
+  mat(TC_N3, Hd, 0, 16, 0);
+  mat(TC_G1, t.KXg, Hd, Hd, 1);
+  mat(TC_G2, Hd, 0, Hd, 1);
+  mat(TC_G3, Hd, 0, 16, 0);
+  int off = 0, po = 0, ko = 0, sf = 0;
+  for (int m = 0; m < TC_NMAT; ++m) {
+    TcMat& M = t.mat[m];
+    M.off = off;
+    off += (M.K / 8) * M.nloc * 16;
+    M.kmap_off = ko;
+    ko += M.K;
+    sf += M.K * M.N;
+    const bool first = m == TC_E1 || m == TC_N1 || m == TC_G1;
+    const bool outl = m == TC_N3 || m == TC_G3;
+    M.par_bias = -1; M.par_gamma = -1; M.par_beta = -1;
+    if (!first) { M.par_bias = po; po += outl ? 16 : Hd; }
+    if (!outl) { M.par_gamma = po; po += Hd; M.par_beta = po; po += Hd; }
   }
   t.image_bytes = off;
-  int po = 0;
-  for (int m = 0; m < 9; ++m) {
-    const bool hidden = (m % 3) != 2;
-    t.par_len[m] = (m == 5 || m == 8) ? 16 : Hd;
-    t.par_off[m][0] = po; po += t.par_len[m];
-    if (hidden) {
-      t.par_off[m][1] = po; po += Hd;
-      t.par_off[m][2] = po; po += Hd;
-    } else {
-      t.par_off[m][1] = t.par_off[m][2] = -1;
-    }
-  }
   t.par_floats = po;
-  // shared memory carve-up
-  int sm = 0;
-  t.sm_w = sm; sm += round_up(t.image_bytes, 1024);
-  const int slot_bytes = (t.KX + Hd) / 8 * 2048;
-  t.sm_slot[0] = sm; sm += slot_bytes;
-  t.sm_slot[1] = sm; sm += slot_bytes;
-  t.sm_par = sm; sm += round_up(t.par_floats * 4, 16);
-  t.sraw_bytes = round_up(t.T_r * md.sd * 4, 16);
-  const int snrm_bytes = round_up(t.T_r * (md.A + md.U + md.N * NA) * 2, 16);
-  t.sm_state[0] = sm; sm += t.sraw_bytes + snrm_bytes;
-  t.sm_state[1] = sm; sm += t.sraw_bytes + snrm_bytes;
-  t.sm_rinfo = sm; sm += 2 * 128 * 8;
-  t.sm_bar = sm; sm += 64;
-  t.smem_bytes = sm;
-  if (t.smem_bytes > 227 * 1024) return false;
-  const int pairs = num_sms / 2;
-  t.ppm = pairs / md.E;
-  if (t.ppm < 1) return false;
+  t.kmap_len = ko;
+  t.scratch_floats = sf;
+  if (kmap_host) {
+    for (int i = 0; i < ko; ++i) kmap_host[i] = -1;
+    const int A = md.A, U = md.U;
+    // header [agent | action | 1]: the reference orders the layer inputs edge [x_i, x_j, agent, action] (gnn_modules.py:123-127),
+    // node [x_i, agent, action, agg] (:213-223), global [agent, action, agg] (:250-254)
+    auto hdr = [&](int m, int src_agent) {
+      int* km = kmap_host + t.mat[m].kmap_off;
+      for (int k = 0; k < A + U; ++k) km[k] = src_agent + k;
+      km[A + U] = -2;
+    };
+    hdr(TC_E1, 2 * NA);
+    for (int f = 0; f < NA; ++f) {
+      kmap_host[t.mat[TC_E1].kmap_off + t.AUp + f] = f;
+      kmap_host[t.mat[TC_E1].kmap_off + t.AUp + t.NAp + f] = NA + f;
+    }
+    hdr(TC_N1, NA);
+    for (int f = 0; f < NA; ++f) kmap_host[t.mat[TC_N1].kmap_off + t.AUp + f] = f;
+    for (int c = 0; c < Hd; ++c) kmap_host[t.mat[TC_N1].kmap_off + t.KXn + c] = kFold + c;
+    hdr(TC_G1, 0);
+    for (int c = 0; c < Hd; ++c) kmap_host[t.mat[TC_G1].kmap_off + t.KXg + c] = kFold + c;
+    for (int m : {TC_E2, TC_N2, TC_N3, TC_G2, TC_G3})
+      for (int k = 0; k < Hd; ++k) kmap_host[t.mat[m].kmap_off + k] = k;
+  }
+  // shared memory carve-up; the group size shrinks (fewer edge passes per group) until two slots fit
+  for (;;) {
+    int sm = 0;
+    t.sm_w = sm; sm += round_up(t.image_bytes, 1024);
+    t.sm_par = sm; sm += round_up(t.par_floats * 4, 16);
+    t.nrm_floats = md.nrm.out_dyn + 2 * md.D;
+    t.sm_nrm = sm; sm += round_up(t.nrm_floats * 4, 16);
+    int so = 0;
+    t.so_h2 = so; so += N == 2 ? 0 : 128 * Hd * 2;
+    t.so_agg = so; so += N == 2 ? 0 : round_up(t.Te * N, 8) * Hd * 2;
+    t.so_glob = so; so += round_up(t.Tmax, 8) * Hd * 2;
+    t.so_snrm = so; so += round_up(t.Tmax * t.SNs * 2, 16);
+    t.so_tail = so; so += round_up(t.Tmax * t.tail * 4, 16);
+    so = round_up(so, 128);
+    t.sm_slot[0] = sm; sm += so;
+    t.sm_slot[1] = sm; sm += so;
+    t.sm_bar = sm; sm += 64;
+    t.smem_bytes = sm;
+    if (t.smem_bytes <= 227 * 1024) break;
+    if (N == 2 || t.n_pass_max <= 1) return false;
+    t.n_pass_max -= 1;
+    t.Tmax = t.n_pass_max * t.Te;
+  }
+  t.pairs = num_sms / 2;
+  if (t.pairs < md.E) return false;
   *out = t;
   return true;
 }
 
-cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, uint8_t* wimg, float* wpar, cudaStream_t st) {
-  dim3 grid(64, md.E);
-  tc_pack_kernel<<<grid, 256, 0, st>>>(w32, md, tl, wimg, wpar);
+cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, const int* kmap_dev, float* scratch,
+                           uint8_t* wimg, float* wpar, cudaStream_t st) {
+  dim3 grid(128, md.E);
+  tc_logical_kernel<<<grid, 256, 0, st>>>(w32, md, tl, kmap_dev, scratch);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  tc_image_kernel<<<dim3(16, md.E), 256, 0, st>>>(w32, md, tl, scratch, wimg, wpar);
   return cudaGetLastError();
 }
 
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                   const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
   cudaError_t e;
-  const dim3 grid(2 * tl.ppm * md.E);
+  const dim3 grid(2 * tl.pairs);
   if (md.Hd == 128) {
     e = cudaFuncSetAttribute(rollout_gnn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
     if (e != cudaSuccess) return e;

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(160, 1) umma_probe_kernel(const __half* __rest
   fence_proxy_async();
   uint32_t ncols = 32;
   while ((int)ncols < N) ncols <<= 1;
+  if (variant & 2) ncols = 512;
   if (warp == 4) {
     if (lane == 0) {
       mbar_init(bar, 1);
@@ -55,6 +56,25 @@ __global__ void __launch_bounds__(160, 1) umma_probe_kernel(const __half* __rest
   if (CG == 2) cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool a_in_tmem = (variant & 2) != 0;
+  const uint32_t a_col0 = 256;  // TS variant: A tile lives in TMEM columns [256, 256 + K/2), two fp16 per 32-bit cell
+  if (a_in_tmem) {
+    if (warp < 4) {
+      const __half* arow = A + (size_t)(rank * 128 + warp * 32 + lane) * K;
+      for (int ks = 0; ks < K / 16; ++ks) {
+        uint32_t v[8];
+        const uint4 lo = *reinterpret_cast<const uint4*>(arow + ks * 16);
+        const uint4 hi = *reinterpret_cast<const uint4*>(arow + ks * 16 + 8);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        tmem_st8(tmem_base + ((uint32_t)(warp * 32) << 16) + a_col0 + ks * 8, v);
+      }
+      tmem_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync();
+    tc_fence_after();
+  }
 
   if (warp == 4 && lane == 0 && rank == 0) {
     uint32_t lbo_a = 2048, sbo_a = 128, lbo_b = nloc * 16, sbo_b = 128;
@@ -66,7 +86,8 @@ __global__ void __launch_bounds__(160, 1) umma_probe_kernel(const __half* __rest
     for (int ks = 0; ks < K / 16; ++ks) {
       const uint64_t da = make_smem_desc(smem_u32(sA) + ks * 2 * 2048, lbo_a, sbo_a);
       const uint64_t db = make_smem_desc(smem_u32(sB) + ks * 2 * nloc * 16, lbo_b, sbo_b);
-      umma_f16_ss<CG>(tmem_base, da, db, idesc, ks > 0 ? 1u : 0u);
+      if (a_in_tmem) umma_f16_ts<CG>(tmem_base, tmem_base + a_col0 + ks * 8, db, idesc, ks > 0 ? 1u : 0u);
+      else umma_f16_ss<CG>(tmem_base, da, db, idesc, ks > 0 ? 1u : 0u);
     }
     if (CG == 1) umma_commit_cg1(bar);
     else umma_commit_cg2_mc(bar, 0x3);

@@ -31,3 +31,12 @@ def test_umma_tile_matches_gemm(cg, K, N):
     assert rc == 0 and st == 0, (rc, st)
     err = (D - want).abs().max().item()
     assert err < 2e-3 * max(1.0, want.abs().max().item()), err
+
+
+@pytest.mark.parametrize("cg,K,N", [(1, 128, 128), (1, 48, 64), (2, 128, 128), (2, 160, 128), (2, 48, 128), (2, 128, 16)])
+def test_umma_tile_a_from_tmem(cg, K, N):
+    """TS mode: the A operand is written to TMEM by the epilogue threads (tcgen05.st) instead of shared memory."""
+    rc, st, D, want = run_probe(cg, K, N, variant=2)
+    assert rc == 0 and st == 0, (rc, st)
+    err = (D - want).abs().max().item()
+    assert err < 2e-3 * max(1.0, want.abs().max().item()), err
