@@ -32,7 +32,8 @@ namespace ceeus {
 namespace {
 using namespace tc;
 
-constexpr int kTcThreads = 320;  // 2 epilogue warpgroups + 2 MMA-issuer warps (warp 8 also does the set-up)
+constexpr int kTcThreads = 256;  // 2 warpgroups; warp 0 of each also issues its slot's MMAs (leader CTA): no dedicated issuer
+                                 // warps, so ptxas may use 255 registers per thread and batch the parameter loads
 constexpr uint32_t FULL = 0xffffffffu;
 constexpr int kFold = 100000;    // kmap code >= kFold: folded aggregate row (index code - kFold)
 
@@ -68,7 +69,6 @@ __device__ __forceinline__ bool wait_bar(const Ctx& cx, uint64_t* bar, uint32_t 
 __device__ __forceinline__ void signal_a(const Ctx& cx, int s, int lane) {
   tmem_wait_st();
   tc_fence_before();
-  __threadfence_block();  // shared-memory staging written by this thread is read by CTA-local threads behind the barrier chain
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster_relaxed(cx.a_ready_leader[s]);
 }
@@ -86,49 +86,85 @@ __device__ __forceinline__ void store_hidden(uint32_t taddr, const uint32_t (&h)
   for (int c0 = 0; c0 < HD / 2; c0 += 32) tmem_st32(taddr + c0, *reinterpret_cast<const uint32_t(*)[32]>(&h[c0]));
 }
 
-// bias + LayerNorm (second moment only: the weights are centred) + activation on the accumulator row -> packed fp16
-template <int HD>
-__device__ __forceinline__ void epi_hidden(uint32_t tacc, const float* __restrict__ pb, const float* __restrict__ pg,
-                                           const float* __restrict__ pbe, bool ln, int act, uint32_t (&h)[HD / 2]) {
-  float x[HD];
-  load_acc<HD>(tacc, x);
-  tmem_wait_ld();
-  if (pb != nullptr) {
+// One 32-column chunk of the accumulator row: (+ bias) and either the second-moment accumulation (pass 1) or
+// LayerNorm scale / shift + activation + fp16 packing (pass 2).
+__device__ __forceinline__ void chunk_bias(float (&x)[32], const float* __restrict__ pb) {
+  float4 b[8];
 #pragma unroll
-    for (int j = 0; j < HD; j += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(pb + j);
-      x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+  for (int j = 0; j < 8; ++j) b[j] = *reinterpret_cast<const float4*>(pb + 4 * j);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { x[4 * j] += b[j].x; x[4 * j + 1] += b[j].y; x[4 * j + 2] += b[j].z; x[4 * j + 3] += b[j].w; }
+}
+__device__ __forceinline__ void chunk_moment(const float (&x)[32], float (&v8)[8]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v8[j & 7] = fmaf(x[j], x[j], v8[j & 7]);
+}
+template <bool RELU>
+__device__ __forceinline__ void chunk_finish(float (&x)[32], const float* __restrict__ pg, const float* __restrict__ pbe, bool ln,
+                                             float rstd, int act, uint32_t (&hc)[16]) {
+  if (ln) {
+    float4 g[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { g[j] = *reinterpret_cast<const float4*>(pg + 4 * j); be[j] = *reinterpret_cast<const float4*>(pbe + 4 * j); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[4 * j] = fmaf(x[4 * j] * rstd, g[j].x, be[j].x); x[4 * j + 1] = fmaf(x[4 * j + 1] * rstd, g[j].y, be[j].y);
+      x[4 * j + 2] = fmaf(x[4 * j + 2] * rstd, g[j].z, be[j].z); x[4 * j + 3] = fmaf(x[4 * j + 3] * rstd, g[j].w, be[j].w);
     }
   }
+  if constexpr (RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) hc[j / 2] = pack_half2_relu(x[j], x[j + 1]);
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < 32; j += 2) hc[j / 2] = pack_half2(act_fn(x[j], act), act_fn(x[j + 1], act));
+  }
+}
+
+// bias + LayerNorm (second moment only: the weights are centred) + activation on the accumulator row -> packed fp16,
+// handed to `sink(c0, hc)` 32 columns (16 packed registers) at a time.  Two passes over the accumulator (TMEM reads are
+// cheap: ~140 cycles latency, > 1 KB/clk per SM); the next chunk's tcgen05.ld is in flight while the current one is
+// processed, and only 64 fp32 values are live, so the parameter loads of a chunk are issued together.  The chunk loop is
+// NOT unrolled beyond the buffer pair and there is exactly one call site: the hot code must stay inside the
+// instruction cache (the fully unrolled version was 800 KB of SASS and stalled on instruction fetch).
+template <int HD, bool RELU, class Sink>
+__device__ __forceinline__ void epi_hidden(uint32_t tacc, const float* __restrict__ pb, const float* __restrict__ pg,
+                                           const float* __restrict__ pbe, bool ln, int act, Sink&& sink) {
+  constexpr int NC = HD / 32;
+  static_assert(NC % 2 == 0, "chunk pairs");
+  float xa[32], xb[32];
+  float rstd = 1.f;
   if (ln) {
     float v8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < HD; j += 8) {
-#pragma unroll
-      for (int t = 0; t < 8; ++t) v8[t] = fmaf(x[j + t], x[j + t], v8[t]);
+    tmem_ld32(tacc, *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
+#pragma unroll 1
+    for (int k = 0; k < NC; k += 2) {
+      tmem_wait_ld();
+      tmem_ld32(tacc + 32 * (k + 1), *reinterpret_cast<uint32_t(*)[32]>(&xb[0]));
+      if (pb != nullptr) chunk_bias(xa, pb + 32 * k);
+      chunk_moment(xa, v8);
+      tmem_wait_ld();
+      if (k + 2 < NC) tmem_ld32(tacc + 32 * (k + 2), *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
+      if (pb != nullptr) chunk_bias(xb, pb + 32 * (k + 1));
+      chunk_moment(xb, v8);
     }
     const float v = ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
-    const float rstd = rsqrtf(v * (1.f / HD) + 1e-5f);
-    if (act == CEEUS_ACT_RELU) {
-#pragma unroll
-      for (int j = 0; j < HD; j += 4) {
-        const float4 g = *reinterpret_cast<const float4*>(pg + j);
-        const float4 be = *reinterpret_cast<const float4*>(pbe + j);
-        h[j / 2] = pack_half2_relu(fmaf(x[j] * rstd, g.x, be.x), fmaf(x[j + 1] * rstd, g.y, be.y));
-        h[j / 2 + 1] = pack_half2_relu(fmaf(x[j + 2] * rstd, g.z, be.z), fmaf(x[j + 3] * rstd, g.w, be.w));
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < HD; j += 4) {
-        const float4 g = *reinterpret_cast<const float4*>(pg + j);
-        const float4 be = *reinterpret_cast<const float4*>(pbe + j);
-        h[j / 2] = pack_half2(act_fn(fmaf(x[j] * rstd, g.x, be.x), act), act_fn(fmaf(x[j + 1] * rstd, g.y, be.y), act));
-        h[j / 2 + 1] = pack_half2(act_fn(fmaf(x[j + 2] * rstd, g.z, be.z), act), act_fn(fmaf(x[j + 3] * rstd, g.w, be.w), act));
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < HD; j += 2) h[j / 2] = pack_half2(act_fn(x[j], act), act_fn(x[j + 1], act));
+    rstd = rsqrtf(v * (1.f / HD) + 1e-5f);
+  }
+  uint32_t hc[16];
+  tmem_ld32(tacc, *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
+#pragma unroll 1
+  for (int k = 0; k < NC; k += 2) {
+    tmem_wait_ld();
+    tmem_ld32(tacc + 32 * (k + 1), *reinterpret_cast<uint32_t(*)[32]>(&xb[0]));
+    if (pb != nullptr) chunk_bias(xa, pb + 32 * k);
+    chunk_finish<RELU>(xa, pg + 32 * k, pbe + 32 * k, ln, rstd, act, hc);
+    sink(32 * k, hc);
+    tmem_wait_ld();
+    if (k + 2 < NC) tmem_ld32(tacc + 32 * (k + 2), *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
+    if (pb != nullptr) chunk_bias(xb, pb + 32 * (k + 1));
+    chunk_finish<RELU>(xb, pg + 32 * (k + 1), pbe + 32 * (k + 1), ln, rstd, act, hc);
+    sink(32 * (k + 1), hc);
   }
 }
 
@@ -151,7 +187,7 @@ __device__ __forceinline__ uint4 pack8(const float (&acc)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int HD>
+template <int HD, bool RELU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     rollout_gnn_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcLayout tl, const uint8_t* __restrict__ wimg,
                           const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg) {
@@ -188,7 +224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 
   // ---- one-time setup ----
   if (tid == 0) *abort_flag = 0;
-  if (warp == 8) {
+  if (warp == 0) {
     if (lane == 0) {
       mbar_init(wbar, 1);
       mbar_init(&a_ready[0], 8);
@@ -216,7 +252,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   __syncthreads();
   Ctx cx;
   cx.abort = abort_flag; cx.err = err;
-  if (warp == 8 && lane == 0) wait_bar(cx, wbar, 0, 1);  // this CTA's weight image has landed
+  if (warp == 0 && lane == 0) wait_bar(cx, wbar, 0, 1);  // this CTA's weight image has landed
   __syncthreads();
   cluster_sync();  // both CTAs: barriers initialised, TMEM allocated, weights resident
   tc_fence_after();
@@ -224,44 +260,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   cx.a_ready_leader[0] = mapa(smem_u32(&a_ready[0]), 0);
   cx.a_ready_leader[1] = mapa(smem_u32(&a_ready[1]), 0);
 
-  if (warp >= 8) {
-    // =========================== MMA issuers (leader CTA): warp 8 -> slot 0, warp 9 -> slot 1 ===========================
-    if (rank == 0 && lane == 0) {
-      const int s = warp - 8;
-      const uint32_t idesc_h = make_idesc_f16(256, HD);
-      const uint32_t idesc_o = make_idesc_f16(256, 16);
-      const uint32_t wbase = smem_u32(sW);
-      const uint32_t acc = tmem_base + (uint32_t)(s * 2 * HD);
-      const uint32_t r1 = acc + HD, r2 = r1 + HD / 2;
-      // K steps [k0, k1) of matrix m with the A operand at TMEM columns a_col + 8 * (ks - k0)
-      auto issue = [&](const TcMat& m, int k0, int k1, uint32_t a_col, uint32_t idesc, bool first) {
-        const uint32_t lbo_b = (uint32_t)m.nloc * 16;
-#pragma unroll 1
-        for (int ks = k0; ks < k1; ++ks) {
-          const uint64_t db = make_smem_desc(wbase + (uint32_t)m.off + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
-          umma_f16_ts<2>(acc, a_col + (uint32_t)(8 * (ks - k0)), db, idesc, (first && ks == k0) ? 0u : 1u);
-        }
-      };
-      uint32_t ph = 0;
-      const int total = rounds * ra.H;
-#pragma unroll 1
-      for (int it = 0; it < total; ++it) {
-#pragma unroll 1
-        for (int st = 0; st < n_stage; ++st) {
-          if (!wait_bar(cx, &a_ready[s], ph, 2)) { it = total; break; }
-          ph ^= 1u;
-          tc_fence_after();
-          const int kind = st < 2 * n_pass ? (st & 1) : 2 + (st - 2 * n_pass);
-          const TcMat& m = tl.mat[kind];
-          const int kx = m.kx / 16, kall = m.K / 16;
-          const uint32_t idesc = (kind == TC_N3 || kind == TC_G3) ? idesc_o : idesc_h;
-          issue(m, 0, kx, r1, idesc, true);
-          if (kall > kx) issue(m, kx, kall, r2, idesc, kx == 0);
-          umma_commit_cg2_mc(&d_ready[s], 0x3);
-        }
-      }
-    }
-  } else {
+  {
     // =========================== warpgroup: tile builder + epilogue ===========================
     const int s = warp >> 2;       // slot
     const int q = warp & 3;        // TMEM lane quadrant
@@ -280,6 +279,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 2 * HD);
     const uint32_t t_acc = lane_base, t_r1 = lane_base + HD, t_r2 = lane_base + HD + HD / 2;
     uint32_t dph = 0;
+    // ---- MMA issue: warp 0 of the warpgroup in the leader CTA waits for both CTAs' A operands and issues the stage ----
+    const bool issuer_warp = rank == 0 && q == 0;
+    uint32_t aph = 0;
+    const uint32_t idesc_h = make_idesc_f16(256, HD);
+    const uint32_t idesc_o = make_idesc_f16(256, 16);
+    const uint32_t wbase = smem_u32(sW);
+    const uint32_t m_acc = tmem_base + (uint32_t)(s * 2 * HD), m_r1 = m_acc + HD, m_r2 = m_r1 + HD / 2;
+    auto mma_stage = [&](int kind) {
+      if (!issuer_warp) return;
+      const bool ok = wait_bar(cx, &a_ready[s], aph, 2);
+      aph ^= 1u;
+      tc_fence_after();
+      if (ok && lane == 0) {
+        const TcMat& mm = tl.mat[kind];
+        const int kx = mm.kx / 16, kall = mm.K / 16;
+        const uint32_t idesc = (kind == TC_N3 || kind == TC_G3) ? idesc_o : idesc_h;
+        const uint32_t lbo_b = (uint32_t)mm.nloc * 16;
+#pragma unroll 1
+        for (int ks = 0; ks < kall; ++ks) {
+          const uint64_t db = make_smem_desc(wbase + (uint32_t)mm.off + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
+          const uint32_t a_col = ks < kx ? m_r1 + (uint32_t)(8 * ks) : m_r2 + (uint32_t)(8 * (ks - kx));
+          umma_f16_ts<2>(m_acc, a_col, db, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit_cg2_mc(&d_ready[s], 0x3);
+      }
+      __syncwarp();
+    };
+    auto kind_of = [&](int st) { return st < 2 * n_pass ? (st & 1) : 2 + (st - 2 * n_pass); };
     auto parp = [&](int off) -> const float* { return off >= 0 ? sPar + off : nullptr; };
     int dbg_n = 0;
     const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && tid == 0;
@@ -374,11 +401,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         }
         build_edge(0);
         signal_a(cx, s, lane);
+        mma_stage(TC_E1);
         float* outp = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
 
 #pragma unroll 1
         for (int st = 0; st < n_stage; ++st) {
-          const int kind = st < 2 * n_pass ? (st & 1) : 2 + (st - 2 * n_pass);
+          const int kind = kind_of(st);
           const int p = st >> 1;  // edge pass (kinds E1 / E2)
           stamp(10 + kind);
           wait_bar(cx, &d_ready[s], dph, 10 + kind);
@@ -390,39 +418,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
             // ------------------ hidden layer: LayerNorm + activation -> fp16 ------------------
             const bool live = kind <= TC_E2 ? (e_bl < Te && p * Te + e_bl < Gc) : kind <= TC_N2 ? live_n : live_g;
             const bool warp_on = __any_sync(FULL, live);
-            uint32_t hreg[HD / 2];
-            if (warp_on) epi_hidden<HD>(t_acc, parp(m.par_bias), parp(m.par_gamma), parp(m.par_beta), ln && m.ln, act, hreg);
-            stamp(30 + kind);
-            if (kind != TC_E2) {
-              if (warp_on) store_hidden<HD>(t_r1, hreg);
-            } else {
-              // ---------- aggregation of the hidden edge activations (models/utils.py:42-51; W3 folded) ----------
-              if (N == 2) {
-                // one outgoing edge per node: the node aggregate is this thread's own row; the global aggregate is the
-                // sum of the two rows of a trajectory (adjacent lanes)
-                if (warp_on) {
-                  store_hidden<HD>(t_r2, hreg);
+            const float* pb = parp(m.par_bias);
+            const float* pg = parp(m.par_gamma);
+            const float* pbe = parp(m.par_beta);
+            const bool lnm = ln && m.ln;
+            // where the fp16 row goes: 0 = R1 (next layer's A operand), 1 = N == 2 aggregation, 2 = staging for N >= 3
+            const int mode = kind != TC_E2 ? 0 : (N == 2 ? 1 : 2);
+            const int gb = row >> 1;
+            const bool gwr = live && (row & 1) == 0;
+            if (warp_on) {
+              epi_hidden<HD, RELU>(t_acc, pb, pg, pbe, lnm, act, [&](int c0, const uint32_t (&hc)[16]) {
+                if (mode == 0) {
+                  tmem_st16(t_r1 + c0 / 2, hc);
+                } else if (mode == 1) {
+                  // one outgoing edge per node: the node aggregate is this thread's own row (-> R2); the global aggregate
+                  // is the sum of the two rows of a trajectory (adjacent lanes) -> s_glob, written by the even lane
+                  tmem_st16(t_r2 + c0 / 2, hc);
+                  uint32_t sm16[16];
 #pragma unroll
-                  for (int j = 0; j < HD / 2; ++j) {
-                    const uint32_t o = __shfl_xor_sync(FULL, hreg[j], 1);
-                    const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&hreg[j]), *reinterpret_cast<const __half2*>(&o));
-                    hreg[j] = *reinterpret_cast<const uint32_t*>(&sum);
+                  for (int j = 0; j < 16; ++j) {
+                    const uint32_t o = __shfl_xor_sync(FULL, hc[j], 1);
+                    const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&hc[j]), *reinterpret_cast<const __half2*>(&o));
+                    sm16[j] = *reinterpret_cast<const uint32_t*>(&sum);
                   }
-                  if (live && (row & 1) == 0) {
-                    const int b = row >> 1;
+                  if (gwr) {
 #pragma unroll
-                    for (int c = 0; c < CH; ++c)
-                      *reinterpret_cast<uint4*>(s_glob + (size_t)b * (HD * 2) + ((c ^ (b & 7)) * 16)) =
-                          make_uint4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
+                    for (int cc = 0; cc < 4; ++cc) {
+                      const int c = c0 / 8 + cc;
+                      *reinterpret_cast<uint4*>(s_glob + (size_t)gb * (HD * 2) + ((c ^ (gb & 7)) * 16)) =
+                          make_uint4(sm16[4 * cc], sm16[4 * cc + 1], sm16[4 * cc + 2], sm16[4 * cc + 3]);
+                    }
                   }
-                }
-              } else {
-                if (warp_on) {
+                } else {
 #pragma unroll
-                  for (int c = 0; c < CH; ++c)
+                  for (int cc = 0; cc < 4; ++cc) {
+                    const int c = c0 / 8 + cc;
                     *reinterpret_cast<uint4*>(s_h2 + (size_t)row * (HD * 2) + ((c ^ (row & 7)) * 16)) =
-                        make_uint4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
+                        make_uint4(hc[4 * cc], hc[4 * cc + 1], hc[4 * cc + 2], hc[4 * cc + 3]);
+                  }
                 }
+              });
+            }
+            stamp(30 + kind);
+            if (kind == TC_E2) {
+              // ---------- aggregation of the hidden edge activations (models/utils.py:42-51; W3 folded) ----------
+              if (N != 2) {
                 wg_sync(s);
                 const int live_tr = max(0, min(Te, Gc - p * Te));  // live trajectories of this pass
                 // phase 1: sums over the N-1 outgoing edges of every node of the pass
@@ -439,24 +479,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
                 wg_sync(s);
                 // phase 2a: the owner of a node row moves its aggregate into the node tile's A operand (R2)
                 if (__any_sync(FULL, n_p == p && live_n)) {
-                  if (n_p == p) {
-                    const int a = min(n_a, Te * N - 1);
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                      const uint4 v = *reinterpret_cast<const uint4*>(s_agg + (size_t)a * (HD * 2) + ((c ^ (a & 7)) * 16));
-                      hreg[4 * c] = v.x; hreg[4 * c + 1] = v.y; hreg[4 * c + 2] = v.z; hreg[4 * c + 3] = v.w;
-                    }
-                  }
                   // tcgen05.st is warp wide: lanes that belong to other passes re-write what R2 already holds
-                  uint32_t cur[HD / 2];
+                  const int a = min(n_a, Te * N - 1);
 #pragma unroll
-                  for (int c0 = 0; c0 < HD / 2; c0 += 32) tmem_ld32(t_r2 + c0, *reinterpret_cast<uint32_t(*)[32]>(&cur[c0]));
-                  tmem_wait_ld();
-                  if (n_p != p) {
+                  for (int c0 = 0; c0 < HD / 2; c0 += 32) {
+                    uint32_t cur[32];
+                    tmem_ld32(t_r2 + c0, cur);
+                    tmem_wait_ld();
+                    if (n_p == p) {
 #pragma unroll
-                    for (int j = 0; j < HD / 2; ++j) hreg[j] = cur[j];
+                      for (int cc = 0; cc < 8; ++cc) {
+                        const int c = c0 / 4 + cc;
+                        const uint4 v = *reinterpret_cast<const uint4*>(s_agg + (size_t)a * (HD * 2) + ((c ^ (a & 7)) * 16));
+                        cur[4 * cc] = v.x; cur[4 * cc + 1] = v.y; cur[4 * cc + 2] = v.z; cur[4 * cc + 3] = v.w;
+                      }
+                    }
+                    tmem_st32(t_r2 + c0, cur);
                   }
-                  store_hidden<HD>(t_r2, hreg);
                 }
                 // phase 2b: sum over all edges of a trajectory = sum of its node sums
                 for (int t = row; t < live_tr * CH; t += 128) {
@@ -483,6 +522,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
               }
             }
             signal_a(cx, s, lane);
+            mma_stage(kind_of(st + 1));
           } else if (kind == TC_N3) {
             // ------------------ node output: delta -> de-normalise, residual update (gnn_ensemble.py:302-334, 935-939) ------------------
             if (__any_sync(FULL, live_n)) {
@@ -504,6 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
               }
             }
             // A operand of the global tile: [hdr | 0] -> R1, sum over all edges -> R2
+            wg_sync(s);  // s_glob rows were written by other threads of this warpgroup (edge passes)
             {
               const int b = min(row, T - 1);
               const uint4* sb = reinterpret_cast<const uint4*>(snrm + b * SNs);
@@ -519,6 +560,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
               store_hidden<HD>(t_r2, hreg);
             }
             signal_a(cx, s, lane);
+            mma_stage(TC_G1);
           } else {
             // ------------------ global output: agent delta, next action, trailing observation part ------------------
             if (__any_sync(FULL, live_g)) {
@@ -562,7 +604,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   tc_fence_before();
   __syncthreads();
   cluster_sync();
-  if (warp == 8) tmem_dealloc<2>(tmem_base, 512);
+  if (warp == 0) tmem_dealloc<2>(tmem_base, 512);
 }
 
 // ---- weight packing ------------------------------------------------------------------------------------------
@@ -795,20 +837,22 @@ cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout
   return cudaGetLastError();
 }
 
+template <int HD, bool RELU>
+static cudaError_t launch_tc_t(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
+                               const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(rollout_gnn_tc_kernel<HD, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
+  if (e != cudaSuccess) return e;
+  rollout_gnn_tc_kernel<HD, RELU><<<dim3(2 * tl.pairs), kTcThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                   const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
-  cudaError_t e;
-  const dim3 grid(2 * tl.pairs);
-  if (md.Hd == 128) {
-    e = cudaFuncSetAttribute(rollout_gnn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
-    if (e != cudaSuccess) return e;
-    rollout_gnn_tc_kernel<128><<<grid, kTcThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
-  } else {
-    e = cudaFuncSetAttribute(rollout_gnn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
-    if (e != cudaSuccess) return e;
-    rollout_gnn_tc_kernel<64><<<grid, kTcThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
-  }
-  return cudaGetLastError();
+  const bool relu = md.act == CEEUS_ACT_RELU;
+  if (md.Hd == 128) return relu ? launch_tc_t<128, true>(md, ra, tl, wimg, wpar, err_flag, dbg, st)
+                                : launch_tc_t<128, false>(md, ra, tl, wimg, wpar, err_flag, dbg, st);
+  return relu ? launch_tc_t<64, true>(md, ra, tl, wimg, wpar, err_flag, dbg, st)
+              : launch_tc_t<64, false>(md, ra, tl, wimg, wpar, err_flag, dbg, st);
 }
 
 }  // namespace ceeus

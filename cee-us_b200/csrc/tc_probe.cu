@@ -111,8 +111,89 @@ __global__ void __launch_bounds__(160, 1) umma_probe_kernel(const __half* __rest
   if (warp == 4) tmem_dealloc<CG>(tmem_base, ncols);
 }
 
+// TMEM <-> register-file micro-benchmark: clock64 around N x tcgen05.ld/st.32x32b.x32 (+ one wait) with 1, 4 or 8 warps active.
+__global__ void __launch_bounds__(256, 1) tmem_bench_kernel(long long* out) {
+  __shared__ uint32_t tmem_slot;
+  __shared__ float sink[256];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) {
+    tmem_alloc<1>(&tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t a[32], b[32], c[32], d[32];
+  for (int j = 0; j < 32; ++j) { a[j] = tid + j; b[j] = tid * 3 + j; c[j] = tid * 5 + j; d[j] = tid * 7 + j; }
+  // fill
+  for (int c0 = 0; c0 < 512; c0 += 32) tmem_st32(base + c0, a);
+  tmem_wait_st();
+  float acc = 0.f;
+  int slot = 0;
+  auto run = [&](int nwarps, int nld, bool serial, bool store) {
+    __syncthreads();
+    const long long t0 = clock64();
+    if (warp < nwarps) {
+      for (int i = 0; i < nld; i += 4) {
+        const uint32_t col = (uint32_t)((i * 32) & 511);
+        if (store) {
+          tmem_st32(base + col, a); if (serial) tmem_wait_st();
+          if (i + 1 < nld) { tmem_st32(base + ((col + 32) & 511), b); if (serial) tmem_wait_st(); }
+          if (i + 2 < nld) { tmem_st32(base + ((col + 64) & 511), c); if (serial) tmem_wait_st(); }
+          if (i + 3 < nld) { tmem_st32(base + ((col + 96) & 511), d); if (serial) tmem_wait_st(); }
+        } else {
+          tmem_ld32(base + col, a); if (serial) tmem_wait_ld();
+          if (i + 1 < nld) { tmem_ld32(base + ((col + 32) & 511), b); if (serial) tmem_wait_ld(); }
+          if (i + 2 < nld) { tmem_ld32(base + ((col + 64) & 511), c); if (serial) tmem_wait_ld(); }
+          if (i + 3 < nld) { tmem_ld32(base + ((col + 96) & 511), d); if (serial) tmem_wait_ld(); }
+        }
+      }
+      if (store) tmem_wait_st(); else tmem_wait_ld();
+      acc += __uint_as_float(a[1] ^ b[2] ^ c[3] ^ d[4]);
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (tid == 0) out[slot] = t1 - t0;
+    ++slot;
+  };
+  run(1, 1, false, false);   // 0: latency of one ld32 + wait
+  run(1, 4, false, false);   // 1
+  run(1, 16, false, false);  // 2
+  run(1, 64, false, false);  // 3
+  run(4, 4, false, false);   // 4
+  run(4, 16, false, false);  // 5
+  run(4, 64, false, false);  // 6
+  run(8, 16, false, false);  // 7
+  run(8, 64, false, false);  // 8
+  run(1, 16, true, false);   // 9: serialised ld + wait
+  run(4, 16, true, false);   // 10
+  run(1, 1, false, true);    // 11: st latency
+  run(4, 16, false, true);   // 12
+  run(4, 64, false, true);   // 13
+  run(8, 64, false, true);   // 14
+  sink[tid] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<1>(tmem_slot, 512);
+  if (sink[(tid + 1) & 255] == 1234.5f) out[31] = 1;
+}
+
 }  // namespace
 }  // namespace ceeus
+
+extern "C" int ceeus_selftest_tmem(long long* out_host /* [32] */) {
+  using namespace ceeus;
+  if (!out_host) return CEEUS_ERR_INVALID;
+  long long* d = nullptr;
+  if (cudaMalloc(&d, 32 * sizeof(long long)) != cudaSuccess) return CEEUS_ERR_CUDA;
+  cudaMemset(d, 0, 32 * sizeof(long long));
+  tmem_bench_kernel<<<1, 256>>>(d);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out_host, d, 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? CEEUS_OK : CEEUS_ERR_CUDA;
+}
 
 extern "C" int ceeus_selftest_umma(int cta_group, const void* a_dev, const void* bt_dev, float* d_dev, int K, int N,
                                    int variant, int* status_host) {

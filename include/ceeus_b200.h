@@ -203,6 +203,10 @@ int ceeus_has_elites(CeeusHandle h);
 int ceeus_selftest_umma(int cta_group, const void* a_dev, const void* bt_dev, float* d_dev, int K, int N, int variant,
                         int* status_host);
 
+/* Diagnostic: cycle counts of TMEM <-> register transfers (tcgen05.ld / tcgen05.st 32x32b.x32) for 1 / 4 / 8 active warps;
+ * out_host receives 32 values (see tmem_bench_kernel in csrc/tc_probe.cu).  No reference counterpart (profiling aid). */
+int ceeus_selftest_tmem(long long* out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,13 @@
+"""Manual diagnostic: TMEM <-> register transfer cycle counts (ceeus_selftest_tmem)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ceeus_b200
+lib = ceeus_b200._lib.load()
+torch.zeros(1, device="cuda")
+names = ["ld x1 1w", "ld x4 1w", "ld x16 1w", "ld x64 1w", "ld x4 4w", "ld x16 4w", "ld x64 4w", "ld x16 8w", "ld x64 8w",
+         "ld+wait x16 1w", "ld+wait x16 4w", "st x1 1w", "st x16 4w", "st x64 4w", "st x64 8w"]
+for rep in range(2):
+    buf = (C.c_longlong * 32)()
+    rc = lib.ceeus_selftest_tmem(buf)
+    print("rc", rc, " | ".join(f"{n}: {buf[i]}" for i, n in enumerate(names)))
