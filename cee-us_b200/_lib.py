@@ -65,8 +65,11 @@ SIGNATURES = {
     "ceeus_kernel_launches": (C.c_int64, [C.c_void_p]),
     "ceeus_has_elites": (C.c_int, [C.c_void_p]),
     "ceeus_tc_status": (C.c_int, [C.c_void_p]),
+    "ceeus_selftest_epilogue": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ceeus_tc_debug_flag": (C.c_int, [C.c_void_p, C.c_longlong]),
     "ceeus_tc_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "ceeus_selftest_tmem": (C.c_int, [C.c_void_p]),
+    "ceeus_selftest_tmem_contention": (C.c_int, [C.c_int, C.c_void_p]),
     "ceeus_selftest_umma": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.POINTER(C.c_int)]),
 }

@@ -536,6 +536,23 @@ int ceeus_tc_debug_timeline(CeeusHandle h, int enable, long long* out_host, int 
   return CEEUS_OK;
 }
 
+int ceeus_selftest_epilogue(int warps_per_scheduler, int with_bias, int with_mma, long long* cycles_host) {
+  if (!cycles_host || warps_per_scheduler < 1 || warps_per_scheduler > 3) return CEEUS_ERR_INVALID;
+  long long* d = nullptr;
+  if (cudaMalloc(&d, 2 * sizeof(long long)) != cudaSuccess) return CEEUS_ERR_CUDA;
+  cudaMemset(d, 0, 2 * sizeof(long long));
+  cudaError_t e = launch_epi_bench(warps_per_scheduler, with_bias, with_mma, d);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(cycles_host, d, 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? CEEUS_OK : CEEUS_ERR_CUDA;
+}
+
+int ceeus_tc_debug_flag(CeeusHandle h, long long flag) {
+  if (!h || !h->d_tc_dbg) return CEEUS_ERR_INVALID;
+  return cudaMemcpy(h->d_tc_dbg + 499, &flag, sizeof(flag), cudaMemcpyHostToDevice) == cudaSuccess ? CEEUS_OK : CEEUS_ERR_CUDA;
+}
+
 int ceeus_tc_status(CeeusHandle h) {
   if (!h) return CEEUS_ERR_INVALID;
   if (!h->d_tc_err) return 0;

@@ -60,6 +60,8 @@ cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                   const float* wpar, int* err_flag, long long* dbg, cudaStream_t st);
 
+cudaError_t launch_epi_bench(int nwg, int with_bias, int with_mma, long long* out_dev);  // profiling aid (ceeus_selftest_epilogue)
+
 // ---- iCEM kernels (icem_kernels.cu) ----
 struct SampleArgs {
   const float* mean;   // [nE,H,U]

@@ -127,9 +127,9 @@ __device__ __forceinline__ void chunk_finish(float (&x)[32], const float* __rest
 // processed, and only 64 fp32 values are live, so the parameter loads of a chunk are issued together.  The chunk loop is
 // NOT unrolled beyond the buffer pair and there is exactly one call site: the hot code must stay inside the
 // instruction cache (the fully unrolled version was 800 KB of SASS and stalled on instruction fetch).
-template <int HD, bool RELU, class Sink>
+template <int HD, bool RELU, class Sink, class Probe>
 __device__ __forceinline__ void epi_hidden(uint32_t tacc, const float* __restrict__ pb, const float* __restrict__ pg,
-                                           const float* __restrict__ pbe, bool ln, int act, Sink&& sink) {
+                                           const float* __restrict__ pbe, bool ln, int act, Sink&& sink, Probe&& probe) {
   constexpr int NC = HD / 32;
   static_assert(NC % 2 == 0, "chunk pairs");
   float xa[32], xb[32];
@@ -140,9 +140,11 @@ __device__ __forceinline__ void epi_hidden(uint32_t tacc, const float* __restric
 #pragma unroll 1
     for (int k = 0; k < NC; k += 2) {
       tmem_wait_ld();
+      probe(110 + k);
       tmem_ld32(tacc + 32 * (k + 1), *reinterpret_cast<uint32_t(*)[32]>(&xb[0]));
       if (pb != nullptr) chunk_bias(xa, pb + 32 * k);
       chunk_moment(xa, v8);
+      probe(111 + k);
       tmem_wait_ld();
       if (k + 2 < NC) tmem_ld32(tacc + 32 * (k + 2), *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
       if (pb != nullptr) chunk_bias(xb, pb + 32 * (k + 1));
@@ -150,6 +152,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t tacc, const float* __restric
     }
     const float v = ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
     rstd = rsqrtf(v * (1.f / HD) + 1e-5f);
+    probe(119);
   }
   uint32_t hc[16];
   tmem_ld32(tacc, *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
@@ -159,7 +162,9 @@ __device__ __forceinline__ void epi_hidden(uint32_t tacc, const float* __restric
     tmem_ld32(tacc + 32 * (k + 1), *reinterpret_cast<uint32_t(*)[32]>(&xb[0]));
     if (pb != nullptr) chunk_bias(xa, pb + 32 * k);
     chunk_finish<RELU>(xa, pg + 32 * k, pbe + 32 * k, ln, rstd, act, hc);
+    probe(120 + k);
     sink(32 * k, hc);
+    probe(121 + k);
     tmem_wait_ld();
     if (k + 2 < NC) tmem_ld32(tacc + 32 * (k + 2), *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
     if (pb != nullptr) chunk_bias(xb, pb + 32 * (k + 1));
@@ -256,7 +261,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   __syncthreads();
   cluster_sync();  // both CTAs: barriers initialised, TMEM allocated, weights resident
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // all 512 columns are allocated, so the base can only be column 0 / lane 0; using the literal keeps every TMEM address
+  // warp uniform for the compiler (checked once)
+  if (*tmem_slot != 0u && tid == 0) atomicExch(err, 7);
+  constexpr uint32_t tmem_base = 0u;
   cx.a_ready_leader[0] = mapa(smem_u32(&a_ready[0]), 0);
   cx.a_ready_leader[1] = mapa(smem_u32(&a_ready[1]), 0);
 
@@ -279,6 +287,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 2 * HD);
     const uint32_t t_acc = lane_base, t_r1 = lane_base + HD, t_r2 = lane_base + HD + HD / 2;
     uint32_t dph = 0;
+    int dbg_n = 0;
+    const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    auto stamp = [&](int tag) {
+      if (dbg_on && dbg_n < 250) { dbg[2 * dbg_n] = tag; dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
+    };
+
     // ---- MMA issue: warp 0 of the warpgroup in the leader CTA waits for both CTAs' A operands and issues the stage ----
     const bool issuer_warp = rank == 0 && q == 0;
     uint32_t aph = 0;
@@ -288,32 +302,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     const uint32_t m_acc = tmem_base + (uint32_t)(s * 2 * HD), m_r1 = m_acc + HD, m_r2 = m_r1 + HD / 2;
     auto mma_stage = [&](int kind) {
       if (!issuer_warp) return;
+      stamp(70 + kind);
       const bool ok = wait_bar(cx, &a_ready[s], aph, 2);
       aph ^= 1u;
       tc_fence_after();
-      if (ok && lane == 0) {
+      stamp(80 + kind);
+      if (ok) {  // warp-converged: one elected lane issues, operands stay warp uniform
+        const uint32_t elected = elect_one();
         const TcMat& mm = tl.mat[kind];
         const int kx = mm.kx / 16, kall = mm.K / 16;
         const uint32_t idesc = (kind == TC_N3 || kind == TC_G3) ? idesc_o : idesc_h;
         const uint32_t lbo_b = (uint32_t)mm.nloc * 16;
+        const uint64_t db0 = make_smem_desc(wbase + (uint32_t)mm.off, lbo_b, 128);
+        const uint32_t db_step = (2u * lbo_b) >> 4;  // descriptor start-address field advances by two 16-byte-chunk rows per K step
 #pragma unroll 1
         for (int ks = 0; ks < kall; ++ks) {
-          const uint64_t db = make_smem_desc(wbase + (uint32_t)mm.off + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
           const uint32_t a_col = ks < kx ? m_r1 + (uint32_t)(8 * ks) : m_r2 + (uint32_t)(8 * (ks - kx));
-          umma_f16_ts<2>(m_acc, a_col, db, idesc, ks > 0 ? 1u : 0u);
+          umma_f16_ts_cg2_elect(m_acc, a_col, db0 + (uint64_t)((uint32_t)ks * db_step), idesc, ks > 0 ? 1u : 0u, elected);
         }
-        umma_commit_cg2_mc(&d_ready[s], 0x3);
+        umma_commit_cg2_mc_elect(&d_ready[s], 0x3, elected);
       }
       __syncwarp();
+      stamp(90 + kind);
     };
     auto kind_of = [&](int st) { return st < 2 * n_pass ? (st & 1) : 2 + (st - 2 * n_pass); };
     auto parp = [&](int off) -> const float* { return off >= 0 ? sPar + off : nullptr; };
-    int dbg_n = 0;
-    const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && tid == 0;
-    auto stamp = [&](int tag) {
-      if (dbg_on && dbg_n < 250) { dbg[2 * dbg_n] = tag; dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
-    };
-
     // ---- static row roles ----
     // edge row (pass-local): trajectory bl, source node ei, target node ej
     const int e_bl = row / NE, e_q = row % NE;
@@ -333,7 +346,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     for (int rd = 0; rd < rounds; ++rd) {
       const int w_lo = min(ra.n, worker * per_worker), w_hi = min(ra.n, w_lo + per_worker);
       const int p0 = w_lo + rd * T;
-      const int Gc = max(0, min(T, w_hi - p0));  // live trajectories of this group (0: pure lock-step filler)
+      int Gc = max(0, min(T, w_hi - p0));  // live trajectories of this group (0: pure lock-step filler)
+      if (dbg != nullptr && dbg[499] == 1 && s == 1) Gc = 0;  // profiling aid: slot 1 idles, slot 0 runs without SIMT contention
       const bool live_n = n_valid && n_b < Gc;
       const bool live_g = row < Gc;
       wg_sync(s);
@@ -457,7 +471,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
                         make_uint4(hc[4 * cc], hc[4 * cc + 1], hc[4 * cc + 2], hc[4 * cc + 3]);
                   }
                 }
-              });
+              }, [](int) {});
             }
             stamp(30 + kind);
             if (kind == TC_E2) {
@@ -607,6 +621,65 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   if (warp == 0) tmem_dealloc<2>(tmem_base, 512);
 }
 
+// ---- epilogue micro-benchmark: the hidden-layer epilogue alone (no barriers), 1..3 warps per scheduler; optionally one
+// extra warp keeps the tensor core busy with back-to-back MMAs into other TMEM columns (with_mma) ----
+template <int NWG>
+__global__ void __launch_bounds__(128 * NWG + 32, 1) epi_bench_kernel(long long* out, int reps, int with_bias, int with_mma) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint64_t bar;
+  __shared__ volatile int stop;
+  __shared__ __align__(16) float par[3 * 128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 3 * 128; i += blockDim.x) par[i] = 0.5f + 0.001f * i;
+  for (int i = tid; i < 16384; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  fence_proxy_async();
+  if (tid == 0) stop = 0;
+  if (warp == 0) {
+    if (lane == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    __syncwarp();
+    tmem_alloc<1>(&tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp < 4 * NWG) {
+    const uint32_t base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+    uint32_t a[32];
+    for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(0.01f * (tid + j));
+    for (int c0 = 0; c0 < 128; c0 += 32) tmem_st32(base + c0, a);
+    tmem_wait_st();
+    asm volatile("bar.sync 1, %0;" ::"r"(128 * NWG) : "memory");
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      epi_hidden<128, true>(base, with_bias ? par : nullptr, par + 128, par + 256, true, CEEUS_ACT_RELU,
+                            [&](int c0, const uint32_t (&hc)[16]) { tmem_st16(base + c0 / 2, hc); }, [](int) {});
+      tmem_wait_st();
+    }
+    const long long t1 = clock64();
+    asm volatile("bar.sync 1, %0;" ::"r"(128 * NWG) : "memory");
+    if (tid == 0) { out[0] = (t1 - t0) / reps; stop = 1; }
+  } else if (with_mma && lane == 0) {
+    const uint32_t idesc = make_idesc_f16(128, 128);
+    const uint64_t da = make_smem_desc(smem_u32(smem), 2048, 128);
+    const uint64_t db = make_smem_desc(smem_u32(smem) + 32768, 2048, 128);
+    uint32_t ph = 0;
+    long long n = 0;
+    while (!stop) {
+      for (int i = 0; i < 8; ++i) umma_f16_ss<1>(tmem_slot + 384, da, db, idesc, i > 0 ? 1u : 0u);
+      umma_commit_cg1(&bar);
+      mbar_wait(&bar, ph, nullptr, 0);
+      ph ^= 1u;
+      n += 8;
+    }
+    out[1] = n;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<1>(tmem_slot, 512);
+}
+
 // ---- weight packing ------------------------------------------------------------------------------------------
 __device__ __forceinline__ const LayerDesc& mat_layer(const ModelDesc& md, int m) {
   switch (m) {
@@ -721,6 +794,25 @@ __global__ void tc_image_kernel(const float* __restrict__ w32, const ModelDesc m
 }
 
 }  // namespace
+
+cudaError_t launch_epi_bench(int nwg, int with_bias, int with_mma, long long* out_dev) {
+  const int smem = 65536;
+  switch (nwg) {
+    case 1:
+      cudaFuncSetAttribute(epi_bench_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      epi_bench_kernel<1><<<1, 128 + 32, smem>>>(out_dev, 50, with_bias, with_mma);
+      break;
+    case 2:
+      cudaFuncSetAttribute(epi_bench_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      epi_bench_kernel<2><<<1, 256 + 32, smem>>>(out_dev, 50, with_bias, with_mma);
+      break;
+    default:
+      cudaFuncSetAttribute(epi_bench_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      epi_bench_kernel<3><<<1, 384 + 32, smem>>>(out_dev, 50, with_bias, with_mma);
+      break;
+  }
+  return cudaGetLastError();
+}
 
 bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_host) {
   TcLayout t{};

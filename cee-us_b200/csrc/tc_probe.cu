@@ -179,8 +179,79 @@ __global__ void __launch_bounds__(256, 1) tmem_bench_kernel(long long* out) {
   if (sink[(tid + 1) & 255] == 1234.5f) out[31] = 1;
 }
 
+// Does a tcgen05.ld / tcgen05.st queue behind in-flight tcgen05.mma?  Warp 4 issues `nmma` MMAs (M=128, N=128, K=16, operands
+// = whatever is in shared memory) into columns [256, 384); warps 0-3 time one ld32 (+wait) / st32 (+wait) of columns [0, 32)
+// issued right after.  out[0] = ld latency, out[1] = st latency, out[2] = cycles until the MMA batch committed.
+__global__ void __launch_bounds__(160, 1) tmem_mma_contention_kernel(long long* out, int nmma) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 16384; i += 160) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;  // fp16 1.0
+  fence_proxy_async();
+  if (warp == 4) {
+    if (lane == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    __syncwarp();
+    tmem_alloc<1>(&tmem_slot, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_slot;
+  uint32_t a[32];
+  for (int j = 0; j < 32; ++j) a[j] = tid + j;
+  if (warp < 4) { tmem_st32(base + ((uint32_t)(warp * 32) << 16), a); tmem_wait_st(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const long long t0 = clock64();
+  if (warp == 4) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 128);
+      for (int i = 0; i < nmma; ++i) {
+        const uint64_t da = make_smem_desc(smem_u32(smem), 2048, 128);
+        const uint64_t db = make_smem_desc(smem_u32(smem) + 32768, 2048, 128);
+        umma_f16_ss<1>(base + 256, da, db, idesc, i > 0 ? 1u : 0u);
+      }
+      umma_commit_cg1(&bar);
+      mbar_wait(&bar, 0, nullptr, 0);
+      out[2] = clock64() - t0;
+    }
+  } else {
+    // small delay so that the MMAs are in flight
+    for (int i = 0; i < 20; ++i) a[i & 31] += (uint32_t)clock64() & 1u;
+    const long long t1 = clock64();
+    tmem_ld32(base + ((uint32_t)(warp * 32) << 16), a);
+    tmem_wait_ld();
+    const long long t2 = clock64();
+    tmem_st32(base + ((uint32_t)(warp * 32) << 16) + 64, a);
+    tmem_wait_st();
+    const long long t3 = clock64();
+    if (tid == 0) { out[0] = t2 - t1; out[1] = t3 - t2; out[3] = t1 - t0; }
+    if (a[3] == 0x12345678u) out[5] = 1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<1>(base, 512);
+}
+
 }  // namespace
 }  // namespace ceeus
+
+extern "C" int ceeus_selftest_tmem_contention(int nmma, long long* out_host /* [8] */) {
+  using namespace ceeus;
+  if (!out_host) return CEEUS_ERR_INVALID;
+  long long* d = nullptr;
+  if (cudaMalloc(&d, 8 * sizeof(long long)) != cudaSuccess) return CEEUS_ERR_CUDA;
+  cudaMemset(d, 0, 8 * sizeof(long long));
+  cudaFuncSetAttribute(tmem_mma_contention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  tmem_mma_contention_kernel<<<1, 160, 65536>>>(d, nmma);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(out_host, d, 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? CEEUS_OK : CEEUS_ERR_CUDA;
+}
 
 extern "C" int ceeus_selftest_tmem(long long* out_host /* [32] */) {
   using namespace ceeus;

@@ -11,3 +11,15 @@ for rep in range(2):
     buf = (C.c_longlong * 32)()
     rc = lib.ceeus_selftest_tmem(buf)
     print("rc", rc, " | ".join(f"{n}: {buf[i]}" for i, n in enumerate(names)))
+
+for nmma in (0, 1, 4, 8, 16, 32):
+    buf = (C.c_longlong * 8)()
+    rc = lib.ceeus_selftest_tmem_contention(nmma, buf)
+    print(f"nmma={nmma:2d} rc={rc} ld_latency={buf[0]} st_latency={buf[1]} mma_batch_done={buf[2]} ld_issued_at={buf[3]}")
+
+for mma in (0, 1):
+    for bias in (0, 1):
+        for nw in (1, 2, 3):
+            v = (C.c_longlong * 2)()
+            rc = lib.ceeus_selftest_epilogue(nw, bias, mma, v)
+            print(f"epilogue mma={mma} bias={bias} warps/scheduler={nw}: {v[0]} cycles per epilogue per warp -> {v[0] / nw:.0f} per scheduler; mmas {v[1]}")
