@@ -218,33 +218,59 @@ __global__ void __launch_bounds__(256) cost_kernel(const CostArgs a, const CostD
     kstar = a.N - unsolved;
   }
   float acc = cd.cost_along == CEEUS_COST_BEST ? CUDART_INF_F : 0.f;
-  for (int h = 0; h < a.H; ++h) {
-    const float* nx = base + (size_t)(h + 1) * hs;
-    float bonus = 0.f;
+  // HB horizon steps at a time: all HB x E loads of a 32-feature column block are issued before any is used, so a warp
+  // keeps ~20 sectors in flight instead of one dependent load chain (HBM-bound kernel: 4 x H x E x n x O bytes read once)
+  constexpr int HB = 4;
+  const float inv_em1 = 1.f / (float)(a.E - 1);
+  for (int h0 = 0; h0 < a.H; h0 += HB) {
+    float bonus[HB];
+#pragma unroll
+    for (int hb = 0; hb < HB; ++hb) bonus[hb] = 0.f;
     if (cd.curiosity) {
       for (int d = lane; d < a.O; d += 32) {
-        // Welford, as torch.std does (exactly 0 for dims identical across members, e.g. the goal)
-        float mean = 0.f, m2 = 0.f;
-        for (int e = 0; e < a.E; ++e) {
-          const float x = __ldg(nx + e * es + d);
-          const float dl = x - mean;
-          mean += dl / (float)(e + 1);
-          m2 = fmaf(dl, x - mean, m2);
+        float x[HB][kMaxEnsemble];
+#pragma unroll
+        for (int hb = 0; hb < HB; ++hb)
+#pragma unroll
+          for (int e = 0; e < kMaxEnsemble; ++e)
+            if (e < a.E && h0 + hb < a.H) x[hb][e] = __ldg(base + (size_t)(h0 + hb + 1) * hs + e * es + d);
+#pragma unroll
+        for (int hb = 0; hb < HB; ++hb) {
+          if (h0 + hb < a.H) {
+            // Welford, as torch.std does (exactly 0 for dims identical across members, e.g. the goal)
+            float mean = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < kMaxEnsemble; ++e)
+              if (e < a.E) {
+                // 1/(e+1) as a compile-time constant multiply: <= 1 ulp from torch's division, and still exactly 0 for
+                // identical members; the IEEE divisions made this kernel instruction-bound (126 us for 105 MB)
+                const float dl = x[hb][e] - mean;
+                mean = fmaf(dl, 1.f / (float)(e + 1), mean);
+                m2 = fmaf(dl, x[hb][e] - mean, m2);
+              }
+            bonus[hb] += sqrtf(m2 * inv_em1);
+          }
         }
-        bonus += sqrtf(m2 / (float)(a.E - 1));
       }
-      bonus = warp_allsum(bonus);
     }
-    float c = 0.f;
-    if (lane < a.E) {
-      float envc = 0.f;
-      if (need_env) envc = env_cost_row(nx + lane * es, a, cd, kstar);
-      c = cd.curiosity ? (cd.extrinsic ? __fadd_rn(-bonus, __fmul_rn(cd.extrinsic_scale, envc)) : -bonus) : envc;
-    }
-    if (cd.cost_along == CEEUS_COST_BEST) {
-      if (h >= 1) acc = fminf(acc, c);  // amin over h >= 1 (mpc_torch.py:131)
-    } else {
-      acc += c;
+#pragma unroll
+    for (int hb = 0; hb < HB; ++hb) {
+      const int h = h0 + hb;
+      if (h < a.H) {
+        const float* nx = base + (size_t)(h + 1) * hs;
+        const float bs = cd.curiosity ? warp_allsum(bonus[hb]) : 0.f;
+        float c = 0.f;
+        if (lane < a.E) {
+          float envc = 0.f;
+          if (need_env) envc = env_cost_row(nx + lane * es, a, cd, kstar);
+          c = cd.curiosity ? (cd.extrinsic ? __fadd_rn(-bs, __fmul_rn(cd.extrinsic_scale, envc)) : -bs) : envc;
+        }
+        if (cd.cost_along == CEEUS_COST_BEST) {
+          if (h >= 1) acc = fminf(acc, c);  // amin over h >= 1 (mpc_torch.py:131)
+        } else {
+          acc += c;
+        }
+      }
     }
   }
   if (lane < a.E) a.cpm[(size_t)p * a.E + lane] = acc;
