@@ -48,6 +48,7 @@ struct TcLayout {
   TcMat mat[TC_NMAT];
   int image_bytes;         // per (member, rank)
   int par_floats;          // per member
+  int par_fold;            // offset of the "LayerNorm affine folded into the weights" flag (1.0 / 0.0)
   int kmap_len;
   int sm_w, sm_par, sm_nrm, nrm_floats, sm_slot[2], sm_bar, smem_bytes;
   int so_h2, so_agg, so_glob, so_snrm, so_tail;  // offsets inside a slot region

@@ -173,6 +173,56 @@ __device__ __forceinline__ void epi_hidden(uint32_t tacc, const float* __restric
   }
 }
 
+// One-pass hidden-layer epilogue on the whole accumulator row held in registers (255 registers per thread are available with
+// 256 threads per CTA).  FOLDED LayerNorm (fold != 0, ReLU): sign(gamma) lives in this layer's weight columns and |gamma| in the
+// consumer's weight rows (pack time), so  relu(gamma * xhat + beta) = |gamma| * relu(sign(gamma) * xhat + beta / |gamma|)  costs
+// one FFMA per element and one parameter vector (pbe = beta / |gamma|).  General path: xhat * gamma + beta, any activation.
+template <int HD, bool RELU>
+__device__ __forceinline__ void epi_row(uint32_t tacc, const float* __restrict__ pb, const float* __restrict__ pg,
+                                        const float* __restrict__ pbe, bool ln, bool fold, int act, uint32_t (&h)[HD / 2]) {
+  float x[HD];
+#pragma unroll
+  for (int c0 = 0; c0 < HD; c0 += 32) tmem_ld32(tacc + c0, *reinterpret_cast<uint32_t(*)[32]>(&x[c0]));
+  tmem_wait_ld();
+  if (pb != nullptr) {
+#pragma unroll
+    for (int j = 0; j < HD; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(pb + j);
+      x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+    }
+  }
+  if (ln) {
+    float v8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < HD; ++j) v8[j & 7] = fmaf(x[j], x[j], v8[j & 7]);
+    const float v = ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
+    const float rstd = rsqrtf(v * (1.f / HD) + 1e-5f);
+    if (RELU && fold) {
+#pragma unroll
+      for (int j = 0; j < HD; j += 4) {
+        const float4 be = *reinterpret_cast<const float4*>(pbe + j);
+        h[j / 2] = pack_half2_relu(fmaf(x[j], rstd, be.x), fmaf(x[j + 1], rstd, be.y));
+        h[j / 2 + 1] = pack_half2_relu(fmaf(x[j + 2], rstd, be.z), fmaf(x[j + 3], rstd, be.w));
+      }
+      return;
+    }
+#pragma unroll
+    for (int j = 0; j < HD; j += 4) {
+      const float4 g = *reinterpret_cast<const float4*>(pg + j);
+      const float4 be = *reinterpret_cast<const float4*>(pbe + j);
+      x[j] = fmaf(x[j] * rstd, g.x, be.x); x[j + 1] = fmaf(x[j + 1] * rstd, g.y, be.y);
+      x[j + 2] = fmaf(x[j + 2] * rstd, g.z, be.z); x[j + 3] = fmaf(x[j + 3] * rstd, g.w, be.w);
+    }
+  }
+  if constexpr (RELU) {
+#pragma unroll
+    for (int j = 0; j < HD; j += 2) h[j / 2] = pack_half2_relu(x[j], x[j + 1]);
+  } else {
+#pragma unroll 4
+    for (int j = 0; j < HD; j += 2) h[j / 2] = pack_half2(act_fn(x[j], act), act_fn(x[j + 1], act));
+  }
+}
+
 __device__ __forceinline__ void add8(float (&acc)[8], const uint4& m) {
   const __half2* hp = reinterpret_cast<const __half2*>(&m);
 #pragma unroll
@@ -284,6 +334,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     const float* __restrict__ nrm = sNrm;
     const bool ln = md.layer_norm != 0;
     const int act = md.act;
+    const bool fold = sPar[tl.par_fold] != 0.f;  // LayerNorm affine folded into the weights (decided per member at pack time)
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 2 * HD);
     const uint32_t t_acc = lane_base, t_r1 = lane_base + HD, t_r2 = lane_base + HD + HD / 2;
     uint32_t dph = 0;
@@ -315,7 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         const uint32_t lbo_b = (uint32_t)mm.nloc * 16;
         const uint64_t db0 = make_smem_desc(wbase + (uint32_t)mm.off, lbo_b, 128);
         const uint32_t db_step = (2u * lbo_b) >> 4;  // descriptor start-address field advances by two 16-byte-chunk rows per K step
-#pragma unroll 1
+#pragma unroll 2
         for (int ks = 0; ks < kall; ++ks) {
           const uint32_t a_col = ks < kx ? m_r1 + (uint32_t)(8 * ks) : m_r2 + (uint32_t)(8 * (ks - kx));
           umma_f16_ts_cg2_elect(m_acc, a_col, db0 + (uint64_t)((uint32_t)ks * db_step), idesc, ks > 0 ? 1u : 0u, elected);
@@ -438,40 +489,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
             const bool lnm = ln && m.ln;
             // where the fp16 row goes: 0 = R1 (next layer's A operand), 1 = N == 2 aggregation, 2 = staging for N >= 3
             const int mode = kind != TC_E2 ? 0 : (N == 2 ? 1 : 2);
-            const int gb = row >> 1;
-            const bool gwr = live && (row & 1) == 0;
             if (warp_on) {
-              epi_hidden<HD, RELU>(t_acc, pb, pg, pbe, lnm, act, [&](int c0, const uint32_t (&hc)[16]) {
-                if (mode == 0) {
-                  tmem_st16(t_r1 + c0 / 2, hc);
-                } else if (mode == 1) {
-                  // one outgoing edge per node: the node aggregate is this thread's own row (-> R2); the global aggregate
-                  // is the sum of the two rows of a trajectory (adjacent lanes) -> s_glob, written by the even lane
-                  tmem_st16(t_r2 + c0 / 2, hc);
-                  uint32_t sm16[16];
+              uint32_t hreg[HD / 2];
+              epi_row<HD, RELU>(t_acc, pb, pg, pbe, lnm, fold, act, hreg);
+              if (mode == 0) {
+                store_hidden<HD>(t_r1, hreg);
+                // the next layer's bias rides in a constant-one K column that lives in R2 (free once this layer's MMA is done)
+                if (tl.mat[kind + 1].K > tl.mat[kind + 1].kx && tl.mat[kind + 1].kx == HD) tmem_st4(t_r2, make_uint4(0x00003c00u, 0u, 0u, 0u)), tmem_st4(t_r2 + 4, make_uint4(0u, 0u, 0u, 0u));
+              } else if (mode == 1) {
+                // one outgoing edge per node: the node aggregate is this thread's own row (-> R2); the global aggregate is the
+                // sum of the two rows of a trajectory (adjacent lanes) -> s_glob, written by the even lane
+                store_hidden<HD>(t_r2, hreg);
 #pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    const uint32_t o = __shfl_xor_sync(FULL, hc[j], 1);
-                    const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&hc[j]), *reinterpret_cast<const __half2*>(&o));
-                    sm16[j] = *reinterpret_cast<const uint32_t*>(&sum);
-                  }
-                  if (gwr) {
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                      const int c = c0 / 8 + cc;
-                      *reinterpret_cast<uint4*>(s_glob + (size_t)gb * (HD * 2) + ((c ^ (gb & 7)) * 16)) =
-                          make_uint4(sm16[4 * cc], sm16[4 * cc + 1], sm16[4 * cc + 2], sm16[4 * cc + 3]);
-                    }
-                  }
-                } else {
-#pragma unroll
-                  for (int cc = 0; cc < 4; ++cc) {
-                    const int c = c0 / 8 + cc;
-                    *reinterpret_cast<uint4*>(s_h2 + (size_t)row * (HD * 2) + ((c ^ (row & 7)) * 16)) =
-                        make_uint4(hc[4 * cc], hc[4 * cc + 1], hc[4 * cc + 2], hc[4 * cc + 3]);
-                  }
+                for (int j = 0; j < HD / 2; ++j) {
+                  const uint32_t o = __shfl_xor_sync(FULL, hreg[j], 1);
+                  const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&hreg[j]), *reinterpret_cast<const __half2*>(&o));
+                  hreg[j] = *reinterpret_cast<const uint32_t*>(&sum);
                 }
-              }, [](int) {});
+                if (live && (row & 1) == 0) {
+                  const int gb = row >> 1;
+#pragma unroll
+                  for (int c = 0; c < CH; ++c)
+                    *reinterpret_cast<uint4*>(s_glob + (size_t)gb * (HD * 2) + ((c ^ (gb & 7)) * 16)) =
+                        make_uint4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+                  *reinterpret_cast<uint4*>(s_h2 + (size_t)row * (HD * 2) + ((c ^ (row & 7)) * 16)) =
+                      make_uint4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
+              }
             }
             stamp(30 + kind);
             if (kind == TC_E2) {
@@ -653,8 +700,9 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) epi_bench_kernel(long long*
     asm volatile("bar.sync 1, %0;" ::"r"(128 * NWG) : "memory");
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
-      epi_hidden<128, true>(base, with_bias ? par : nullptr, par + 128, par + 256, true, CEEUS_ACT_RELU,
-                            [&](int c0, const uint32_t (&hc)[16]) { tmem_st16(base + c0 / 2, hc); }, [](int) {});
+      uint32_t hreg[64];
+      epi_row<128, true>(base, (with_bias & 1) ? par : nullptr, par + 128, par + 256, true, (with_bias & 2) != 0, CEEUS_ACT_RELU, hreg);
+      store_hidden<128>(base, hreg);
       tmem_wait_st();
     }
     const long long t1 = clock64();
@@ -694,12 +742,44 @@ __device__ __forceinline__ const LayerDesc& mat_layer(const ModelDesc& md, int m
   }
 }
 
+// LayerNorm layer whose (hidden) output feeds the K rows of stage matrix m (-1: the rows are raw inputs)
+__device__ __forceinline__ int producer_of(int m) {
+  switch (m) {
+    case TC_E2: return TC_E1;
+    case TC_N1: case TC_G1: return TC_E2;  // folded aggregate rows
+    case TC_N2: return TC_N1;
+    case TC_N3: return TC_N2;
+    case TC_G2: return TC_G1;
+    case TC_G3: return TC_G2;
+    default: return -1;
+  }
+}
+
+// One block per member: can the LayerNorm affine be folded into the weights?  Needs ReLU, LayerNorm, and for every hidden
+// feature gamma != 0 and a moderate beta / |gamma| (the folded activation is scaled by 1 / |gamma| before the fp16 rounding).
+__global__ void tc_fold_flag_kernel(const float* __restrict__ w32, const ModelDesc md, const TcLayout tl, float* __restrict__ wpar) {
+  const int e = blockIdx.x;
+  const float* wm = w32 + (size_t)e * md.member_stride;
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = (md.act != CEEUS_ACT_RELU || !md.layer_norm) ? 1 : 0;
+  __syncthreads();
+  const int lnl[6] = {TC_E1, TC_E2, TC_N1, TC_N2, TC_G1, TC_G2};
+  for (int idx = threadIdx.x; idx < 6 * md.Hd; idx += blockDim.x) {
+    const LayerDesc& ld = mat_layer(md, lnl[idx / md.Hd]);
+    const float g = fabsf(wm[ld.g_off + idx % md.Hd]), b = fabsf(wm[ld.be_off + idx % md.Hd]);
+    if (md.layer_norm && (!(g > 1e-4f) || !(b <= 1024.f * g) || !(g < 1e4f))) atomicExch(&bad, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) wpar[(size_t)e * tl.par_floats + tl.par_fold] = bad ? 0.f : 1.f;
+}
+
 // scratch[e][m][k][n] (fp32): the logical B matrix of every stage in tile-K order, with the edge output layer folded into
 // the aggregate rows of N1 / G1, mean-aggregation scales applied and first-layer biases placed in the constant-one row.
 __global__ void tc_logical_kernel(const float* __restrict__ w32, const ModelDesc md, const TcLayout tl, const int* __restrict__ kmap,
-                                  float* __restrict__ scratch) {
+                                  const float* __restrict__ wpar, float* __restrict__ scratch) {
   const int e = blockIdx.y;
   const float* wm = w32 + (size_t)e * md.member_stride;
+  const bool fold = wpar[(size_t)e * tl.par_floats + tl.par_fold] != 0.f;
   float* out = scratch + (size_t)e * tl.scratch_floats;
   const LayerDesc& e3 = md.mlp[0].layer[2];
   const int NE = md.N * (md.N - 1);
@@ -733,6 +813,10 @@ __global__ void tc_logical_kernel(const float* __restrict__ w32, const ModelDesc
       } else if (code >= 0) {
         v = wm[ld.w_off + (size_t)code * ld.Npad + n];
       }
+      // folded LayerNorm: |gamma| of the producing layer scales the consumer's K row
+      const int pm = producer_of(m);
+      if (fold && pm >= 0 && (code >= kFold || (code >= 0 && m != TC_N1 && m != TC_G1)))
+        v *= fabsf(wm[mat_layer(md, pm).g_off + (code >= kFold ? code - kFold : code)]);
     }
     out[idx] = v;
   }
@@ -744,6 +828,7 @@ __global__ void tc_image_kernel(const float* __restrict__ w32, const ModelDesc m
   const int e = blockIdx.y;
   const float* wm = w32 + (size_t)e * md.member_stride;
   const float* L = scratch + (size_t)e * tl.scratch_floats;
+  const bool fold = wpar[(size_t)e * tl.par_floats + tl.par_fold] != 0.f;
   int rows_total = 0;
   for (int t = 0; t < TC_NMAT; ++t) rows_total += tl.mat[t].K;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < rows_total; idx += gridDim.x * blockDim.x) {
@@ -761,8 +846,10 @@ __global__ void tc_image_kernel(const float* __restrict__ w32, const ModelDesc m
       for (int n = 0; n < nreal; ++n) mean += rowp[n];
       mean /= (float)nreal;
     }
+    const LayerDesc& ldm = mat_layer(md, m);
     for (int n = 0; n < M.N; ++n) {
-      const float v = n < nreal ? rowp[n] - mean : 0.f;
+      float v = n < nreal ? rowp[n] - mean : 0.f;
+      if (fold && M.ln && n < nreal && wm[ldm.g_off + n] < 0.f) v = -v;  // sign(gamma) into the (centred) output column
       const int rk = n / M.nloc, nl = n % M.nloc;
       uint8_t* img = wimg + ((size_t)e * 2 + rk) * tl.image_bytes;
       reinterpret_cast<__half*>(img + M.off)[((size_t)(k / 8) * M.nloc + nl) * 8 + (k % 8)] = __float2half_rn(v);
@@ -784,9 +871,11 @@ __global__ void tc_image_kernel(const float* __restrict__ w32, const ModelDesc m
           float mean = 0.f;
           for (int n = 0; n < ld.N; ++n) mean += wm[ld.b_off + n];
           v -= mean / (float)ld.N;
+          if (fold && wm[ld.g_off + j] < 0.f) v = -v;
         }
       } else {
         v = wm[(w == 1 ? ld.g_off : ld.be_off) + j];
+        if (fold && w == 2) v /= fabsf(wm[ld.g_off + j]);  // beta / |gamma|
       }
     }
     wpar[(size_t)e * tl.par_floats + off + j] = v;
@@ -842,12 +931,12 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
     t.mat[m].K = kx + kagg; t.mat[m].kx = kx; t.mat[m].N = n; t.mat[m].nloc = n / 2; t.mat[m].ln = lnf;
   };
   mat(TC_E1, t.KE1, 0, Hd, 1);
-  mat(TC_E2, Hd, 0, Hd, 1);
+  mat(TC_E2, Hd, N == 2 ? 16 : 0, Hd, 1);  // + constant-one K block (bias) in R2 where R2 is free during the MMA
   mat(TC_N1, t.KXn, Hd, Hd, 1);
-  mat(TC_N2, Hd, 0, Hd, 1);
+  mat(TC_N2, Hd, 16, Hd, 1);
   mat(TC_N3, Hd, 0, 16, 0);
   mat(TC_G1, t.KXg, Hd, Hd, 1);
-  mat(TC_G2, Hd, 0, Hd, 1);
+  mat(TC_G2, Hd, 16, Hd, 1);
   mat(TC_G3, Hd, 0, 16, 0);
   int off = 0, po = 0, ko = 0, sf = 0;
   for (int m = 0; m < TC_NMAT; ++m) {
@@ -860,10 +949,11 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
     const bool first = m == TC_E1 || m == TC_N1 || m == TC_G1;
     const bool outl = m == TC_N3 || m == TC_G3;
     M.par_bias = -1; M.par_gamma = -1; M.par_beta = -1;
-    if (!first) { M.par_bias = po; po += outl ? 16 : Hd; }
+    if (!first && M.K == M.kx) { M.par_bias = po; po += outl ? 16 : Hd; }  // otherwise the bias is a K row
     if (!outl) { M.par_gamma = po; po += Hd; M.par_beta = po; po += Hd; }
   }
   t.image_bytes = off;
+  t.par_fold = po; po += 4;
   t.par_floats = po;
   t.kmap_len = ko;
   t.scratch_floats = sf;
@@ -887,8 +977,10 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
     for (int c = 0; c < Hd; ++c) kmap_host[t.mat[TC_N1].kmap_off + t.KXn + c] = kFold + c;
     hdr(TC_G1, 0);
     for (int c = 0; c < Hd; ++c) kmap_host[t.mat[TC_G1].kmap_off + t.KXg + c] = kFold + c;
-    for (int m : {TC_E2, TC_N2, TC_N3, TC_G2, TC_G3})
+    for (int m : {TC_E2, TC_N2, TC_N3, TC_G2, TC_G3}) {
       for (int k = 0; k < Hd; ++k) kmap_host[t.mat[m].kmap_off + k] = k;
+      if (t.mat[m].K > Hd) kmap_host[t.mat[m].kmap_off + Hd] = -2;  // bias row behind the constant-one column
+    }
   }
   // shared memory carve-up; the group size shrinks (fewer edge passes per group) until two slots fit
   for (;;) {
@@ -922,7 +1014,8 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
 cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, const int* kmap_dev, float* scratch,
                            uint8_t* wimg, float* wpar, cudaStream_t st) {
   dim3 grid(128, md.E);
-  tc_logical_kernel<<<grid, 256, 0, st>>>(w32, md, tl, kmap_dev, scratch);
+  tc_fold_flag_kernel<<<md.E, 256, 0, st>>>(w32, md, tl, wpar);
+  tc_logical_kernel<<<grid, 256, 0, st>>>(w32, md, tl, kmap_dev, wpar, scratch);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   tc_image_kernel<<<dim3(16, md.E), 256, 0, st>>>(w32, md, tl, scratch, wimg, wpar);

@@ -137,3 +137,39 @@ def test_tc_full_step_config2_and_unsupported():
     spec5, w5, n5, o5, g5 = build_inputs(c5)
     with pytest.raises(RuntimeError, match="CEEUS_PREC_TC"):
         product_model(c5, product_env(c5, g5), w5, n5, precision="tc")._rollout_engine(8, 4)
+
+
+@pytest.mark.parametrize("variant", ["signed_gamma", "zero_gamma"])
+@pytest.mark.parametrize("env_kind,n_obj,hidden", [("construction", 2, 128), ("construction", 4, 128), ("playground", 4, 64)])
+def test_tc_rollout_with_trained_like_layernorm(env_kind, n_obj, hidden, variant):
+    """Non-trivial LayerNorm affine parameters.  `signed_gamma`: gamma of either sign, beta != 0 -> the pack-time folding
+    (sign into this layer's weight columns, |gamma| into the consumer's rows, beta / |gamma| in the epilogue) is active;
+    `zero_gamma`: one gamma is exactly 0, which cannot be folded -> the general epilogue path must be taken."""
+    P, H = 97, 12
+    c = dict(kind="rollout", env=env_kind, n_obj=n_obj, model="gnn", hidden=hidden, layers=2, P=P, H=H,
+             wseed=4100 + n_obj + hidden, identity_norm=False, running=False, oseed=903)
+    spec, weights, norms, obs, goal = build_inputs(c)
+    rs = np.random.RandomState(77)
+    weights = dict(weights)
+    for k in list(weights):
+        if k.endswith(".gamma"):
+            g = rs.uniform(0.5, 1.5, weights[k].shape) * rs.choice([-1.0, 1.0], weights[k].shape)
+            if variant == "zero_gamma" and k.startswith("node_mlp.layers.0"):
+                g[:, 3] = 0.0
+            weights[k] = g.astype(np.float32)
+        elif k.endswith(".beta"):
+            weights[k] = (0.3 * rs.standard_normal(weights[k].shape)).astype(np.float32)
+    env = product_env(c, goal)
+    pm = product_model(c, env, weights, norms, precision="tc")
+    om = oracle_model(c, spec, weights, norms)
+    acts = rollout_actions(c, spec)
+    starts = np.tile(obs, (P, 1))
+    starts[:, :spec.state_dim] += (0.05 * rs.standard_normal((P, spec.state_dim))).astype(np.float32)
+    want = orc.rollout(om, torch.from_numpy(starts), torch.from_numpy(acts), torch.from_numpy(goal)).numpy()
+    pm.predict_n_steps(start_observations=torch.from_numpy(starts).to(DEV), start_states=None,
+                       policy=_Policy(torch.from_numpy(acts).to(DEV)), horizon=H)
+    eng = pm._rollout_engine(P, H)
+    got = eng.traj_.cpu().numpy()
+    assert eng.tc_status() == 0 and np.isfinite(got).all()
+    assert rel_l2(got, want) < TOL_TC
+    assert rel_err(got, want) < 5e-3
