@@ -142,8 +142,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default=os.environ.get("CEEUS_PRECISION", "auto"),
-                    help="tc (tcgen05, fp16 operands / fp32 accumulate, parity 1e-3) | fp32 (parity 1e-5) | auto = tc for the GNN "
-                         "ensemble, fp32 for the dense-MLP ensemble (no tensor-core kernel yet)")
+                    help="tc (tcgen05, fp16 operands / fp32 accumulate, parity 1e-3) | fp32 (parity 1e-5) | auto = tc")
     ap.add_argument("--cpu-sample-traj", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -157,7 +156,7 @@ def main():
 
     desc, c = case_dict(args.config, world)
     if args.precision == "auto":
-        args.precision = "tc" if c["model"] == "gnn" else "fp32"
+        args.precision = "tc"
     inputs = build_inputs(c)
     spec, weights, norms, obs, goal = inputs
     E, iters = 5, 3
@@ -271,7 +270,7 @@ def main():
         tc_peak, peak_src = peaks["bf16_burst"] / 2.0, f"{peaks['source']}: bf16_tflops / 2 (tf32-class dense peak)"
     flop_per_launch = float(flops_ms) * nenv * c["P"] * c["H"] * E
     achieved = flop_per_launch / (roll_ms / 1e3) / 1e12
-    kernel_name = ("rollout_gnn_tc_kernel" if tc_mode else "rollout_gnn_simt_kernel") if c["model"] == "gnn" else "rollout_mlp_simt_kernel"
+    kernel_name = f"rollout_{c['model']}_{'tc' if tc_mode else 'simt'}_kernel"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libceeus_b200.so")
-SOURCES = ["ceeus_api.cu", "rollout_simt.cu", "icem_kernels.cu", "tc_probe.cu", "rollout_tc.cu"]
+SOURCES = ["ceeus_api.cu", "rollout_simt.cu", "icem_kernels.cu", "tc_probe.cu", "rollout_tc.cu", "rollout_mlp_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared"]
 

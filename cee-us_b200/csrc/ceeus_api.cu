@@ -35,7 +35,8 @@ struct CeeusHandle_t {
   float* h_obs = nullptr;     // pinned staging
   float* h_action = nullptr;  // pinned staging
   int norm_floats = 0;
-  TcLayout tc{};             // CEEUS_PREC_TC only
+  TcLayout tc{};             // CEEUS_PREC_TC only (GNN ensemble)
+  TcMlpLayout tcm{};         // CEEUS_PREC_TC only (dense-MLP ensemble)
   uint8_t* d_wimg = nullptr;
   float* d_wpar = nullptr;
   int* d_kmap = nullptr;         // K permutation / folding map of every stage matrix
@@ -243,7 +244,16 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
   if (e == cudaSuccess) e = alloc(&h->d_irdft, (size_t)2 * h->F * c.horizon);
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_obs, (size_t)c.num_envs * md.O * sizeof(float));
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_action, (size_t)c.num_envs * md.U * sizeof(float));
-  if (e == cudaSuccess && c.precision == CEEUS_PREC_TC) {
+  if (e == cudaSuccess && c.precision == CEEUS_PREC_TC && c.model_kind == CEEUS_MODEL_MLP) {
+    if (!make_mlp_tc_layout(md, h->num_sms, &h->tcm)) {
+      ceeus_destroy(h);
+      return fail(nullptr, CEEUS_ERR_INVALID,
+                  "CEEUS_PREC_TC supports the dense-MLP ensemble with hidden_dim 128/256, no LayerNorm, state dim <= 128");
+    }
+    e = cudaMalloc(&h->d_wimg, (size_t)md.E * 2 * h->tcm.image_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_tc_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(h->d_tc_err, 0, sizeof(int));
+  } else if (e == cudaSuccess && c.precision == CEEUS_PREC_TC) {
     std::vector<int> kmap(4096, -1);
     if (c.model_kind != CEEUS_MODEL_GNN || !make_tc_layout(md, h->num_sms, &h->tc, kmap.data())) {
       ceeus_destroy(h);
@@ -304,7 +314,9 @@ int ceeus_set_weights(CeeusHandle h, const float* const* dev_ptrs, int n, void* 
     const TensorSpec& t = h->wspec[i];
     LAUNCH(h, launch_repack(dev_ptrs[i], h->d_weights, h->md.E, t.rows, t.cols, h->md.member_stride, t.dst_off, t.dst_ld, S(stream)));
   }
-  if (h->cfg.precision == CEEUS_PREC_TC)
+  if (h->cfg.precision == CEEUS_PREC_TC && h->md.kind == CEEUS_MODEL_MLP)
+    LAUNCH(h, launch_mlp_tc_pack(h->d_weights, h->md, h->tcm, h->d_wimg, S(stream)));
+  else if (h->cfg.precision == CEEUS_PREC_TC)
     LAUNCH(h, launch_tc_pack(h->d_weights, h->md, h->tc, h->d_kmap, h->d_tc_scratch, h->d_wimg, h->d_wpar, S(stream)));
   h->weights_set = true;
   return CEEUS_OK;
@@ -353,7 +365,9 @@ static int do_rollout(CeeusHandle h, const float* start_obs_dev, int traj_per_st
   ra.weights = h->d_weights; ra.norm = h->d_norm; ra.start_obs = start_obs_dev; ra.goal = h->d_goal;
   ra.actions = actions_dev; ra.traj = traj_dev; ra.n = n; ra.H = h->cfg.horizon;
   ra.traj_per_start = traj_per_start; ra.traj_per_goal = traj_per_goal;
-  if (h->cfg.precision == CEEUS_PREC_TC)
+  if (h->cfg.precision == CEEUS_PREC_TC && h->md.kind == CEEUS_MODEL_MLP)
+    LAUNCH(h, launch_rollout_mlp_tc(h->md, ra, h->tcm, h->d_wimg, h->d_tc_err, st));
+  else if (h->cfg.precision == CEEUS_PREC_TC)
     LAUNCH(h, launch_rollout_gnn_tc(h->md, ra, h->tc, h->d_wimg, h->d_wpar, h->d_tc_err, h->d_tc_dbg, st));
   else if (h->md.kind == CEEUS_MODEL_GNN) LAUNCH(h, launch_rollout_gnn_simt(h->md, ra, h->num_sms, st));
   else LAUNCH(h, launch_rollout_mlp_simt(h->md, ra, st));

@@ -61,6 +61,20 @@ cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                   const float* wpar, int* err_flag, long long* dbg, cudaStream_t st);
 
+// ---- tensor-core rollout of the dense-MLP ensemble (rollout_mlp_tc.cu) ----
+struct TcMlpMat { int K, N, nloc, off; };
+struct TcMlpLayout {
+  int HD, L, K1, NOUT;      // hidden width, hidden layers, padded input K, padded output width
+  TcMlpMat mat[kMaxLayers];
+  int image_bytes, nrm_floats;
+  int sm_w, sm_nrm, sm_state, sm_snrm, sm_act, sm_bar, smem_bytes;
+  int pairs;
+};
+bool make_mlp_tc_layout(const ModelDesc& md, int num_sms, TcMlpLayout* out);
+cudaError_t launch_mlp_tc_pack(const float* w32, const ModelDesc& md, const TcMlpLayout& tl, uint8_t* wimg, cudaStream_t st);
+cudaError_t launch_rollout_mlp_tc(const ModelDesc& md, const RolloutArgs& ra, const TcMlpLayout& tl, const uint8_t* wimg, int* err_flag,
+                                  cudaStream_t st);
+
 cudaError_t launch_epi_bench(int nwg, int with_bias, int with_mma, long long* out_dev);  // profiling aid (ceeus_selftest_epilogue)
 
 // ---- iCEM kernels (icem_kernels.cu) ----

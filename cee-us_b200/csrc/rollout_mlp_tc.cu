@@ -1,0 +1,331 @@
+// CEEUS_PREC_TC for the dense-MLP ensemble: the whole horizon of ParallelNNDeterministicEnsemble.predict_n_steps
+// (mbrl/models/mlp_ensemble.py:502-611; model = MLPParallelEnsemble, simple.py:18-101: [Linear -> act] x L -> Linear,
+// yaml construction/common/mlp_ensemble.yaml: 62 -> 256 -> 256 -> 256 -> 58, SiLU, no LayerNorm) in one persistent launch.
+//
+// Same machinery as rollout_tc.cu: CTA pairs (tcgen05 cta_group::2, M = 256), one ensemble member per pair, all L+1 weight
+// matrices resident in shared memory as fp16 (split by output column between the two CTAs: 169 KB per CTA for the yaml model),
+// A operands in TMEM (tcgen05.mma TS form), biases in a constant-one K column.  One tile of 128 trajectories per CTA; two
+// threads per row, each owning half of the 256 accumulator columns (no LayerNorm, so the epilogue is purely element-wise).
+// TMEM: accumulator [0, HD), A operand [HD, HD + HD/2), constant-one block [HD + HD/2, +8).
+// SiLU is evaluated as h + h * tanh(h), h = x / 2, with tanh.approx.f32 (one MUFU per element, 2^-11 relative).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+#include "tc_rollout_common.cuh"
+
+namespace ceeus {
+
+namespace {
+using namespace tc;
+
+constexpr int kMlpThreads = 256;
+
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool SILU>
+__device__ __forceinline__ float mlp_act(float x, int act) {
+  if constexpr (SILU) {
+    const float h = 0.5f * x;
+    return fmaf(h, tanh_approx(h), h);
+  } else {
+    return act_fn(x, act);
+  }
+}
+
+template <int HD, bool SILU>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
+    rollout_mlp_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcMlpLayout tl, const uint8_t* __restrict__ wimg,
+                          int* __restrict__ err) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int W = HD / 2;  // accumulator columns per thread in a hidden layer
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int U = md.U, sd = md.sd, O = md.O, in = sd + U, L = tl.L, K1 = tl.K1;
+
+  int e, lp, np;
+  {
+    const int base = tl.pairs / md.E, rem = tl.pairs % md.E;
+    if (pair < rem * (base + 1)) { e = pair / (base + 1); lp = pair % (base + 1); np = base + 1; }
+    else { const int q2 = pair - rem * (base + 1); e = rem + q2 / base; lp = q2 % base; np = base; }
+  }
+  const int per_worker = (ra.n + 2 * np - 1) / (2 * np);
+  const int rounds = (per_worker + 127) / 128;
+  const int T = (per_worker + rounds - 1) / rounds;  // trajectories per tile, <= 128
+  const int worker = lp * 2 + (int)rank;
+
+  uint8_t* sW = smem + tl.sm_w;
+  float* sNrm = reinterpret_cast<float*>(smem + tl.sm_nrm);
+  float* s_state = reinterpret_cast<float*>(smem + tl.sm_state);  // [128][sd] raw fp32 state
+  __half* snrm = reinterpret_cast<__half*>(smem + tl.sm_snrm);    // [128][K1] normalised [state | action | 1 | 0..]
+  float* s_act = reinterpret_cast<float*>(smem + tl.sm_act);      // [128][8] next step's raw action
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tl.sm_bar);
+  uint64_t* wbar = bars;
+  uint64_t* a_ready = bars + 1;
+  uint64_t* d_ready = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  if (tid == 0) *abort_flag = 0;
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(wbar, 1);
+      mbar_init(a_ready, 16);  // 8 warps x 2 CTAs
+      mbar_init(d_ready, 1);
+      fence_barrier_init();
+      mbar_expect_tx(wbar, (uint32_t)tl.image_bytes);
+      bulk_g2s(sW, wimg + ((size_t)e * 2 + rank) * tl.image_bytes, (uint32_t)tl.image_bytes, wbar);
+    }
+    __syncwarp();
+    tmem_alloc<2>(tmem_slot, 512);
+    tmem_relinquish<2>();
+  }
+  // normalisers: input group as (mean, 1/std), output group as (mean, std)
+  for (int i = tid; i < tl.nrm_floats; i += kMlpThreads) {
+    const float v = __ldg(ra.norm + i);
+    sNrm[i] = (i >= md.nrm.in_all + in && i < md.nrm.out_all) ? 1.f / v : v;
+  }
+  tc_fence_before();
+  __syncthreads();
+  Ctx cx;
+  cx.abort = abort_flag; cx.err = err;
+  if (warp == 0 && lane == 0) wait_bar(cx, wbar, 0, 1);
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  if (*tmem_slot != 0u && tid == 0) atomicExch(err, 7);
+  cx.a_ready_leader[0] = mapa(smem_u32(a_ready), 0);
+  cx.a_ready_leader[1] = cx.a_ready_leader[0];
+
+  const int hf = warp >> 2;   // column half
+  const int q = warp & 3;     // TMEM lane quadrant
+  const int row = tid & 127;  // tile row == TMEM lane == trajectory of the tile
+  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const uint32_t t_acc = lane_base, t_a = lane_base + HD, t_one = lane_base + HD + HD / 2;
+  const float* __restrict__ nrm = sNrm;
+  const int act = md.act;
+  const bool issuer_warp = rank == 0 && warp == 0;
+  uint32_t aph = 0, dph = 0;
+  const uint32_t wbase = smem_u32(sW);
+  auto mma_layer = [&](int m) {
+    if (!issuer_warp) return;
+    const bool ok = wait_bar(cx, a_ready, aph, 2);
+    aph ^= 1u;
+    tc_fence_after();
+    if (ok) {
+      const uint32_t elected = elect_one();
+      const TcMlpMat& mm = tl.mat[m];
+      const uint32_t idesc = make_idesc_f16(256, mm.N);
+      const uint32_t lbo_b = (uint32_t)mm.nloc * 16;
+      const uint64_t db0 = make_smem_desc(wbase + (uint32_t)mm.off, lbo_b, 128);
+      const uint32_t db_step = (2u * lbo_b) >> 4;
+      const int kall = mm.K / 16;
+#pragma unroll 2
+      for (int ks = 0; ks < kall; ++ks)
+        umma_f16_ts_cg2_elect(0u, (uint32_t)HD + (uint32_t)(8 * ks), db0 + (uint64_t)((uint32_t)ks * db_step), idesc, ks > 0 ? 1u : 0u, elected);
+      umma_commit_cg2_mc_elect(d_ready, 0x3, elected);
+    }
+    __syncwarp();
+  };
+  auto cta_sync = [&]() { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+  // the constant-one K block behind the hidden activations (bias rows of layers 1..L): written once
+  tmem_st4(t_one, make_uint4(0x00003c00u, 0u, 0u, 0u));  // both threads of a row write the same value
+  tmem_st4(t_one + 4, make_uint4(0u, 0u, 0u, 0u));
+  tmem_wait_st();
+
+  for (int rd = 0; rd < rounds; ++rd) {
+    const int w_lo = min(ra.n, worker * per_worker), w_hi = min(ra.n, w_lo + per_worker);
+    const int p0 = w_lo + rd * T;
+    const int Gc = max(0, min(T, w_hi - p0));
+    const bool live = row < Gc;
+    cta_sync();
+    // ---- tile init: start observation -> state, snrm, traj[0] ----
+    for (int idx = tid; idx < (128 * K1) / 8; idx += kMlpThreads) reinterpret_cast<uint4*>(snrm)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    for (int idx = tid; idx < Gc * O; idx += kMlpThreads) {
+      const int b = idx / O, c = idx % O;
+      const float v = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
+      ra.traj[((size_t)e * ra.n + p0 + b) * O + c] = v;
+      if (c < sd) s_state[b * sd + c] = v;
+    }
+    cta_sync();
+    for (int idx = tid; idx < Gc * in; idx += kMlpThreads) {
+      const int b = idx / in, c = idx % in;
+      const float x = c < sd ? s_state[b * sd + c] : __ldg(ra.actions + ((size_t)(p0 + b) * ra.H) * U + (c - sd));
+      snrm[b * K1 + c] = __float2half_rn((x - nrm[md.nrm.in_all + c]) * nrm[md.nrm.in_all + in + c]);
+    }
+    if (tid < 128 && live) snrm[tid * K1 + in] = __float2half_rn(1.f);
+    cta_sync();
+
+    for (int h = 0; h < ra.H; ++h) {
+      if (hf == 1 && live && h + 1 < ra.H) {  // prefetch the next step's action; consumed in the output epilogue
+        for (int j = 0; j < U; ++j)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_act + row * 8 + j)),
+                       "l"(ra.actions + ((size_t)(p0 + row) * ra.H + h + 1) * U + j)
+                       : "memory");
+      }
+      // A operand of layer 0: this row's normalised input, the two halves write alternate 16-byte chunks
+      {
+        const uint4* sb = reinterpret_cast<const uint4*>(snrm + row * K1);
+        for (int c = hf; c < K1 / 8; c += 2) tmem_st4(t_a + 4 * c, sb[c]);
+      }
+      signal_a(cx, 0, lane);
+      mma_layer(0);
+      float* outp = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
+
+#pragma unroll 1
+      for (int m = 0; m <= L; ++m) {
+        wait_bar(cx, d_ready, dph, 10 + m);
+        dph ^= 1u;
+        tc_fence_after();
+        const bool warp_on = __any_sync(FULL, live);
+        if (m < L) {
+          // ---------------- hidden layer: activation -> fp16 -> next A operand ----------------
+          if (warp_on) {
+#pragma unroll
+            for (int c0 = 0; c0 < W; c0 += 32) {
+              float x[32];
+              uint32_t hc[16];
+              tmem_ld32(t_acc + hf * W + c0, *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) hc[j / 2] = pack_half2(mlp_act<SILU>(x[j], act), mlp_act<SILU>(x[j + 1], act));
+              tmem_st16(t_a + (hf * W + c0) / 2, hc);
+            }
+          }
+          signal_a(cx, 0, lane);
+          mma_layer(m + 1);
+        } else {
+          // ---------------- output layer: delta -> de-normalise, residual update (mlp_ensemble.py:530-573) ----------------
+          const int OW = tl.NOUT / 2;  // output columns per thread
+          if (warp_on) {
+            for (int c0 = 0; c0 < OW; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld16(t_acc + hf * OW + c0, v);
+              tmem_wait_ld();
+              if (live) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const int d = hf * OW + c0 + j;
+                  if (d < sd) {
+                    const float nv = s_state[row * sd + d] + fmaf(nrm[md.nrm.out_all + sd + d], __uint_as_float(v[j]), nrm[md.nrm.out_all + d]);
+                    s_state[row * sd + d] = nv;
+                    outp[(size_t)row * O + d] = nv;
+                    snrm[row * K1 + d] = __float2half_rn((nv - nrm[md.nrm.in_all + d]) * nrm[md.nrm.in_all + in + d]);
+                  }
+                }
+              }
+            }
+          }
+          if (hf == 1 && live) {
+            if (h + 1 < ra.H) {
+              asm volatile("cp.async.wait_all;" ::: "memory");
+              for (int j = 0; j < U; ++j)
+                snrm[row * K1 + sd + j] = __float2half_rn((s_act[row * 8 + j] - nrm[md.nrm.in_all + sd + j]) * nrm[md.nrm.in_all + in + sd + j]);
+            }
+            // goal part of the observation (env.obs_postproc)
+            const float* g = ra.goal + (size_t)((p0 + row) / ra.traj_per_goal) * md.G;
+            for (int c = 0; c < md.G; ++c) outp[(size_t)row * O + sd + c] = __ldg(g + c);
+          }
+          tc_fence_before();
+        }
+      }
+      cta_sync();  // snrm of the next step is complete
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) tmem_dealloc<2>(0u, 512);
+}
+
+// fp32 packed weights -> fp16 B-operand images with the bias in the constant-one K row
+__global__ void mlp_tc_pack_kernel(const float* __restrict__ w32, const ModelDesc md, const TcMlpLayout tl, uint8_t* __restrict__ wimg) {
+  const int e = blockIdx.y;
+  const float* wm = w32 + (size_t)e * md.member_stride;
+  int total = 0;
+  for (int m = 0; m <= tl.L; ++m) total += tl.mat[m].K * tl.mat[m].N;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    int m = 0, base = 0;
+    for (int t = 0; t <= tl.L; ++t) {
+      if (idx >= base + tl.mat[t].K * tl.mat[t].N) base += tl.mat[t].K * tl.mat[t].N;
+      else { m = t; break; }
+    }
+    const TcMlpMat& M = tl.mat[m];
+    const int k = (idx - base) / M.N, n = (idx - base) % M.N;
+    const LayerDesc& ld = md.mlp[0].layer[m];
+    const int kreal = m == 0 ? md.sd + md.U : tl.HD;  // the constant-one column follows the real inputs
+    float v = 0.f;
+    if (n < ld.N) {
+      if (k < kreal) v = wm[ld.w_off + (size_t)k * ld.Npad + n];
+      else if (k == kreal) v = wm[ld.b_off + n];
+    }
+    const int rk = n / M.nloc, nl = n % M.nloc;
+    uint8_t* img = wimg + ((size_t)e * 2 + rk) * tl.image_bytes;
+    reinterpret_cast<__half*>(img + M.off)[((size_t)(k / 8) * M.nloc + nl) * 8 + (k % 8)] = __float2half_rn(v);
+  }
+}
+
+template <int HD, bool SILU>
+cudaError_t launch_mlp_t(const ModelDesc& md, const RolloutArgs& ra, const TcMlpLayout& tl, const uint8_t* wimg, int* err_flag,
+                         cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(rollout_mlp_tc_kernel<HD, SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
+  if (e != cudaSuccess) return e;
+  rollout_mlp_tc_kernel<HD, SILU><<<dim3(2 * tl.pairs), kMlpThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, err_flag);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool make_mlp_tc_layout(const ModelDesc& md, int num_sms, TcMlpLayout* out) {
+  TcMlpLayout t{};
+  if (md.kind != CEEUS_MODEL_MLP || (md.Hd != 128 && md.Hd != 256) || md.layer_norm || md.L < 1 || md.L + 1 > kMaxLayers) return false;
+  if (md.U > 8 || md.sd > 128) return false;
+  t.HD = md.Hd;
+  t.L = md.L;
+  t.K1 = round_up(md.sd + md.U + 1, 16);
+  t.NOUT = round_up(md.sd, 32);
+  if (t.K1 > md.Hd || t.NOUT > md.Hd) return false;
+  int off = 0;
+  for (int m = 0; m <= md.L; ++m) {
+    TcMlpMat& M = t.mat[m];
+    M.K = m == 0 ? t.K1 : md.Hd + 16;
+    M.N = m == md.L ? t.NOUT : md.Hd;
+    M.nloc = M.N / 2;
+    M.off = off;
+    off += (M.K / 8) * M.nloc * 16;
+  }
+  t.image_bytes = off;
+  t.nrm_floats = 2 * (md.sd + md.U) + 2 * md.sd;
+  int sm = 0;
+  t.sm_w = sm; sm += round_up(t.image_bytes, 1024);
+  t.sm_nrm = sm; sm += round_up(t.nrm_floats * 4, 16);
+  t.sm_state = sm; sm += round_up(128 * md.sd * 4, 16);
+  t.sm_snrm = sm; sm += 128 * t.K1 * 2;
+  t.sm_act = sm; sm += 128 * 8 * 4;
+  t.sm_bar = sm; sm += 64;
+  t.smem_bytes = sm;
+  if (t.smem_bytes > 227 * 1024) return false;
+  t.pairs = num_sms / 2;
+  if (t.pairs < md.E) return false;
+  *out = t;
+  return true;
+}
+
+cudaError_t launch_mlp_tc_pack(const float* w32, const ModelDesc& md, const TcMlpLayout& tl, uint8_t* wimg, cudaStream_t st) {
+  mlp_tc_pack_kernel<<<dim3(128, md.E), 256, 0, st>>>(w32, md, tl, wimg);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rollout_mlp_tc(const ModelDesc& md, const RolloutArgs& ra, const TcMlpLayout& tl, const uint8_t* wimg, int* err_flag,
+                                  cudaStream_t st) {
+  const bool silu = md.act == CEEUS_ACT_SILU;
+  if (md.Hd == 256) return silu ? launch_mlp_t<256, true>(md, ra, tl, wimg, err_flag, st) : launch_mlp_t<256, false>(md, ra, tl, wimg, err_flag, st);
+  return silu ? launch_mlp_t<128, true>(md, ra, tl, wimg, err_flag, st) : launch_mlp_t<128, false>(md, ra, tl, wimg, err_flag, st);
+}
+
+}  // namespace ceeus

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
+#include "tc_rollout_common.cuh"
 
 namespace ceeus {
 
@@ -34,44 +35,9 @@ using namespace tc;
 
 constexpr int kTcThreads = 256;  // 2 warpgroups; warp 0 of each also issues its slot's MMAs (leader CTA): no dedicated issuer
                                  // warps, so ptxas may use 255 registers per thread and batch the parameter loads
-constexpr uint32_t FULL = 0xffffffffu;
 constexpr int kFold = 100000;    // kmap code >= kFold: folded aggregate row (index code - kFold)
 
 __device__ __forceinline__ void wg_sync(int s) { asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory"); }
-
-__device__ __forceinline__ float act_fn(float x, int act) {
-  switch (act) {
-    case CEEUS_ACT_RELU: return fmaxf(x, 0.f);
-    case CEEUS_ACT_SILU: return x / (1.f + __expf(-x));
-    case CEEUS_ACT_TANH: return tanhf(x);
-    default: return x;
-  }
-}
-
-struct Ctx {
-  volatile int* abort;  // per CTA
-  int* err;             // global
-  uint32_t a_ready_leader[2];  // cluster addresses of the leader's a_ready barriers
-};
-
-__device__ __forceinline__ bool wait_bar(const Ctx& cx, uint64_t* bar, uint32_t parity, int code) {
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
-    if (mbar_try_wait(bar, parity)) return true;
-    if ((it & 1023u) == 1023u && *cx.abort) return false;
-  }
-  *cx.abort = 1;
-  atomicExch(cx.err, code);
-  return false;
-}
-
-// The A operand of this warpgroup's next MMA stage is complete in TMEM: retire the tcgen05.st, order them (and the
-// earlier tcgen05.ld of the accumulator) before the barrier, one arrival per warp on the leader's barrier.
-__device__ __forceinline__ void signal_a(const Ctx& cx, int s, int lane) {
-  tmem_wait_st();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive_cluster_relaxed(cx.a_ready_leader[s]);
-}
 
 template <int HD>
 __device__ __forceinline__ void load_acc(uint32_t taddr, float (&x)[HD]) {

@@ -78,7 +78,7 @@ def test_tc_rollout_matches_oracle_fresh_inputs(env_kind, n_obj, hidden, P, H):
     assert rel_err(got, want) < 5e-3
 
 
-@pytest.mark.parametrize("name", ["mpc_gnn_c2_curious", "mpc_gnn_c6_stack_extr", "mpc_gnn_pg4_curious"])
+@pytest.mark.parametrize("name", ["mpc_gnn_c2_curious", "mpc_gnn_c6_stack_extr", "mpc_gnn_pg4_curious", "mpc_mlp_c4_curious"])
 def test_tc_mpc_steps_against_oracle(name):
     """Whole MPC steps in TC mode.  The oracle is re-run from the product's own (mean, std, elites) at every step so
     that one legitimately ambiguous elite (cost tie within tolerance) cannot snowball into a different plan."""
@@ -133,7 +133,7 @@ def test_tc_full_step_config2_and_unsupported():
     ctrl_b = product_controller(c, env, product_model(c, env, weights, norms, precision="tc"), precision="tc", seed=11)
     ctrl_b.beginning_of_rollout(observation=obs, state=None, mode="train")
     np.testing.assert_array_equal(ctrl_b.get_action(obs, None), a1)
-    c5 = dict(CASES["rollout_mlp_c4"])
+    c5 = dict(CASES["rollout_mlp_c4"], hidden=64)  # the tensor-core MLP kernel needs hidden_dim 128 / 256
     spec5, w5, n5, o5, g5 = build_inputs(c5)
     with pytest.raises(RuntimeError, match="CEEUS_PREC_TC"):
         product_model(c5, product_env(c5, g5), w5, n5, precision="tc")._rollout_engine(8, 4)
@@ -171,5 +171,47 @@ def test_tc_rollout_with_trained_like_layernorm(env_kind, n_obj, hidden, variant
     eng = pm._rollout_engine(P, H)
     got = eng.traj_.cpu().numpy()
     assert eng.tc_status() == 0 and np.isfinite(got).all()
+    assert rel_l2(got, want) < TOL_TC
+    assert rel_err(got, want) < 5e-3
+
+
+def test_tc_mlp_rollout_matches_reference_fixture():
+    """Dense-MLP ensemble (mlp_ensemble_cee_us.yaml: 62-256-256-256-58, SiLU) on the tensor-core path."""
+    name = "rollout_mlp_c4"
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    model = product_model(c, env, weights, norms, precision="tc")
+    acts = torch.from_numpy(rollout_actions(c, spec)).to(DEV)
+    start = torch.from_numpy(obs).view(1, -1).expand(c["P"], -1).contiguous().to(DEV)
+    buf, _ = model.predict_n_steps(start_observations=start, start_states=None, policy=_Policy(acts), horizon=c["H"])
+    nxt = buf.as_array("next_observations").cpu().numpy()
+    eng = model._rollout_engine(c["P"], c["H"])
+    assert eng.tc_status() == 0
+    assert rel_l2(nxt, g["next_observations"]) < TOL_TC
+    assert rel_err(nxt, g["next_observations"]) < 5e-3
+
+
+@pytest.mark.parametrize("n_obj,hidden,layers,P,H", [(4, 256, 3, 300, 30), (2, 256, 3, 77, 5), (4, 128, 2, 1000, 8), (6, 256, 1, 130, 4)])
+def test_tc_mlp_rollout_matches_oracle_fresh_inputs(n_obj, hidden, layers, P, H):
+    c = dict(kind="rollout", env="construction", n_obj=n_obj, model="mlp", hidden=hidden, layers=layers, P=P, H=H,
+             wseed=3000 + n_obj + hidden, identity_norm=False, running=False, oseed=55 + P)
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    pm = product_model(c, env, weights, norms, precision="tc")
+    om = oracle_model(c, spec, weights, norms)
+    acts = rollout_actions(c, spec)
+    rs = np.random.RandomState(6)
+    starts = np.tile(obs, (P, 1))
+    starts[:, :spec.state_dim] += (0.05 * rs.standard_normal((P, spec.state_dim))).astype(np.float32)
+    want = orc.rollout(om, torch.from_numpy(starts), torch.from_numpy(acts), torch.from_numpy(goal)).numpy()
+    pm.predict_n_steps(start_observations=torch.from_numpy(starts).to(DEV), start_states=None,
+                       policy=_Policy(torch.from_numpy(acts).to(DEV)), horizon=H)
+    eng = pm._rollout_engine(P, H)
+    got = eng.traj_.cpu().numpy()
+    assert eng.tc_status() == 0 and np.isfinite(got).all()
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[..., spec.state_dim:], want[..., spec.state_dim:])
     assert rel_l2(got, want) < TOL_TC
     assert rel_err(got, want) < 5e-3
