@@ -18,7 +18,7 @@ for nmma in (0, 1, 4, 8, 16, 32):
     print(f"nmma={nmma:2d} rc={rc} ld_latency={buf[0]} st_latency={buf[1]} mma_batch_done={buf[2]} ld_issued_at={buf[3]}")
 
 for mma in (0, 1):
-    for bias in (0, 1):
+    for bias in (0, 1, 2):  # bit 0: bias add, bit 1: folded LayerNorm affine
         for nw in (1, 2, 3):
             v = (C.c_longlong * 2)()
             rc = lib.ceeus_selftest_epilogue(nw, bias, mma, v)
