@@ -33,8 +33,11 @@ namespace ceeus {
 namespace {
 using namespace tc;
 
-constexpr int kTcThreads = 256;  // 2 warpgroups; warp 0 of each also issues its slot's MMAs (leader CTA): no dedicated issuer
-                                 // warps, so ptxas may use 255 registers per thread and batch the parameter loads
+// Warpgroups ("slots") per CTA: each owns 2 * HD TMEM columns, so the 512 columns hold two slots at Hd = 128 (256 threads, up to
+// 255 registers each: the epilogue keeps a whole 128-column row in registers) and four at Hd = 64 (512 threads, 128 registers).
+// Warp 0 of every slot also issues that slot's MMAs (leader CTA): there are no dedicated issuer warps.
+template <int HD>
+struct TcSlots { static constexpr int value = 512 / (2 * HD); };
 constexpr int kFold = 100000;    // kmap code >= kFold: folded aggregate row (index code - kFold)
 
 __device__ __forceinline__ void wg_sync(int s) { asm volatile("bar.sync %0, 128;" ::"r"(1 + s) : "memory"); }
@@ -209,11 +212,13 @@ __device__ __forceinline__ uint4 pack8(const float (&acc)[8]) {
 
 // ------------------------------------------------------------------------------------------------------------
 template <int HD, bool RELU>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::value, 1)
     rollout_gnn_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcLayout tl, const uint8_t* __restrict__ wimg,
                           const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int CH = HD / 8;  // 16-byte chunks per hidden row
+  constexpr int NS = TcSlots<HD>::value;
+  constexpr int kTcThreads = 128 * NS;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
@@ -227,7 +232,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     if (pair < rem * (base + 1)) { e = pair / (base + 1); lp = pair % (base + 1); np = base + 1; }
     else { const int q = pair - rem * (base + 1); e = rem + q / base; lp = q % base; np = base; }
   }
-  const int per_worker = (ra.n + 4 * np - 1) / (4 * np);
+  const int per_worker = (ra.n + 2 * NS * np - 1) / (2 * NS * np);
   const int rounds = (per_worker + tl.Tmax - 1) / tl.Tmax;
   const int T = (per_worker + rounds - 1) / rounds;  // trajectories per group, <= Tmax
   const int Te = tl.Te;
@@ -238,9 +243,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   float* sPar = reinterpret_cast<float*>(smem + tl.sm_par);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tl.sm_bar);
   uint64_t* wbar = bars;        // weights landed
-  uint64_t* a_ready = bars + 1; // [2] (used in the leader CTA)
-  uint64_t* d_ready = bars + 3; // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* a_ready = bars + 1;       // [NS] (used in the leader CTA)
+  uint64_t* d_ready = bars + 1 + NS;  // [NS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * NS);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   // ---- one-time setup ----
@@ -248,10 +253,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   if (warp == 0) {
     if (lane == 0) {
       mbar_init(wbar, 1);
-      mbar_init(&a_ready[0], 8);
-      mbar_init(&a_ready[1], 8);
-      mbar_init(&d_ready[0], 1);
-      mbar_init(&d_ready[1], 1);
+      for (int i = 0; i < NS; ++i) {
+        mbar_init(&a_ready[i], 8);
+        mbar_init(&d_ready[i], 1);
+      }
       fence_barrier_init();
       mbar_expect_tx(wbar, (uint32_t)tl.image_bytes);
       bulk_g2s(sW, wimg + ((size_t)e * 2 + rank) * tl.image_bytes, (uint32_t)tl.image_bytes, wbar);
@@ -281,15 +286,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   // warp uniform for the compiler (checked once)
   if (*tmem_slot != 0u && tid == 0) atomicExch(err, 7);
   constexpr uint32_t tmem_base = 0u;
-  cx.a_ready_leader[0] = mapa(smem_u32(&a_ready[0]), 0);
-  cx.a_ready_leader[1] = mapa(smem_u32(&a_ready[1]), 0);
+  for (int i = 0; i < NS; ++i) cx.a_ready_leader[i] = mapa(smem_u32(&a_ready[i]), 0);
 
   {
     // =========================== warpgroup: tile builder + epilogue ===========================
     const int s = warp >> 2;       // slot
     const int q = warp & 3;        // TMEM lane quadrant
     const int row = tid & 127;     // tile row == TMEM lane
-    const int worker = (lp * 2 + (int)rank) * 2 + s;
+    const int worker = (lp * 2 + (int)rank) * NS + s;
     uint8_t* slot = smem + tl.sm_slot[s];
     uint8_t* s_h2 = slot + tl.so_h2;      // [128][HD] fp16, 16-byte chunks swizzled by (row & 7)
     uint8_t* s_agg = slot + tl.so_agg;    // [Te*N][HD] fp16 sums over the N-1 outgoing edges (N >= 3)
@@ -875,6 +879,7 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
   if (md.D > 16 || md.A > 16 || md.U > 8 || md.N < 2) return false;
   const int N = md.N, NA = md.D + md.S, NE = N * (N - 1), Hd = md.Hd;
   t.HD = Hd;
+  t.NS = 512 / (2 * Hd);
   t.AUp = round_up(md.A + md.U + 1, 8);
   t.NAp = round_up(NA, 8);
   t.SNs = t.AUp + N * t.NAp;
@@ -962,9 +967,8 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
     t.so_snrm = so; so += round_up(t.Tmax * t.SNs * 2, 16);
     t.so_tail = so; so += round_up(t.Tmax * t.tail * 4, 16);
     so = round_up(so, 128);
-    t.sm_slot[0] = sm; sm += so;
-    t.sm_slot[1] = sm; sm += so;
-    t.sm_bar = sm; sm += 64;
+    for (int i = 0; i < t.NS; ++i) { t.sm_slot[i] = sm; sm += so; }
+    t.sm_bar = sm; sm += 128;
     t.smem_bytes = sm;
     if (t.smem_bytes <= 227 * 1024) break;
     if (N == 2 || t.n_pass_max <= 1) return false;
@@ -993,7 +997,7 @@ static cudaError_t launch_tc_t(const ModelDesc& md, const RolloutArgs& ra, const
                                const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(rollout_gnn_tc_kernel<HD, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
   if (e != cudaSuccess) return e;
-  rollout_gnn_tc_kernel<HD, RELU><<<dim3(2 * tl.pairs), kTcThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
+  rollout_gnn_tc_kernel<HD, RELU><<<dim3(2 * tl.pairs), 128 * TcSlots<HD>::value, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
   return cudaGetLastError();
 }
 

@@ -21,7 +21,7 @@ __device__ __forceinline__ float act_fn(float x, int act) {
 struct Ctx {
   volatile int* abort;  // per CTA
   int* err;             // global
-  uint32_t a_ready_leader[2];  // cluster addresses of the leader's a_ready barriers
+  uint32_t a_ready_leader[4];  // cluster addresses of the leader's a_ready barriers (one per slot)
 };
 
 __device__ __forceinline__ bool wait_bar(const Ctx& cx, uint64_t* bar, uint32_t parity, int code) {
