@@ -131,8 +131,10 @@ def test_full_size_properties_config2():
     assert not np.array_equal(ctrl3.get_action(obs, None), a)
 
 
-def test_multi_env_equals_independent_controllers():
-    """num_envs = 3 batched planning == 3 independent single-env controllers (config-4 semantics)."""
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_multi_env_equals_independent_controllers(precision):
+    """num_envs = 3 batched planning == 3 independent single-env controllers (config-4 semantics), bit for
+    bit in both precision modes: a trajectory's result does not depend on the tile row it lands in."""
     c = dict(CASES["mpc_gnn_pg4_curious"])
     c["P"], c["H"] = 32, 6
     spec, weights, norms, obs, goal = build_inputs(c)
@@ -143,15 +145,15 @@ def test_multi_env_equals_independent_controllers():
     obss[:, spec.state_dim:] = goals
     env = product_env(c, goal)
     env.goal = goals
-    model = product_model(c, env, weights, norms)
-    batched = product_controller(c, env, model, num_envs=3)
+    model = product_model(c, env, weights, norms, precision=precision)
+    batched = product_controller(c, env, model, precision=precision, num_envs=3)
     batched.beginning_of_rollout(observation=obss, state=None, mode="train")
     noise = SeededNoise(5, 3.5)
     P, U, H = c["P"], spec.action_dim, c["H"]
     singles = []
     for i in range(3):
         env_i = product_env(c, goals[i])
-        ctl = product_controller(c, env_i, product_model(c, env_i, weights, norms))
+        ctl = product_controller(c, env_i, product_model(c, env_i, weights, norms, precision=precision), precision=precision)
         ctl.beginning_of_rollout(observation=obss[i], state=None, mode="train")
         singles.append(ctl)
     for step in range(2):
@@ -166,8 +168,9 @@ def test_multi_env_equals_independent_controllers():
             assert torch.equal(batched.engine.elite_idx_[i], singles[i].engine.elite_idx_[0])
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
 @pytest.mark.parametrize("name", ["mpc_gnn_c2_curious", "mpc_gnn_c6_stack_extr"])
-def test_sharded_ranks_equal_single_gpu(name):
+def test_sharded_ranks_equal_single_gpu(name, precision):
     """world_size = 2 emulated on one GPU: two rank-engines run their local stage one after the other (no waiting on
     each other), their candidate records are concatenated as the all-gather would, both run the merge.  Result must
     equal the single-GPU planner bit for bit, and both ranks must agree."""
@@ -176,8 +179,8 @@ def test_sharded_ranks_equal_single_gpu(name):
     c = CASES[name]
     spec, weights, norms, obs, goal = build_inputs(c)
     env = product_env(c, goal)
-    model = product_model(c, env, weights, norms)
-    single = product_controller(c, env, model)
+    model = product_model(c, env, weights, norms, precision=precision)
+    single = product_controller(c, env, model, precision=precision)
     single.beginning_of_rollout(observation=obs, state=None, mode="train")
     sp = dict(single.engine.sampler)
     kw = dict(horizon=c["H"], num_traj=c["P"] // 2, sampler=sp, cost_along_trajectory=c["cost"],
