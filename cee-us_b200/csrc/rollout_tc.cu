@@ -276,6 +276,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
   }
   tc_fence_before();
   __syncthreads();
+  // output-layer tables (float4-friendly, 16 entries each): new = old + c1 * acc + c0 with c1 = std_out, c0 = std_out * bias +
+  // mean_out; the re-normalised fp16 copy is (new - mean_in) * inv_std_in.  [0]: node rows (dyn), [1]: global rows (agent)
+  float* sOut = reinterpret_cast<float*>(smem + tl.sm_out);
+  for (int i = tid; i < 2 * 4 * 16; i += kTcThreads) {
+    const int which = i / 64, arr = (i / 16) % 4, j = i % 16;
+    const int dim = which == 0 ? md.D : md.A;
+    const int o_out = which == 0 ? md.nrm.out_dyn : md.nrm.out_agent, o_in = which == 0 ? md.nrm.in_dyn : md.nrm.in_agent;
+    const float* pbias = sPar + tl.mat[which == 0 ? TC_N3 : TC_G3].par_bias;
+    float v = 0.f;
+    if (j < dim) {
+      const float sdv = sNrm[o_out + dim + j];
+      v = arr == 0 ? sdv : arr == 1 ? fmaf(sdv, pbias[j], sNrm[o_out + j]) : arr == 2 ? sNrm[o_in + j] : sNrm[o_in + dim + j];
+    }
+    sOut[i] = v;
+  }
+  __syncthreads();
   Ctx cx;
   cx.abort = abort_flag; cx.err = err;
   if (warp == 0 && lane == 0) wait_bar(cx, wbar, 0, 1);  // this CTA's weight image has landed
@@ -363,6 +379,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     // global row: trajectory == row
 
     float dyn[16], agent[16], act_next[8];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { dyn[j] = 0.f; agent[j] = 0.f; }  // padded entries take part in the vectorised output update
 
     for (int rd = 0; rd < rounds; ++rd) {
       const int w_lo = min(ra.n, worker * per_worker), w_hi = min(ra.n, w_lo + per_worker);
@@ -561,17 +579,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
               tmem_ld16(t_acc, v);
               tmem_wait_ld();
               if (live_n) {
-                const float* pb = sPar + m.par_bias;
-                __half* dst = snrm + n_b * SNs + AUp + n_i * NAp;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(snrm + n_b * SNs + AUp + n_i * NAp);
                 float* og = outp + (size_t)n_b * O + A + n_i * D;
+                const float4* tb = reinterpret_cast<const float4*>(sOut);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (j < D) {
-                    const float dl = __uint_as_float(v[j]) + pb[j];
-                    dyn[j] += fmaf(nrm[md.nrm.out_dyn + D + j], dl, nrm[md.nrm.out_dyn + j]);
-                    og[j] = dyn[j];
-                    dst[j] = __float2half_rn((dyn[j] - nrm[md.nrm.in_dyn + j]) * nrm[md.nrm.in_dyn + D + j]);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  if (4 * j4 < D) {
+                    const float4 c1 = tb[j4], c0 = tb[4 + j4], mi = tb[8 + j4], is = tb[12 + j4];
+                    const float n0 = dyn[4 * j4] + fmaf(c1.x, __uint_as_float(v[4 * j4]), c0.x);
+                    const float n1 = dyn[4 * j4 + 1] + fmaf(c1.y, __uint_as_float(v[4 * j4 + 1]), c0.y);
+                    const float n2 = dyn[4 * j4 + 2] + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
+                    const float n3 = dyn[4 * j4 + 3] + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
+                    dyn[4 * j4] = n0; dyn[4 * j4 + 1] = n1; dyn[4 * j4 + 2] = n2; dyn[4 * j4 + 3] = n3;
+                    if (4 * j4 < D) og[4 * j4] = n0;
+                    if (4 * j4 + 1 < D) og[4 * j4 + 1] = n1;
+                    if (4 * j4 + 2 < D) og[4 * j4 + 2] = n2;
+                    if (4 * j4 + 3 < D) og[4 * j4 + 3] = n3;
+                    // padded entries have c1 = c0 = mi = is = 0 -> exact zeros, like the zero padding of the node block
+                    if (4 * j4 + 1 < D || S == 0) dst[2 * j4] = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y);
+                    else reinterpret_cast<__half*>(dst)[4 * j4] = __float2half_rn((n0 - mi.x) * is.x);
+                    if (4 * j4 + 3 < D || (S == 0 && 4 * j4 + 2 < D)) dst[2 * j4 + 1] = pack_half2((n2 - mi.z) * is.z, (n3 - mi.w) * is.w);
+                    else if (4 * j4 + 2 < D) reinterpret_cast<__half*>(dst)[4 * j4 + 2] = __float2half_rn((n2 - mi.z) * is.z);
                   }
+                }
               }
             }
             // A operand of the global tile: [hdr | 0] -> R1, sum over all edges -> R2
@@ -599,32 +629,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
               tmem_ld16(t_acc, v);
               tmem_wait_ld();
               if (live_g) {
-                const float* pb = sPar + m.par_bias;
-                __half* dst = snrm + row * SNs;
+                __half* dsth = snrm + row * SNs;
+                uint32_t* dst = reinterpret_cast<uint32_t*>(dsth);
                 float* og = outp + (size_t)row * O;
+                const float4* tb = reinterpret_cast<const float4*>(sOut + 64);
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  if (j < A) {
-                    const float dl = __uint_as_float(v[j]) + pb[j];
-                    agent[j] += fmaf(nrm[md.nrm.out_agent + A + j], dl, nrm[md.nrm.out_agent + j]);
-                    og[j] = agent[j];
-                    dst[j] = __float2half_rn((agent[j] - nrm[md.nrm.in_agent + j]) * nrm[md.nrm.in_agent + A + j]);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                  if (4 * j4 < A) {
+                    const float4 c1 = tb[j4], c0 = tb[4 + j4], mi = tb[8 + j4], is = tb[12 + j4];
+                    const float n0 = agent[4 * j4] + fmaf(c1.x, __uint_as_float(v[4 * j4]), c0.x);
+                    const float n1 = agent[4 * j4 + 1] + fmaf(c1.y, __uint_as_float(v[4 * j4 + 1]), c0.y);
+                    const float n2 = agent[4 * j4 + 2] + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
+                    const float n3 = agent[4 * j4 + 3] + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
+                    agent[4 * j4] = n0; agent[4 * j4 + 1] = n1; agent[4 * j4 + 2] = n2; agent[4 * j4 + 3] = n3;
+                    if (4 * j4 < A) og[4 * j4] = n0;
+                    if (4 * j4 + 1 < A) og[4 * j4 + 1] = n1;
+                    if (4 * j4 + 2 < A) og[4 * j4 + 2] = n2;
+                    if (4 * j4 + 3 < A) og[4 * j4 + 3] = n3;
+                    // the agent part is followed by the action in the header: only whole pairs may be written as 32 bits
+                    if (4 * j4 + 1 < A) dst[2 * j4] = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y);
+                    else dsth[4 * j4] = __float2half_rn((n0 - mi.x) * is.x);
+                    if (4 * j4 + 3 < A) dst[2 * j4 + 1] = pack_half2((n2 - mi.z) * is.z, (n3 - mi.w) * is.w);
+                    else if (4 * j4 + 2 < A) dsth[4 * j4 + 2] = __float2half_rn((n2 - mi.z) * is.z);
                   }
+                }
                 if (h + 1 < ra.H) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j)
                     if (j < U)
-                      dst[A + j] = __float2half_rn((act_next[j] - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]);
+                      dsth[A + j] = __float2half_rn((act_next[j] - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]);
                 }
+                // trailing part of the observation (static features + goal, env.obs_postproc): constant along the horizon
+                for (int c = 0; c < tail; ++c) og[(sd - N * S) + c] = s_tail[row * tail + c];
               }
             }
             tc_fence_before();
           }
-        }
-        // trailing part of the observation (static features + goal, env.obs_postproc): constant along the horizon
-        for (int idx = row; idx < Gc * tail; idx += 128) {
-          const int b = idx / tail, c = idx % tail;
-          outp[(size_t)b * O + (sd - N * S) + c] = s_tail[idx];
         }
         wg_sync(s);  // snrm of the next step is complete
         stamp(60);
@@ -960,6 +1000,7 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
     t.sm_par = sm; sm += round_up(t.par_floats * 4, 16);
     t.nrm_floats = md.nrm.out_dyn + 2 * md.D;
     t.sm_nrm = sm; sm += round_up(t.nrm_floats * 4, 16);
+    t.sm_out = sm; sm += 2 * 4 * 16 * 4;
     int so = 0;
     t.so_h2 = so; so += N == 2 ? 0 : 128 * Hd * 2;
     t.so_agg = so; so += N == 2 ? 0 : round_up(t.Te * N, 8) * Hd * 2;
