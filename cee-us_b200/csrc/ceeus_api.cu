@@ -2,6 +2,7 @@
 // iCEM planning step.  No CPU fallback: every entry point either enqueues CUDA work or returns an error.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -34,6 +35,7 @@ struct CeeusHandle_t {
   float* d_irdft = nullptr;
   float* h_obs = nullptr;     // pinned staging
   float* h_action = nullptr;  // pinned staging
+  int* h_tc_err = nullptr;    // pinned copy of the tensor-core kernels' protocol-error flag (read back with the action)
   int norm_floats = 0;
   TcLayout tc{};             // CEEUS_PREC_TC only (GNN ensemble)
   TcMlpLayout tcm{};         // CEEUS_PREC_TC only (dense-MLP ensemble)
@@ -46,8 +48,14 @@ struct CeeusHandle_t {
   CeeusBuffers bufs{};
   bool bound = false, weights_set = false, norms_set = false;
   bool has_elites = false;
-  uint64_t step_counter = 0;
+  unsigned long long* d_step_ctr = nullptr;  // MPC steps planned so far (base of the Philox stream ids), lives on the device
   int64_t launches = 0;
+  // ceeus_plan_step as a CUDA graph: [0] first step after begin_rollout (no elites to shift), [1] steady state
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t gevent = nullptr;
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  int64_t graph_launches[2] = {0, 0};
+  bool capturing = false;
   int F = 0;
   std::vector<TensorSpec> wspec;
   std::string err;
@@ -242,7 +250,13 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
   if (e == cudaSuccess) e = cudaMemset(h->d_goal, 0, (size_t)c.num_envs * (md.G ? md.G : 1) * sizeof(float));
   if (e == cudaSuccess) e = alloc(&h->d_obs, (size_t)c.num_envs * md.O);
   if (e == cudaSuccess) e = alloc(&h->d_irdft, (size_t)2 * h->F * c.horizon);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_step_ctr, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->d_step_ctr, 0, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->gevent, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_obs, (size_t)c.num_envs * md.O * sizeof(float));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_tc_err, sizeof(int));
+  if (e == cudaSuccess) *h->h_tc_err = 0;
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_action, (size_t)c.num_envs * md.U * sizeof(float));
   if (e == cudaSuccess && c.precision == CEEUS_PREC_TC && c.model_kind == CEEUS_MODEL_MLP) {
     if (!make_mlp_tc_layout(md, h->num_sms, &h->tcm)) {
@@ -287,13 +301,26 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
   return CEEUS_OK;
 }
 
+static void drop_graphs(CeeusHandle h) {
+  for (int i = 0; i < 2; ++i)
+    if (h->graph_exec[i]) {
+      cudaGraphExecDestroy(h->graph_exec[i]);
+      h->graph_exec[i] = nullptr;
+    }
+}
+
 void ceeus_destroy(CeeusHandle h) {
   if (!h) return;
+  drop_graphs(h);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
+  if (h->gevent) cudaEventDestroy(h->gevent);
+  cudaFree(h->d_step_ctr);
   cudaFree(h->d_weights); cudaFree(h->d_norm); cudaFree(h->d_low); cudaFree(h->d_high);
   cudaFree(h->d_goal); cudaFree(h->d_obs); cudaFree(h->d_irdft);
   cudaFree(h->d_wimg); cudaFree(h->d_wpar); cudaFree(h->d_kmap); cudaFree(h->d_tc_scratch); cudaFree(h->d_tc_err); cudaFree(h->d_tc_dbg);
   if (h->h_obs) cudaFreeHost(h->h_obs);
   if (h->h_action) cudaFreeHost(h->h_action);
+  if (h->h_tc_err) cudaFreeHost(h->h_tc_err);
   delete h;
 }
 
@@ -351,6 +378,7 @@ int ceeus_bind_buffers(CeeusHandle h, const CeeusBuffers* b) {
     return fail(h, CEEUS_ERR_INVALID, "bind_buffers: every buffer must be non-null");
   h->bufs = *b;
   h->bound = true;
+  drop_graphs(h);  // captured launches hold the old pointers
   return CEEUS_OK;
 }
 
@@ -403,7 +431,7 @@ int ceeus_sample(CeeusHandle h, const float* mean_dev, const float* std_dev, con
   a.mean = mean_dev; a.std = std_dev; a.low = h->d_low; a.high = h->d_high; a.noise = noise_dev; a.gauss = gauss_dev;
   a.write_gauss = write_gauss; a.irdft = h->d_irdft; a.actions = actions_dev; a.n = n; a.H = h->cfg.horizon;
   a.U = h->md.U; a.F = h->F; a.rows_per_env = n / h->cfg.num_envs; a.colored = h->cfg.colored_noise;
-  a.seed = h->cfg.seed; a.stream_id = stream_id; a.first_row = first_row;
+  a.seed = h->cfg.seed; a.stream_id = stream_id; a.step_ctr = nullptr; a.streams_per_step = 0; a.first_row = first_row;
   a.global_rows_per_env = (long long)(n / h->cfg.num_envs) * h->cfg.world_size;
   LAUNCH(h, launch_sample(a, S(stream)));
   return CEEUS_OK;
@@ -414,6 +442,7 @@ static FinishArgs finish_args(CeeusHandle h) {
   f.mean = h->bufs.mean; f.std = h->bufs.std; f.elite_actions = h->bufs.elite_actions; f.low = h->d_low; f.high = h->d_high;
   f.action_out = h->bufs.action_out; f.nE = h->cfg.num_envs; f.k = h->cfg.num_elites; f.H = h->cfg.horizon; f.U = h->md.U;
   f.execute_best = h->cfg.execute_best_elite; f.relative_init = h->cfg.relative_init; f.init_std = h->cfg.init_std;
+  f.step_ctr = h->d_step_ctr;
   return f;
 }
 
@@ -435,13 +464,13 @@ int ceeus_plan_iter_local(CeeusHandle h, int iter, const float* obs_dev, const f
   if (iter < 0 || iter >= c.opt_iterations) return fail(h, CEEUS_ERR_INVALID, "plan_iter_local: iter out of range");
   cudaStream_t st = S(stream);
   const int n = c.num_envs * c.num_traj;
-  const uint32_t streams_per_step = (uint32_t)c.opt_iterations + 1u;
-  const uint32_t base_stream = (uint32_t)(h->step_counter * streams_per_step);
+  const uint32_t streams_per_step = (uint32_t)c.opt_iterations + 1u;  // one Philox stream per iteration + one for shifted elites
   // 1. sample_action_sequences (mpc_torch.py:204-236)
   SampleArgs a{};
   a.mean = h->bufs.mean; a.std = h->bufs.std; a.low = h->d_low; a.high = h->d_high; a.noise = noise_dev; a.gauss = nullptr;
   a.write_gauss = 0; a.irdft = h->d_irdft; a.actions = h->bufs.actions; a.n = n; a.H = c.horizon; a.U = h->md.U; a.F = h->F;
-  a.rows_per_env = c.num_traj; a.colored = c.colored_noise; a.seed = c.seed; a.stream_id = base_stream + (uint32_t)iter;
+  a.rows_per_env = c.num_traj; a.colored = c.colored_noise; a.seed = c.seed; a.stream_id = (uint32_t)iter;
+  a.step_ctr = h->d_step_ctr; a.streams_per_step = streams_per_step;
   a.first_row = (long long)c.rank * c.num_traj; a.global_rows_per_env = (long long)c.num_traj * c.world_size;
   LAUNCH(h, launch_sample(a, st));
   // 2. mean-action row + elites shifted over time live at global rows 0..n_kept-1 => rank 0
@@ -453,7 +482,7 @@ int ceeus_plan_iter_local(CeeusHandle h, int iter, const float* obs_dev, const f
     f.colored = c.colored_noise;
     f.write_mean_row = c.use_mean_actions && iter == c.opt_iterations - 1;
     f.shift_elites = iter == 0 && c.shift_elites_over_time && h->has_elites && c.num_kept > 0;
-    f.seed = c.seed; f.stream_id = base_stream + (uint32_t)c.opt_iterations;
+    f.seed = c.seed; f.stream_id = (uint32_t)c.opt_iterations; f.step_ctr = h->d_step_ctr; f.streams_per_step = streams_per_step;
     if (f.write_mean_row || f.shift_elites) LAUNCH(h, launch_fixup(f, st));
   }
   // 3. predict_n_steps
@@ -489,18 +518,15 @@ int ceeus_plan_finish(CeeusHandle h, void* stream) {
   if (!h) return CEEUS_ERR_INVALID;
   if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
   LAUNCH(h, launch_finish(finish_args(h), S(stream)));
-  h->has_elites = true;
-  h->step_counter += 1;
+  if (!h->capturing) h->has_elites = true;
   return CEEUS_OK;
 }
 
-int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, const float* noise_dev_or_null, void* stream) {
-  if (!h || !obs_host || !action_host) return fail(h, CEEUS_ERR_INVALID, "plan_step: null argument");
-  if (h->cfg.world_size != 1) return fail(h, CEEUS_ERR_INVALID, "plan_step is single-GPU; use plan_iter_local/update with an all-gather");
+// The launch sequence of one MPC step on `stream` (shared by the eager path and the graph capture).
+static int enqueue_plan_step(CeeusHandle h, const float* noise_dev_or_null, void* stream) {
   const CeeusConfig& c = h->cfg;
   cudaStream_t st = S(stream);
   const size_t ob = (size_t)c.num_envs * h->md.O * sizeof(float);
-  std::memcpy(h->h_obs, obs_host, ob);
   CU_CHECK(h, cudaMemcpyAsync(h->d_obs, h->h_obs, ob, cudaMemcpyHostToDevice, st));
   const size_t per_iter = (size_t)c.num_envs * c.num_traj * h->md.U * c.horizon;
   const size_t per_shift = (size_t)c.num_envs * c.num_kept * h->md.U * c.horizon;
@@ -521,12 +547,51 @@ int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, co
   if (int rc = ceeus_plan_finish(h, stream)) return rc;
   const size_t ab = (size_t)c.num_envs * h->md.U * sizeof(float);
   CU_CHECK(h, cudaMemcpyAsync(h->h_action, h->bufs.action_out, ab, cudaMemcpyDeviceToHost, st));
-  CU_CHECK(h, cudaStreamSynchronize(st));
-  if (h->d_tc_err) {
-    const int tcs = ceeus_tc_status(h);
-    if (tcs != 0) return fail(h, CEEUS_ERR_CUDA, "tensor-core rollout kernel reported protocol error " + std::to_string(tcs));
+  if (h->d_tc_err) CU_CHECK(h, cudaMemcpyAsync(h->h_tc_err, h->d_tc_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  return CEEUS_OK;
+}
+
+int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, const float* noise_dev_or_null, void* stream) {
+  if (!h || !obs_host || !action_host) return fail(h, CEEUS_ERR_INVALID, "plan_step: null argument");
+  if (h->cfg.world_size != 1) return fail(h, CEEUS_ERR_INVALID, "plan_step is single-GPU; use plan_iter_local/update with an all-gather");
+  if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
+  const CeeusConfig& c = h->cfg;
+  cudaStream_t st = S(stream);
+  std::memcpy(h->h_obs, obs_host, (size_t)c.num_envs * h->md.O * sizeof(float));
+  static const bool no_graph = std::getenv("CEEUS_NO_GRAPH") != nullptr;
+  if (noise_dev_or_null == nullptr && !no_graph) {
+    // Device RNG path: the whole step (H2D obs, ~30 kernels, D2H action) is one CUDA graph launch.  Nothing in the sequence
+    // depends on host state except "are there elites to shift" (two graphs); the Philox stream base is a device counter.
+    const int v = h->has_elites ? 1 : 0;
+    if (!h->graph_exec[v]) {
+      cudaGraph_t g = nullptr;
+      const int64_t l0 = h->launches;
+      h->capturing = true;
+      CU_CHECK(h, cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed));
+      const int rc = enqueue_plan_step(h, nullptr, h->gstream);
+      const cudaError_t ce = cudaStreamEndCapture(h->gstream, &g);
+      h->capturing = false;
+      h->graph_launches[v] = h->launches - l0;
+      h->launches = l0;
+      if (rc != CEEUS_OK) { if (g) cudaGraphDestroy(g); return rc; }
+      CU_CHECK(h, ce);
+      const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec[v], g, 0);
+      cudaGraphDestroy(g);
+      CU_CHECK(h, ie);
+    }
+    CU_CHECK(h, cudaEventRecord(h->gevent, st));  // work already queued on the caller's stream (weight repack, ...) comes first
+    CU_CHECK(h, cudaStreamWaitEvent(h->gstream, h->gevent, 0));
+    CU_CHECK(h, cudaGraphLaunch(h->graph_exec[v], h->gstream));
+    h->launches += h->graph_launches[v];
+    h->has_elites = true;
+    CU_CHECK(h, cudaStreamSynchronize(h->gstream));
+  } else {
+    if (int rc = enqueue_plan_step(h, noise_dev_or_null, stream)) return rc;
+    CU_CHECK(h, cudaStreamSynchronize(st));
   }
-  std::memcpy(action_host, h->h_action, ab);
+  if (h->d_tc_err && *h->h_tc_err != 0)
+    return fail(h, CEEUS_ERR_CUDA, "tensor-core rollout kernel reported protocol error " + std::to_string(*h->h_tc_err));
+  std::memcpy(action_host, h->h_action, (size_t)c.num_envs * h->md.U * sizeof(float));
   return CEEUS_OK;
 }
 

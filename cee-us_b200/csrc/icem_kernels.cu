@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
   const int tid = threadIdx.x;
   const long long pair0 = (long long)blockIdx.x * kPairsPerBlock;
   const long long npairs = (long long)a.n * a.U;
+  const unsigned sid = a.stream_id + (a.step_ctr != nullptr ? (unsigned)(*a.step_ctr) * a.streams_per_step : 0u);
 
   if (a.noise == nullptr) {
     if (a.colored)
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
           const long long r = pr / a.U;
           const int u = (int)(pr % a.U);
           const long long grow = (r / a.rows_per_env) * a.global_rows_per_env + a.first_row + r % a.rows_per_env;
-          const float4 z = philox_normal4(a.seed, a.stream_id, (unsigned long long)(grow * a.U + u), (unsigned)b);
+          const float4 z = philox_normal4(a.seed, sid, (unsigned long long)(grow * a.U + u), (unsigned)b);
           *reinterpret_cast<float4*>(zbuf + lp * nzp + b * 4) = z;
         }
       }
@@ -123,6 +124,7 @@ __global__ void fixup_kernel(const FixupArgs a) {
   if (a.write_mean_row)
     for (int i = tid; i < HU; i += blockDim.x) act[i] = mean[i];
   if (a.shift_elites) {
+    const unsigned sid = a.stream_id + (a.step_ctr != nullptr ? (unsigned)(*a.step_ctr) * a.streams_per_step : 0u);
     __syncthreads();
     const float* el = a.elite_actions + (size_t)env * a.k * HU;
     for (int i = tid; i < a.n_kept * HU; i += blockDim.x) {
@@ -139,7 +141,7 @@ __global__ void fixup_kernel(const FixupArgs a) {
           y = 0.f;
           const int nb = (2 * a.F + 3) / 4;
           for (int b = 0; b < nb; ++b) {
-            const float4 z = philox_normal4(a.seed, a.stream_id, (unsigned long long)pr, (unsigned)b);
+            const float4 z = philox_normal4(a.seed, sid, (unsigned long long)pr, (unsigned)b);
             const float zz[4] = {z.x, z.y, z.z, z.w};
             for (int c = 0; c < 4; ++c) {
               const int k = b * 4 + c;
@@ -147,7 +149,7 @@ __global__ void fixup_kernel(const FixupArgs a) {
             }
           }
         } else {
-          const float4 z = philox_normal4(a.seed, a.stream_id, (unsigned long long)pr, (unsigned)(t / 4));
+          const float4 z = philox_normal4(a.seed, sid, (unsigned long long)pr, (unsigned)(t / 4));
           const float zz[4] = {z.x, z.y, z.z, z.w};
           y = zz[t % 4];
         }
@@ -439,6 +441,7 @@ __global__ void finish_kernel(const FinishArgs a, const int pick_action, const i
   float* mean = a.mean + (size_t)env * HU;
   float* std = a.std + (size_t)env * HU;
   if (pick_action) {
+    if (env == 0 && tid == 0 && a.step_ctr != nullptr) *a.step_ctr += 1ull;  // next MPC step draws from fresh Philox streams
     for (int u = tid; u < a.U; u += blockDim.x)
       a.action_out[env * a.U + u] = a.execute_best ? a.elite_actions[(size_t)env * a.k * HU + u] : mean[u];
   }

@@ -91,7 +91,9 @@ struct SampleArgs {
   float* actions;      // [n,H,U]
   int n, H, U, F, rows_per_env, colored;
   unsigned long long seed;
-  unsigned int stream_id;
+  unsigned int stream_id;     // Philox stream: stream_id + (*step_ctr) * streams_per_step  (step_ctr may be null)
+  const unsigned long long* step_ctr;
+  unsigned int streams_per_step;
   long long first_row;  // global index of local row 0 (RNG is keyed by the global row)
   long long global_rows_per_env;
 };
@@ -109,7 +111,9 @@ struct FixupArgs {  // mean-action row and elites shifted over time (mpc_torch.p
   int nE, P, H, U, F, k, n_kept, colored;
   int write_mean_row, shift_elites;
   unsigned long long seed;
-  unsigned int stream_id;
+  unsigned int stream_id;     // + (*step_ctr) * streams_per_step, as in SampleArgs
+  const unsigned long long* step_ctr;
+  unsigned int streams_per_step;
 };
 cudaError_t launch_fixup(const FixupArgs& a, cudaStream_t st);
 
@@ -154,6 +158,7 @@ struct FinishArgs {
   float* action_out;  // [nE,U]
   int nE, k, H, U, execute_best, relative_init;
   float init_std;
+  unsigned long long* step_ctr;  // MPC step counter on the device (RNG stream base); incremented by finish_kernel
 };
 cudaError_t launch_finish(const FinishArgs& a, cudaStream_t st);
 cudaError_t launch_reset_dist(const FinishArgs& a, cudaStream_t st);  // beginning_of_rollout: mean + std reset
