@@ -215,3 +215,37 @@ def test_tc_mlp_rollout_matches_oracle_fresh_inputs(n_obj, hidden, layers, P, H)
     np.testing.assert_array_equal(got[..., spec.state_dim:], want[..., spec.state_dim:])
     assert rel_l2(got, want) < TOL_TC
     assert rel_err(got, want) < 5e-3
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tc", TOL_TC)])
+@pytest.mark.parametrize("act,layer_norm,aggr", [("relu", True, "sum"), ("silu", True, "mean"), ("tanh", False, "sum"),
+                                                 ("relu", False, "mean")])
+def test_gnn_model_param_variants(act, layer_norm, aggr, precision, tol):
+    """The other values `model_params` can take on this path (gnn_modules.py:17-131: act_fn, layer_norm, aggr_fn): sum
+    aggregation (the folded W3 then carries no 1/(N-1) scale), non-ReLU activations and no LayerNorm (general epilogue)."""
+    import ceeus_b200
+
+    n_obj, hidden, P, H = 3, 128, 70, 6
+    c = dict(kind="rollout", env="construction", n_obj=n_obj, model="gnn", hidden=hidden, layers=2, P=P, H=H,
+             wseed=5100, identity_norm=False, running=False, oseed=31)
+    spec, weights, norms, obs, goal = build_inputs(c)
+    if not layer_norm:
+        weights = {k: v for k, v in weights.items() if not (k.endswith(".gamma") or k.endswith(".beta"))}
+    env = product_env(c, goal)
+    pm = ceeus_b200.B200GNNEnsemble(env=env, model_params=dict(n=5, hidden_dim=hidden, num_layers=2, layer_norm=layer_norm,
+                                                                act_fn=act, aggr_fn=aggr),
+                                    backend_params=dict(precision=precision))
+    pm.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    pm.set_normalizers(norms)
+    om = orc.GNNEnsembleOracle(spec=spec, weights=weights, normalizers=norms, hidden=hidden, num_layers=2, act=act,
+                               layer_norm=layer_norm, aggr=aggr)
+    acts = rollout_actions(c, spec)
+    starts = np.tile(obs, (P, 1))
+    want = orc.rollout(om, torch.from_numpy(starts), torch.from_numpy(acts), torch.from_numpy(goal)).numpy()
+    pm.predict_n_steps(start_observations=torch.from_numpy(starts).to(DEV), start_states=None,
+                       policy=_Policy(torch.from_numpy(acts).to(DEV)), horizon=H)
+    eng = pm._rollout_engine(P, H)
+    got = eng.traj_.cpu().numpy()
+    assert eng.tc_status() == 0 and np.isfinite(got).all()
+    assert rel_l2(got, want) < tol
+    assert rel_err(got, want) < 5 * tol
