@@ -211,7 +211,9 @@ __device__ __forceinline__ uint4 pack8(const float (&acc)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int HD, bool RELU>
+// N2: the two-object graph (one edge per node: aggregation in registers) gets its own instantiation -- the kernel is one
+// big function and register pressure anywhere costs spills everywhere, so the N >= 3 aggregation code must not be in it.
+template <int HD, bool RELU, bool N2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::value, 1)
     rollout_gnn_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcLayout tl, const uint8_t* __restrict__ wimg,
                           const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg) {
@@ -222,7 +224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
-  const int N = md.N, A = md.A, D = md.D, S = md.S, U = md.U, sd = md.sd, O = md.O;
+  const int N = N2 ? 2 : md.N, A = md.A, D = md.D, S = md.S, U = md.U, sd = md.sd, O = md.O;
   const int NE = N * (N - 1);
 
   // ---- member / trajectory range of this pair: pairs are dealt to members as evenly as the count allows ----
@@ -316,6 +318,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     uint8_t* s_glob = slot + tl.so_glob;  // [T][HD] fp16 sums over all edges
     __half* snrm = reinterpret_cast<__half*>(slot + tl.so_snrm);  // [T][SNs] normalised [hdr | node blocks]
     float* s_tail = reinterpret_cast<float*>(slot + tl.so_tail);  // [T][tail] static features + goal (fp32)
+    short* s_first = reinterpret_cast<short*>(slot + tl.so_first);  // [Te*N] first edge row of aggregate row a (pass-local)
     const int SNs = tl.SNs, AUp = tl.AUp, NAp = tl.NAp, tail = tl.tail;
     const float* __restrict__ nrm = sNrm;
     const bool ln = md.layer_norm != 0;
@@ -372,7 +375,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     // node row: pass n_p, pass-local aggregate row n_a = bl * N + i.  N == 2: node row == edge row (one edge per node);
     // N >= 3: each pass's rows are dealt over the four warps so that the aggregation owners are spread.
     int n_p, n_a;
-    if (N == 2) { n_p = 0; n_a = row; }
+    if (N2) { n_p = 0; n_a = row; }
     else { n_p = lane / tl.q_n; n_a = (lane % tl.q_n) * 4 + q; }
     const bool n_valid = n_a < Te * N && n_p < n_pass;
     const int n_b = n_p * Te + n_a / N, n_i = n_a % N;  // group-local trajectory, node
@@ -381,6 +384,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     float dyn[16], agent[16], act_next[8];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { dyn[j] = 0.f; agent[j] = 0.f; }  // padded entries take part in the vectorised output update
+
+    for (int a = row; a < tl.Te * N; a += 128) s_first[a] = (short)((a / N) * NE + (a % N) * (N - 1));
 
     for (int rd = 0; rd < rounds; ++rd) {
       const int w_lo = min(ra.n, worker * per_worker), w_hi = min(ra.n, w_lo + per_worker);
@@ -476,7 +481,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
             const float* pbe = parp(m.par_beta);
             const bool lnm = ln && m.ln;
             // where the fp16 row goes: 0 = R1 (next layer's A operand), 1 = N == 2 aggregation, 2 = staging for N >= 3
-            const int mode = kind != TC_E2 ? 0 : (N == 2 ? 1 : 2);
+            const int mode = kind != TC_E2 ? 0 : (N2 ? 1 : 2);
             if (warp_on) {
               uint32_t hreg[HD / 2];
               epi_row<HD, RELU>(t_acc, pb, pg, pbe, lnm, fold, act, hreg);
@@ -484,7 +489,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                 store_hidden<HD>(t_r1, hreg);
                 // the next layer's bias rides in a constant-one K column that lives in R2 (free once this layer's MMA is done)
                 if (tl.mat[kind + 1].K > tl.mat[kind + 1].kx && tl.mat[kind + 1].kx == HD) tmem_st4(t_r2, make_uint4(0x00003c00u, 0u, 0u, 0u)), tmem_st4(t_r2 + 4, make_uint4(0u, 0u, 0u, 0u));
-              } else if (mode == 1) {
+              } else if (N2) {
                 // one outgoing edge per node: the node aggregate is this thread's own row (-> R2); the global aggregate is the
                 // sum of the two rows of a trajectory (adjacent lanes) -> s_glob, written by the even lane
                 store_hidden<HD>(t_r2, hreg);
@@ -511,13 +516,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
             stamp(30 + kind);
             if (kind == TC_E2) {
               // ---------- aggregation of the hidden edge activations (models/utils.py:42-51; W3 folded) ----------
-              if (N != 2) {
+              if constexpr (!N2) {
                 wg_sync(s);
                 const int live_tr = max(0, min(Te, Gc - p * Te));  // live trajectories of this pass
-                // phase 1: sums over the N-1 outgoing edges of every node of the pass
+                // phase 1: sums over the N-1 outgoing edges of every node of the pass (kept as a plain loop: batching the loads
+                // in registers was tried and lost more to spills elsewhere in this kernel than it gained here)
                 for (int t = row; t < live_tr * N * CH; t += 128) {
                   const int a = t / CH, c = t % CH;
-                  const int first = (a / N) * NE + (a % N) * (N - 1);
+                  const int first = s_first[a];
                   float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                   for (int e2 = 0; e2 < N - 1; ++e2) {
                     const int r = first + e2;
@@ -1007,6 +1013,7 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
     t.so_glob = so; so += round_up(t.Tmax, 8) * Hd * 2;
     t.so_snrm = so; so += round_up(t.Tmax * t.SNs * 2, 16);
     t.so_tail = so; so += round_up(t.Tmax * t.tail * 4, 16);
+    t.so_first = so; so += round_up(t.Te * N * 2, 16);
     so = round_up(so, 128);
     for (int i = 0; i < t.NS; ++i) { t.sm_slot[i] = sm; sm += so; }
     t.sm_bar = sm; sm += 128;
@@ -1033,22 +1040,29 @@ cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout
   return cudaGetLastError();
 }
 
-template <int HD, bool RELU>
+template <int HD, bool RELU, bool N2>
 static cudaError_t launch_tc_t(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(rollout_gnn_tc_kernel<HD, RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
+  cudaError_t e = cudaFuncSetAttribute(rollout_gnn_tc_kernel<HD, RELU, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
   if (e != cudaSuccess) return e;
-  rollout_gnn_tc_kernel<HD, RELU><<<dim3(2 * tl.pairs), 128 * TcSlots<HD>::value, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
+  rollout_gnn_tc_kernel<HD, RELU, N2><<<dim3(2 * tl.pairs), 128 * TcSlots<HD>::value, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
   return cudaGetLastError();
+}
+
+template <int HD, bool RELU>
+static cudaError_t launch_tc_n(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
+                               const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
+  return md.N == 2 ? launch_tc_t<HD, RELU, true>(md, ra, tl, wimg, wpar, err_flag, dbg, st)
+                   : launch_tc_t<HD, RELU, false>(md, ra, tl, wimg, wpar, err_flag, dbg, st);
 }
 
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                   const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
   const bool relu = md.act == CEEUS_ACT_RELU;
-  if (md.Hd == 128) return relu ? launch_tc_t<128, true>(md, ra, tl, wimg, wpar, err_flag, dbg, st)
-                                : launch_tc_t<128, false>(md, ra, tl, wimg, wpar, err_flag, dbg, st);
-  return relu ? launch_tc_t<64, true>(md, ra, tl, wimg, wpar, err_flag, dbg, st)
-              : launch_tc_t<64, false>(md, ra, tl, wimg, wpar, err_flag, dbg, st);
+  if (md.Hd == 128) return relu ? launch_tc_n<128, true>(md, ra, tl, wimg, wpar, err_flag, dbg, st)
+                                : launch_tc_n<128, false>(md, ra, tl, wimg, wpar, err_flag, dbg, st);
+  return relu ? launch_tc_n<64, true>(md, ra, tl, wimg, wpar, err_flag, dbg, st)
+              : launch_tc_n<64, false>(md, ra, tl, wimg, wpar, err_flag, dbg, st);
 }
 
 }  // namespace ceeus
