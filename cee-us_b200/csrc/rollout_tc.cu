@@ -213,7 +213,7 @@ __device__ __forceinline__ uint4 pack8(const float (&acc)[8]) {
 // ------------------------------------------------------------------------------------------------------------
 // N2: the two-object graph (one edge per node: aggregation in registers) gets its own instantiation -- the kernel is one
 // big function and register pressure anywhere costs spills everywhere, so the N >= 3 aggregation code must not be in it.
-template <int HD, bool RELU, bool N2>
+template <int HD, bool RELU, bool N2, bool DBG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::value, 1)
     rollout_gnn_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcLayout tl, const uint8_t* __restrict__ wimg,
                           const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg) {
@@ -328,8 +328,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     const uint32_t t_acc = lane_base, t_r1 = lane_base + HD, t_r2 = lane_base + HD + HD / 2;
     uint32_t dph = 0;
     int dbg_n = 0;
-    const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool dbg_on = DBG && dbg != nullptr && blockIdx.x == 0 && tid == 0;
     auto stamp = [&](int tag) {
+      if constexpr (!DBG) return;  // the timeline probes exist only in the profiling instantiation
       if (dbg_on && dbg_n < 250) { dbg[2 * dbg_n] = tag; dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
     };
 
@@ -391,7 +392,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       const int w_lo = min(ra.n, worker * per_worker), w_hi = min(ra.n, w_lo + per_worker);
       const int p0 = w_lo + rd * T;
       int Gc = max(0, min(T, w_hi - p0));  // live trajectories of this group (0: pure lock-step filler)
-      if (dbg != nullptr && dbg[499] == 1 && s == 1) Gc = 0;  // profiling aid: slot 1 idles, slot 0 runs without SIMT contention
+      if (DBG && dbg != nullptr && dbg[499] == 1 && s == 1) Gc = 0;  // profiling aid: slot 1 idles, slot 0 runs without SIMT contention
       const bool live_n = n_valid && n_b < Gc;
       const bool live_g = row < Gc;
       wg_sync(s);
@@ -1043,9 +1044,10 @@ cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout
 template <int HD, bool RELU, bool N2>
 static cudaError_t launch_tc_t(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(rollout_gnn_tc_kernel<HD, RELU, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
+  auto kern = dbg != nullptr ? rollout_gnn_tc_kernel<HD, RELU, N2, true> : rollout_gnn_tc_kernel<HD, RELU, N2, false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
   if (e != cudaSuccess) return e;
-  rollout_gnn_tc_kernel<HD, RELU, N2><<<dim3(2 * tl.pairs), 128 * TcSlots<HD>::value, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
+  kern<<<dim3(2 * tl.pairs), 128 * TcSlots<HD>::value, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
   return cudaGetLastError();
 }
 
