@@ -43,6 +43,7 @@ struct CeeusHandle_t {
   float* d_wpar = nullptr;
   int* d_kmap = nullptr;         // K permutation / folding map of every stage matrix
   float* d_tc_scratch = nullptr; // logical fp32 stage matrices (pack-time only)
+  bool tc_all_fold = false;      // every member's LayerNorm affine could be folded into the weights (read back after packing)
   int* d_tc_err = nullptr;
   long long* d_tc_dbg = nullptr;  // optional timeline of one warpgroup (ceeus_tc_debug_timeline)
   CeeusBuffers bufs{};
@@ -344,7 +345,17 @@ int ceeus_set_weights(CeeusHandle h, const float* const* dev_ptrs, int n, void* 
   if (h->cfg.precision == CEEUS_PREC_TC && h->md.kind == CEEUS_MODEL_MLP)
     LAUNCH(h, launch_mlp_tc_pack(h->d_weights, h->md, h->tcm, h->d_wimg, S(stream)));
   else if (h->cfg.precision == CEEUS_PREC_TC)
+  {
     LAUNCH(h, launch_tc_pack(h->d_weights, h->md, h->tc, h->d_kmap, h->d_tc_scratch, h->d_wimg, h->d_wpar, S(stream)));
+    // which epilogue variant the rollout kernel may use: one small read-back per set_weights (rare: after training / load)
+    CU_CHECK(h, cudaStreamSynchronize(S(stream)));
+    h->tc_all_fold = true;
+    for (int e = 0; e < h->md.E; ++e) {
+      float f = 0.f;
+      CU_CHECK(h, cudaMemcpy(&f, h->d_wpar + (size_t)e * h->tc.par_floats + h->tc.par_fold, sizeof(float), cudaMemcpyDeviceToHost));
+      if (f == 0.f) h->tc_all_fold = false;
+    }
+  }
   h->weights_set = true;
   return CEEUS_OK;
 }
@@ -396,7 +407,7 @@ static int do_rollout(CeeusHandle h, const float* start_obs_dev, int traj_per_st
   if (h->cfg.precision == CEEUS_PREC_TC && h->md.kind == CEEUS_MODEL_MLP)
     LAUNCH(h, launch_rollout_mlp_tc(h->md, ra, h->tcm, h->d_wimg, h->d_tc_err, st));
   else if (h->cfg.precision == CEEUS_PREC_TC)
-    LAUNCH(h, launch_rollout_gnn_tc(h->md, ra, h->tc, h->d_wimg, h->d_wpar, h->d_tc_err, h->d_tc_dbg, st));
+    LAUNCH(h, launch_rollout_gnn_tc(h->md, ra, h->tc, h->d_wimg, h->d_wpar, h->d_tc_err, h->d_tc_dbg, h->tc_all_fold, st));
   else if (h->md.kind == CEEUS_MODEL_GNN) LAUNCH(h, launch_rollout_gnn_simt(h->md, ra, h->num_sms, st));
   else LAUNCH(h, launch_rollout_mlp_simt(h->md, ra, st));
   return CEEUS_OK;

@@ -60,7 +60,7 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
 cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, const int* kmap_dev, float* scratch,
                            uint8_t* wimg, float* wpar, cudaStream_t st);
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
-                                  const float* wpar, int* err_flag, long long* dbg, cudaStream_t st);
+                                  const float* wpar, int* err_flag, long long* dbg, bool all_fold, cudaStream_t st);
 
 // ---- tensor-core rollout of the dense-MLP ensemble (rollout_mlp_tc.cu) ----
 struct TcMlpMat { int K, N, nloc, off; };

@@ -146,7 +146,7 @@ __device__ __forceinline__ void epi_hidden(uint32_t tacc, const float* __restric
 // 256 threads per CTA).  FOLDED LayerNorm (fold != 0, ReLU): sign(gamma) lives in this layer's weight columns and |gamma| in the
 // consumer's weight rows (pack time), so  relu(gamma * xhat + beta) = |gamma| * relu(sign(gamma) * xhat + beta / |gamma|)  costs
 // one FFMA per element and one parameter vector (pbe = beta / |gamma|).  General path: xhat * gamma + beta, any activation.
-template <int HD, bool RELU>
+template <int HD, bool RELU, bool FOLD>
 __device__ __forceinline__ void epi_row(uint32_t tacc, const float* __restrict__ pb, const float* __restrict__ pg,
                                         const float* __restrict__ pbe, bool ln, bool fold, int act, uint32_t (&h)[HD / 2]) {
   float x[HD];
@@ -166,7 +166,7 @@ __device__ __forceinline__ void epi_row(uint32_t tacc, const float* __restrict__
     for (int j = 0; j < HD; ++j) v8[j & 7] = fmaf(x[j], x[j], v8[j & 7]);
     const float v = ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
     const float rstd = rsqrtf(v * (1.f / HD) + 1e-5f);
-    if (RELU && fold) {
+    if (FOLD || (RELU && fold)) {
 #pragma unroll
       for (int j = 0; j < HD; j += 4) {
         const float4 be = *reinterpret_cast<const float4*>(pbe + j);
@@ -175,6 +175,7 @@ __device__ __forceinline__ void epi_row(uint32_t tacc, const float* __restrict__
       }
       return;
     }
+    if constexpr (FOLD) return;  // (unreachable: FOLD kernels only run members whose LayerNorm affine is folded)
 #pragma unroll
     for (int j = 0; j < HD; j += 4) {
       const float4 g = *reinterpret_cast<const float4*>(pg + j);
@@ -213,7 +214,7 @@ __device__ __forceinline__ uint4 pack8(const float (&acc)[8]) {
 // ------------------------------------------------------------------------------------------------------------
 // N2: the two-object graph (one edge per node: aggregation in registers) gets its own instantiation -- the kernel is one
 // big function and register pressure anywhere costs spills everywhere, so the N >= 3 aggregation code must not be in it.
-template <int HD, bool RELU, bool N2, bool DBG>
+template <int HD, bool RELU, bool N2, bool DBG, bool FOLD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::value, 1)
     rollout_gnn_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcLayout tl, const uint8_t* __restrict__ wimg,
                           const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg) {
@@ -323,7 +324,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     const float* __restrict__ nrm = sNrm;
     const bool ln = md.layer_norm != 0;
     const int act = md.act;
-    const bool fold = sPar[tl.par_fold] != 0.f;  // LayerNorm affine folded into the weights (decided per member at pack time)
+    // LayerNorm affine folded into the weights: decided per member at pack time; the FOLD instantiation is launched when every
+    // member folds (the host reads the flags after packing) and does not contain the general LayerNorm code at all
+    const bool fold = FOLD || sPar[tl.par_fold] != 0.f;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * 2 * HD);
     const uint32_t t_acc = lane_base, t_r1 = lane_base + HD, t_r2 = lane_base + HD + HD / 2;
     uint32_t dph = 0;
@@ -485,7 +488,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
             const int mode = kind != TC_E2 ? 0 : (N2 ? 1 : 2);
             if (warp_on) {
               uint32_t hreg[HD / 2];
-              epi_row<HD, RELU>(t_acc, pb, pg, pbe, lnm, fold, act, hreg);
+              epi_row<HD, RELU, FOLD>(t_acc, pb, pg, pbe, lnm, fold, act, hreg);
               if (mode == 0) {
                 store_hidden<HD>(t_r1, hreg);
                 // the next layer's bias rides in a constant-one K column that lives in R2 (free once this layer's MMA is done)
@@ -718,7 +721,7 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) epi_bench_kernel(long long*
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
       uint32_t hreg[64];
-      epi_row<128, true>(base, (with_bias & 1) ? par : nullptr, par + 128, par + 256, true, (with_bias & 2) != 0, CEEUS_ACT_RELU, hreg);
+      epi_row<128, true, false>(base, (with_bias & 1) ? par : nullptr, par + 128, par + 256, true, (with_bias & 2) != 0, CEEUS_ACT_RELU, hreg);
       store_hidden<128>(base, hreg);
       tmem_wait_st();
     }
@@ -1043,8 +1046,10 @@ cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout
 
 template <int HD, bool RELU, bool N2>
 static cudaError_t launch_tc_t(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
-                               const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
-  auto kern = dbg != nullptr ? rollout_gnn_tc_kernel<HD, RELU, N2, true> : rollout_gnn_tc_kernel<HD, RELU, N2, false>;
+                               const float* wpar, int* err_flag, long long* dbg, bool all_fold, cudaStream_t st) {
+  auto kern = rollout_gnn_tc_kernel<HD, RELU, N2, false, false>;
+  if (dbg != nullptr) kern = rollout_gnn_tc_kernel<HD, RELU, N2, true, false>;
+  else if (RELU && all_fold) kern = rollout_gnn_tc_kernel<HD, RELU, N2, false, RELU>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
   if (e != cudaSuccess) return e;
   kern<<<dim3(2 * tl.pairs), 128 * TcSlots<HD>::value, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
@@ -1053,18 +1058,18 @@ static cudaError_t launch_tc_t(const ModelDesc& md, const RolloutArgs& ra, const
 
 template <int HD, bool RELU>
 static cudaError_t launch_tc_n(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
-                               const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
-  return md.N == 2 ? launch_tc_t<HD, RELU, true>(md, ra, tl, wimg, wpar, err_flag, dbg, st)
-                   : launch_tc_t<HD, RELU, false>(md, ra, tl, wimg, wpar, err_flag, dbg, st);
+                               const float* wpar, int* err_flag, long long* dbg, bool all_fold, cudaStream_t st) {
+  return md.N == 2 ? launch_tc_t<HD, RELU, true>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st)
+                   : launch_tc_t<HD, RELU, false>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st);
 }
 
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
-                                  const float* wpar, int* err_flag, long long* dbg, cudaStream_t st) {
+                                  const float* wpar, int* err_flag, long long* dbg, bool all_fold, cudaStream_t st) {
   const bool relu = md.act == CEEUS_ACT_RELU;
-  if (md.Hd == 128) return relu ? launch_tc_n<128, true>(md, ra, tl, wimg, wpar, err_flag, dbg, st)
-                                : launch_tc_n<128, false>(md, ra, tl, wimg, wpar, err_flag, dbg, st);
-  return relu ? launch_tc_n<64, true>(md, ra, tl, wimg, wpar, err_flag, dbg, st)
-              : launch_tc_n<64, false>(md, ra, tl, wimg, wpar, err_flag, dbg, st);
+  if (md.Hd == 128) return relu ? launch_tc_n<128, true>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st)
+                                : launch_tc_n<128, false>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st);
+  return relu ? launch_tc_n<64, true>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st)
+              : launch_tc_n<64, false>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st);
 }
 
 }  // namespace ceeus
