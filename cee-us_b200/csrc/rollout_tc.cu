@@ -157,21 +157,33 @@ __device__ __forceinline__ void epi_row(uint32_t tacc, const float* __restrict__
 #pragma unroll
     for (int j = 0; j < HD; j += 4) {
       const float4 b = *reinterpret_cast<const float4*>(pb + j);
-      x[j] += b.x; x[j + 1] += b.y; x[j + 2] += b.z; x[j + 3] += b.w;
+      upk2(fadd2(pk2(x[j], x[j + 1]), pk2(b.x, b.y)), x[j], x[j + 1]);
+      upk2(fadd2(pk2(x[j + 2], x[j + 3]), pk2(b.z, b.w)), x[j + 2], x[j + 3]);
     }
   }
   if (ln) {
-    float v8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // second moment with packed fp32 FMAs (FFMA2): four independent accumulator pairs
+    uint64_t v2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-    for (int j = 0; j < HD; ++j) v8[j & 7] = fmaf(x[j], x[j], v8[j & 7]);
+    for (int j = 0; j < HD; j += 2) {
+      const uint64_t xp = pk2(x[j], x[j + 1]);
+      v2[(j >> 1) & 3] = ffma2(xp, xp, v2[(j >> 1) & 3]);
+    }
+    float v8[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) upk2(v2[j], v8[2 * j], v8[2 * j + 1]);
     const float v = ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
     const float rstd = rsqrtf(v * (1.f / HD) + 1e-5f);
     if (FOLD || (RELU && fold)) {
+      const uint64_t r2 = pk2(rstd, rstd);
 #pragma unroll
       for (int j = 0; j < HD; j += 4) {
         const float4 be = *reinterpret_cast<const float4*>(pbe + j);
-        h[j / 2] = pack_half2_relu(fmaf(x[j], rstd, be.x), fmaf(x[j + 1], rstd, be.y));
-        h[j / 2 + 1] = pack_half2_relu(fmaf(x[j + 2], rstd, be.z), fmaf(x[j + 3], rstd, be.w));
+        float a0, a1, a2, a3;
+        upk2(ffma2(pk2(x[j], x[j + 1]), r2, pk2(be.x, be.y)), a0, a1);
+        upk2(ffma2(pk2(x[j + 2], x[j + 3]), r2, pk2(be.z, be.w)), a2, a3);
+        h[j / 2] = pack_half2_relu(a0, a1);
+        h[j / 2 + 1] = pack_half2_relu(a2, a3);
       }
       return;
     }
