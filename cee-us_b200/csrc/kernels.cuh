@@ -43,7 +43,7 @@ struct TcLayout {
   int HD;
   int AUp, NAp, SNs;       // halves: header [agent|action|1|0..], node block [dyn|stat|0..], per-trajectory snrm row
   int KE1, KXn, KXg;       // padded K of the edge input, node x-part, global x-part
-  int Te, Tmax, n_pass_max, q_n;  // trajectories per edge pass, per group; node-tile lanes per warp and pass
+  int tpw, Tmax;           // whole trajectories per warp, per group (4 warps)
   int tail;                // N*S + G floats behind the dynamic part of an observation
   TcMat mat[TC_NMAT];
   int image_bytes;         // per (member, rank)
@@ -52,7 +52,7 @@ struct TcLayout {
   int kmap_len;
   int NS;                  // warpgroups (slots) per CTA: 2 at Hd = 128, 4 at Hd = 64
   int sm_w, sm_par, sm_nrm, sm_out, nrm_floats, sm_slot[4], sm_bar, smem_bytes;
-  int so_h2, so_agg, so_glob, so_snrm, so_tail, so_first;  // offsets inside a slot region
+  int so_stage, so_glob, so_snrm, so_tail;  // offsets inside a slot region
   int pairs;               // CTA pairs in the grid
   int scratch_floats;      // per member: logical fp32 matrices built by the pack kernels
 };

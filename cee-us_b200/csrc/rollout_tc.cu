@@ -224,9 +224,14 @@ __device__ __forceinline__ uint4 pack8(const float (&acc)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// N2: the two-object graph (one edge per node: aggregation in registers) gets its own instantiation -- the kernel is one
-// big function and register pressure anywhere costs spills everywhere, so the N >= 3 aggregation code must not be in it.
-template <int HD, bool RELU, bool N2, bool DBG, bool FOLD>
+// Row layout ("node major"): TMEM lane == tile row == (trajectory b, node i); a warp owns 32 / N whole trajectories, so every
+// exchange between the rows of a trajectory stays inside one warp (__syncwarp, no block barriers in the step loop).
+//   * edge pass jj (0 .. N-2): row (b, i) carries the edge i -> j, j = jj + (jj >= i): E1, E2.  The sum over the outgoing edges
+//     of node i is a running fp16 sum in the row's own TMEM lane (R2), i.e. the node aggregate needs no communication at all.
+//   * the sum over all edges of a trajectory (global aggregate) is formed once per step from the N node aggregates through a
+//     warp-private staging buffer and parked in shared memory until the global tile needs it.
+//   * node tile rows == the same lanes; global tile row of trajectory b == lane (b, 0).
+template <int HD, bool RELU, bool DBG, bool FOLD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::value, 1)
     rollout_gnn_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcLayout tl, const uint8_t* __restrict__ wimg,
                           const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg) {
@@ -234,11 +239,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
   constexpr int CH = HD / 8;  // 16-byte chunks per hidden row
   constexpr int NS = TcSlots<HD>::value;
   constexpr int kTcThreads = 128 * NS;
+  constexpr int kAU = 16, kNA = 16;  // halves: header [agent | action | 1 | 0..], node block [dyn | stat | 0..]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
-  const int N = N2 ? 2 : md.N, A = md.A, D = md.D, S = md.S, U = md.U, sd = md.sd, O = md.O;
-  const int NE = N * (N - 1);
+  const int N = md.N, A = md.A, D = md.D, S = md.S, U = md.U, O = md.O;
 
   // ---- member / trajectory range of this pair: pairs are dealt to members as evenly as the count allows ----
   int e, lp, np;
@@ -250,9 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
   const int per_worker = (ra.n + 2 * NS * np - 1) / (2 * NS * np);
   const int rounds = (per_worker + tl.Tmax - 1) / tl.Tmax;
   const int T = (per_worker + rounds - 1) / rounds;  // trajectories per group, <= Tmax
-  const int Te = tl.Te;
-  const int n_pass = (T + Te - 1) / Te;
-  const int n_stage = 2 * n_pass + 6;
+  const int n_stage = 2 * (N - 1) + 6;
 
   uint8_t* sW = smem + tl.sm_w;
   float* sPar = reinterpret_cast<float*>(smem + tl.sm_par);
@@ -326,13 +329,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     const int row = tid & 127;     // tile row == TMEM lane
     const int worker = (lp * 2 + (int)rank) * NS + s;
     uint8_t* slot = smem + tl.sm_slot[s];
-    uint8_t* s_h2 = slot + tl.so_h2;      // [128][HD] fp16, 16-byte chunks swizzled by (row & 7)
-    uint8_t* s_agg = slot + tl.so_agg;    // [Te*N][HD] fp16 sums over the N-1 outgoing edges (N >= 3)
-    uint8_t* s_glob = slot + tl.so_glob;  // [T][HD] fp16 sums over all edges
-    __half* snrm = reinterpret_cast<__half*>(slot + tl.so_snrm);  // [T][SNs] normalised [hdr | node blocks]
-    float* s_tail = reinterpret_cast<float*>(slot + tl.so_tail);  // [T][tail] static features + goal (fp32)
-    short* s_first = reinterpret_cast<short*>(slot + tl.so_first);  // [Te*N] first edge row of aggregate row a (pass-local)
-    const int SNs = tl.SNs, AUp = tl.AUp, NAp = tl.NAp, tail = tl.tail;
+    uint8_t* s_stage = slot + tl.so_stage + q * (32 * HD);  // this warp's staging rows: [32][HD/2] fp16 (half a hidden row)
+    uint8_t* s_glob = slot + tl.so_glob;  // [Tmax][HD] fp16 sums over all edges of a trajectory
+    __half* snrm = reinterpret_cast<__half*>(slot + tl.so_snrm);  // [Tmax][SNs] normalised [hdr | node blocks]
+    float* s_tail = reinterpret_cast<float*>(slot + tl.so_tail);  // [Tmax][tail] static features + goal (fp32)
+    const int SNs = tl.SNs, tail = tl.tail, tpw = tl.tpw;
     const float* __restrict__ nrm = sNrm;
     const bool ln = md.layer_norm != 0;
     const int act = md.act;
@@ -349,8 +350,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       if (dbg_on && dbg_n < 250) { dbg[2 * dbg_n] = tag; dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
     };
 
-    // ---- MMA issue: warp 0 of the warpgroup in the leader CTA waits for both CTAs' A operands and issues the stage ----
-    const bool issuer_warp = rank == 0 && q == 0;
+    // ---- static row roles ----
+    // The warps of a slot are filled with trajectories in order; odd slots fill from the last scheduler backwards, so that at
+    // partial fill the busy warps of neighbouring slots sit on different schedulers.
+    const int qf = (s & 1) ? 3 - q : q;
+    const int bw = lane / N, ni = lane - bw * N;  // trajectory inside the warp, node
+    const bool lane_ok = bw < tpw;
+    const int b = qf * tpw + min(bw, tpw - 1);  // group-local trajectory of this row (clamped for the idle lanes)
+
+    // ---- MMA issue: the last-filled warp of the warpgroup in the leader CTA waits for both CTAs' A operands and issues ----
+    const bool issuer_warp = rank == 0 && qf == 3;
     uint32_t aph = 0;
     const uint32_t idesc_h = make_idesc_f16(256, HD);
     const uint32_t idesc_o = make_idesc_f16(256, 16);
@@ -381,64 +390,56 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       __syncwarp();
       stamp(90 + kind);
     };
-    auto kind_of = [&](int st) { return st < 2 * n_pass ? (st & 1) : 2 + (st - 2 * n_pass); };
+    auto kind_of = [&](int st) { return st < 2 * (N - 1) ? (st & 1) : 2 + (st - 2 * (N - 1)); };
     auto parp = [&](int off) -> const float* { return off >= 0 ? sPar + off : nullptr; };
-    // ---- static row roles ----
-    // edge row (pass-local): trajectory bl, source node ei, target node ej
-    const int e_bl = row / NE, e_q = row % NE;
-    const int e_i = e_q / (N - 1), e_jj = e_q % (N - 1);
-    const int e_j = e_jj + (e_jj >= e_i ? 1 : 0);
-    // node row: pass n_p, pass-local aggregate row n_a = bl * N + i.  N == 2: node row == edge row (one edge per node);
-    // N >= 3: each pass's rows are dealt over the four warps so that the aggregation owners are spread.
-    int n_p, n_a;
-    if (N2) { n_p = 0; n_a = row; }
-    else { n_p = lane / tl.q_n; n_a = (lane % tl.q_n) * 4 + q; }
-    const bool n_valid = n_a < Te * N && n_p < n_pass;
-    const int n_b = n_p * Te + n_a / N, n_i = n_a % N;  // group-local trajectory, node
-    // global row: trajectory == row
 
     float dyn[16], agent[16], act_next[8];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { dyn[j] = 0.f; agent[j] = 0.f; }  // padded entries take part in the vectorised output update
-
-    for (int a = row; a < tl.Te * N; a += 128) s_first[a] = (short)((a / N) * NE + (a % N) * (N - 1));
 
     for (int rd = 0; rd < rounds; ++rd) {
       const int w_lo = min(ra.n, worker * per_worker), w_hi = min(ra.n, w_lo + per_worker);
       const int p0 = w_lo + rd * T;
       int Gc = max(0, min(T, w_hi - p0));  // live trajectories of this group (0: pure lock-step filler)
       if (DBG && dbg != nullptr && dbg[499] == 1 && s == 1) Gc = 0;  // profiling aid: slot 1 idles, slot 0 runs without SIMT contention
-      const bool live_n = n_valid && n_b < Gc;
-      const bool live_g = row < Gc;
+      const bool live = lane_ok && b < Gc;
+      const bool live_g = live && ni == 0;
+      const bool warp_on = qf * tpw < Gc;  // this warp owns at least one live trajectory
+      const uint4* sb = reinterpret_cast<const uint4*>(snrm + b * SNs);  // this row's trajectory: [hdr(2) | node blocks (2 each)]
       wg_sync(s);
-      // ---- group init: start observation -> registers, snrm, tail cache, traj[0] ----
-      for (int idx = row; idx < (T * SNs) / 8; idx += 128) reinterpret_cast<uint4*>(snrm)[idx] = make_uint4(0u, 0u, 0u, 0u);
+      // ---- group init: start observation -> registers, snrm, traj[0]; the trailing observation part for every step ----
+      for (int idx = row; idx < (tl.Tmax * SNs) / 8; idx += 128) reinterpret_cast<uint4*>(snrm)[idx] = make_uint4(0u, 0u, 0u, 0u);
       for (int idx = row; idx < Gc * O; idx += 128) {
-        const int b = idx / O, c = idx % O;
-        const float v = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
-        ra.traj[((size_t)e * ra.n + p0 + b) * O + c] = v;
+        const int bb = idx / O, c = idx % O;
+        const float v = __ldg(ra.start_obs + (size_t)((p0 + bb) / ra.traj_per_start) * O + c);
+        ra.traj[((size_t)e * ra.n + p0 + bb) * O + c] = v;
       }
       for (int idx = row; idx < Gc * tail; idx += 128) {
-        const int b = idx / tail, c = idx % tail;
-        s_tail[idx] = c < N * S ? __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + A + N * D + c)
-                                : __ldg(ra.goal + (size_t)((p0 + b) / ra.traj_per_goal) * md.G + (c - N * S));
+        const int bb = idx / tail, c = idx % tail;
+        s_tail[idx] = c < N * S ? __ldg(ra.start_obs + (size_t)((p0 + bb) / ra.traj_per_start) * O + A + N * D + c)
+                                : __ldg(ra.goal + (size_t)((p0 + bb) / ra.traj_per_goal) * md.G + (c - N * S));
       }
       wg_sync(s);
-      if (live_n) {
-        const float* so = ra.start_obs + (size_t)((p0 + n_b) / ra.traj_per_start) * O;
-        __half* dst = snrm + n_b * SNs + AUp + n_i * NAp;
+      // static features + goal (env.obs_postproc) are constant along the horizon: written here, outside the step loop
+      for (int hh = 1; hh <= ra.H; ++hh) {
+        float* oh = ra.traj + (((size_t)hh * md.E + e) * ra.n + p0) * O + (A + N * D);
+        for (int idx = row; idx < Gc * tail; idx += 128) oh[(size_t)(idx / tail) * O + idx % tail] = s_tail[idx];
+      }
+      if (live) {
+        const float* so = ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O;
+        __half* dst = snrm + b * SNs + kAU + ni * kNA;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (j < D) {
-            dyn[j] = __ldg(so + A + n_i * D + j);
+            dyn[j] = __ldg(so + A + ni * D + j);
             dst[j] = __float2half_rn((dyn[j] - nrm[md.nrm.in_dyn + j]) * nrm[md.nrm.in_dyn + D + j]);
           }
         for (int j = 0; j < S; ++j)
-          dst[D + j] = __float2half_rn((__ldg(so + A + N * D + n_i * S + j) - nrm[md.nrm.in_stat + j]) * nrm[md.nrm.in_stat + S + j]);
+          dst[D + j] = __float2half_rn((__ldg(so + A + N * D + ni * S + j) - nrm[md.nrm.in_stat + j]) * nrm[md.nrm.in_stat + S + j]);
       }
       if (live_g) {
-        const float* so = ra.start_obs + (size_t)((p0 + row) / ra.traj_per_start) * O;
-        __half* dst = snrm + row * SNs;
+        const float* so = ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O;
+        __half* dst = snrm + b * SNs;
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (j < A) {
@@ -448,22 +449,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (j < U) {
-            const float a0 = __ldg(ra.actions + ((size_t)(p0 + row) * ra.H) * U + j);
+            const float a0 = __ldg(ra.actions + ((size_t)(p0 + b) * ra.H) * U + j);
             dst[A + j] = __float2half_rn((a0 - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]);
           }
         dst[A + U] = __float2half_rn(1.f);
       }
       wg_sync(s);
 
-      // A operand of an edge pass: [hdr | x_i | x_j] of this thread's edge row -> R1
-      auto build_edge = [&](int p) {
-        const int b = min(p * Te + e_bl, T - 1);
-        const uint4* sb = reinterpret_cast<const uint4*>(snrm + b * SNs);
-        int col = 0;
-        for (int c = 0; c < AUp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[c]);
-        for (int c = 0; c < NAp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[(AUp + e_i * NAp) / 8 + c]);
-        for (int c = 0; c < NAp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[(AUp + e_j * NAp) / 8 + c]);
-        for (; col < tl.KE1 / 2; col += 4) tmem_st4(t_r1 + col, make_uint4(0u, 0u, 0u, 0u));
+      // A operand of edge pass jj: [hdr | x_i | x_j] of this row's edge -> R1 (KE1 = 48 halves = 24 columns)
+      auto build_edge = [&](int jj) {
+        const int nj = min(jj + (jj >= ni ? 1 : 0), N - 1);
+        const uint4 h0 = sb[0], h1 = sb[1], xi0 = sb[2 + 2 * ni], xi1 = sb[3 + 2 * ni], xj0 = sb[2 + 2 * nj], xj1 = sb[3 + 2 * nj];
+        const uint32_t v[16] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, xi0.x, xi0.y, xi0.z, xi0.w, xi1.x, xi1.y, xi1.z, xi1.w};
+        const uint32_t w[8] = {xj0.x, xj0.y, xj0.z, xj0.w, xj1.x, xj1.y, xj1.z, xj1.w};
+        tmem_st16(t_r1, v);
+        tmem_st8(t_r1 + 16, w);
+      };
+      // state after model step hh -> traj[hh + 1] (issued while an MMA stage runs, off the dependency chain)
+      auto flush_outputs = [&](int hh) {
+        float* og = ra.traj + (((size_t)(hh + 1) * md.E + e) * ra.n + p0 + b) * O;
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < D) og[A + ni * D + j] = dyn[j];
+        }
+        if (live_g) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < A) og[j] = agent[j];
+        }
       };
 
       for (int h = 0; h < ra.H; ++h) {
@@ -471,17 +485,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
         if (live_g && h + 1 < ra.H) {  // prefetch the next step's action; consumed in the G3 epilogue
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (j < U) act_next[j] = __ldg(ra.actions + ((size_t)(p0 + row) * ra.H + h + 1) * U + j);
+            if (j < U) act_next[j] = __ldg(ra.actions + ((size_t)(p0 + b) * ra.H + h + 1) * U + j);
         }
-        build_edge(0);
+        if (warp_on) build_edge(0);
         signal_a(cx, s, lane);
         mma_stage(TC_E1);
-        float* outp = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
+        if (h > 0) flush_outputs(h - 1);
 
 #pragma unroll 1
         for (int st = 0; st < n_stage; ++st) {
           const int kind = kind_of(st);
-          const int p = st >> 1;  // edge pass (kinds E1 / E2)
+          const int jj = st >> 1;  // edge pass (kinds E1 / E2)
           stamp(10 + kind);
           wait_bar(cx, &d_ready[s], dph, 10 + kind);
           dph ^= 1u;
@@ -490,119 +504,76 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
           const TcMat& m = tl.mat[kind];
           if (kind != TC_N3 && kind != TC_G3) {
             // ------------------ hidden layer: LayerNorm + activation -> fp16 ------------------
-            const bool live = kind <= TC_E2 ? (e_bl < Te && p * Te + e_bl < Gc) : kind <= TC_N2 ? live_n : live_g;
-            const bool warp_on = __any_sync(FULL, live);
-            const float* pb = parp(m.par_bias);
-            const float* pg = parp(m.par_gamma);
-            const float* pbe = parp(m.par_beta);
-            const bool lnm = ln && m.ln;
-            // where the fp16 row goes: 0 = R1 (next layer's A operand), 1 = N == 2 aggregation, 2 = staging for N >= 3
-            const int mode = kind != TC_E2 ? 0 : (N2 ? 1 : 2);
             if (warp_on) {
               uint32_t hreg[HD / 2];
-              epi_row<HD, RELU, FOLD>(t_acc, pb, pg, pbe, lnm, fold, act, hreg);
-              if (mode == 0) {
+              epi_row<HD, RELU, FOLD>(t_acc, parp(m.par_bias), parp(m.par_gamma), parp(m.par_beta), ln && m.ln, fold, act, hreg);
+              if (kind != TC_E2) {
                 store_hidden<HD>(t_r1, hreg);
                 // the next layer's bias rides in a constant-one K column that lives in R2 (free once this layer's MMA is done)
                 if (tl.mat[kind + 1].K > tl.mat[kind + 1].kx && tl.mat[kind + 1].kx == HD) tmem_st4(t_r2, make_uint4(0x00003c00u, 0u, 0u, 0u)), tmem_st4(t_r2 + 4, make_uint4(0u, 0u, 0u, 0u));
-              } else if (N2) {
-                // one outgoing edge per node: the node aggregate is this thread's own row (-> R2); the global aggregate is the
-                // sum of the two rows of a trajectory (adjacent lanes) -> s_glob, written by the even lane
-                store_hidden<HD>(t_r2, hreg);
-#pragma unroll
-                for (int j = 0; j < HD / 2; ++j) {
-                  const uint32_t o = __shfl_xor_sync(FULL, hreg[j], 1);
-                  const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&hreg[j]), *reinterpret_cast<const __half2*>(&o));
-                  hreg[j] = *reinterpret_cast<const uint32_t*>(&sum);
-                }
-                if (live && (row & 1) == 0) {
-                  const int gb = row >> 1;
-#pragma unroll
-                  for (int c = 0; c < CH; ++c)
-                    *reinterpret_cast<uint4*>(s_glob + (size_t)gb * (HD * 2) + ((c ^ (gb & 7)) * 16)) =
-                        make_uint4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
-                }
               } else {
-#pragma unroll
-                for (int c = 0; c < CH; ++c)
-                  *reinterpret_cast<uint4*>(s_h2 + (size_t)row * (HD * 2) + ((c ^ (row & 7)) * 16)) =
-                      make_uint4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
-              }
-            }
-            stamp(30 + kind);
-            if (kind == TC_E2) {
-              // ---------- aggregation of the hidden edge activations (models/utils.py:42-51; W3 folded) ----------
-              if constexpr (!N2) {
-                wg_sync(s);
-                const int live_tr = max(0, min(Te, Gc - p * Te));  // live trajectories of this pass
-                // phase 1: sums over the N-1 outgoing edges of every node of the pass (kept as a plain loop: batching the loads
-                // in registers was tried and lost more to spills elsewhere in this kernel than it gained here)
-                for (int t = row; t < live_tr * N * CH; t += 128) {
-                  const int a = t / CH, c = t % CH;
-                  const int first = s_first[a];
-                  float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                  for (int e2 = 0; e2 < N - 1; ++e2) {
-                    const int r = first + e2;
-                    add8(acc8, *reinterpret_cast<const uint4*>(s_h2 + (size_t)r * (HD * 2) + ((c ^ (r & 7)) * 16)));
-                  }
-                  *reinterpret_cast<uint4*>(s_agg + (size_t)a * (HD * 2) + ((c ^ (a & 7)) * 16)) = pack8(acc8);
-                }
-                wg_sync(s);
-                // phase 2a: the owner of a node row moves its aggregate into the node tile's A operand (R2)
-                if (__any_sync(FULL, n_p == p && live_n)) {
-                  // tcgen05.st is warp wide: lanes that belong to other passes re-write what R2 already holds
-                  const int a = min(n_a, Te * N - 1);
+                // ---------- aggregation of the hidden edge activations (models/utils.py:42-51; W3 folded) ----------
+                // node aggregate: running sum over this row's outgoing edges, kept in the row's own TMEM lane (R2)
+                if (jj > 0) {
 #pragma unroll
                   for (int c0 = 0; c0 < HD / 2; c0 += 32) {
                     uint32_t cur[32];
                     tmem_ld32(t_r2 + c0, cur);
                     tmem_wait_ld();
-                    if (n_p == p) {
 #pragma unroll
-                      for (int cc = 0; cc < 8; ++cc) {
-                        const int c = c0 / 4 + cc;
-                        const uint4 v = *reinterpret_cast<const uint4*>(s_agg + (size_t)a * (HD * 2) + ((c ^ (a & 7)) * 16));
-                        cur[4 * cc] = v.x; cur[4 * cc + 1] = v.y; cur[4 * cc + 2] = v.z; cur[4 * cc + 3] = v.w;
-                      }
+                    for (int j = 0; j < 32; ++j) {
+                      const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&hreg[c0 + j]), *reinterpret_cast<const __half2*>(&cur[j]));
+                      hreg[c0 + j] = *reinterpret_cast<const uint32_t*>(&sum);
                     }
-                    tmem_st32(t_r2 + c0, cur);
                   }
                 }
-                // phase 2b: sum over all edges of a trajectory = sum of its node sums
-                for (int t = row; t < live_tr * CH; t += 128) {
-                  const int bl = t / CH, c = t % CH;
-                  float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                  for (int i2 = 0; i2 < N; ++i2) {
-                    const int a = bl * N + i2;
-                    add8(acc8, *reinterpret_cast<const uint4*>(s_agg + (size_t)a * (HD * 2) + ((c ^ (a & 7)) * 16)));
+                store_hidden<HD>(t_r2, hreg);
+                if (jj == N - 2) {
+                  // global aggregate: sum of the N node aggregates of every trajectory of this warp, half a hidden row at a time
+                  // through the warp's staging rows; parked in s_glob until the global tile is built
+#pragma unroll
+                  for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+                    for (int c = 0; c < CH / 2; ++c)
+                      *reinterpret_cast<uint4*>(s_stage + lane * HD + ((c ^ (lane & (CH / 2 - 1))) * 16)) =
+                          make_uint4(hreg[hf * (HD / 4) + 4 * c], hreg[hf * (HD / 4) + 4 * c + 1], hreg[hf * (HD / 4) + 4 * c + 2], hreg[hf * (HD / 4) + 4 * c + 3]);
+                    __syncwarp();
+                    for (int it = lane; it < tpw * (CH / 2); it += 32) {
+                      const int tb = it / (CH / 2), c = it % (CH / 2);
+                      float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                      for (int i2 = 0; i2 < N; ++i2) {
+                        const int r = tb * N + i2;
+                        add8(acc8, *reinterpret_cast<const uint4*>(s_stage + r * HD + ((c ^ (r & (CH / 2 - 1))) * 16)));
+                      }
+                      const int gb = qf * tpw + tb, cg = hf * (CH / 2) + c;
+                      *reinterpret_cast<uint4*>(s_glob + (size_t)gb * (HD * 2) + ((cg ^ (gb & 7)) * 16)) = pack8(acc8);
+                    }
+                    __syncwarp();
                   }
-                  const int b = p * Te + bl;
-                  *reinterpret_cast<uint4*>(s_glob + (size_t)b * (HD * 2) + ((c ^ (b & 7)) * 16)) = pack8(acc8);
                 }
               }
-              stamp(40 + kind);
-              // next A operand: the following edge pass, or the x part of the node tile
-              if (p + 1 < n_pass) {
-                build_edge(p + 1);
+            }
+            stamp(30 + kind);
+            if (kind == TC_E2 && warp_on) {
+              // next A operand: the following edge pass, or the x part of the node tile ([hdr | x_i], KXn = 32 halves)
+              if (jj + 1 < N - 1) {
+                build_edge(jj + 1);
               } else {
-                const uint4* sb = reinterpret_cast<const uint4*>(snrm + min(n_b, T - 1) * SNs);
-                int col = 0;
-                for (int c = 0; c < AUp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[c]);
-                for (int c = 0; c < NAp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[(AUp + n_i * NAp) / 8 + c]);
-                for (; col < tl.KXn / 2; col += 4) tmem_st4(t_r1 + col, make_uint4(0u, 0u, 0u, 0u));
+                const uint4 h0 = sb[0], h1 = sb[1], xi0 = sb[2 + 2 * ni], xi1 = sb[3 + 2 * ni];
+                const uint32_t v[16] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, xi0.x, xi0.y, xi0.z, xi0.w, xi1.x, xi1.y, xi1.z, xi1.w};
+                tmem_st16(t_r1, v);
               }
             }
             signal_a(cx, s, lane);
             mma_stage(kind_of(st + 1));
           } else if (kind == TC_N3) {
             // ------------------ node output: delta -> de-normalise, residual update (gnn_ensemble.py:302-334, 935-939) ------------------
-            if (__any_sync(FULL, live_n)) {
+            if (warp_on) {
               uint32_t v[16];
               tmem_ld16(t_acc, v);
               tmem_wait_ld();
-              if (live_n) {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(snrm + n_b * SNs + AUp + n_i * NAp);
-                float* og = outp + (size_t)n_b * O + A + n_i * D;
+              if (live) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(snrm + b * SNs + kAU + ni * kNA);
                 const float4* tb = reinterpret_cast<const float4*>(sOut);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -613,10 +584,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                     const float n2 = dyn[4 * j4 + 2] + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
                     const float n3 = dyn[4 * j4 + 3] + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
                     dyn[4 * j4] = n0; dyn[4 * j4 + 1] = n1; dyn[4 * j4 + 2] = n2; dyn[4 * j4 + 3] = n3;
-                    if (4 * j4 < D) og[4 * j4] = n0;
-                    if (4 * j4 + 1 < D) og[4 * j4 + 1] = n1;
-                    if (4 * j4 + 2 < D) og[4 * j4 + 2] = n2;
-                    if (4 * j4 + 3 < D) og[4 * j4 + 3] = n3;
                     // padded entries have c1 = c0 = mi = is = 0 -> exact zeros, like the zero padding of the node block
                     if (4 * j4 + 1 < D || S == 0) dst[2 * j4] = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y);
                     else reinterpret_cast<__half*>(dst)[4 * j4] = __float2half_rn((n0 - mi.x) * is.x);
@@ -625,35 +592,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                   }
                 }
               }
-            }
-            // A operand of the global tile: [hdr | 0] -> R1, sum over all edges -> R2
-            wg_sync(s);  // s_glob rows were written by other threads of this warpgroup (edge passes)
-            {
-              const int b = min(row, T - 1);
-              const uint4* sb = reinterpret_cast<const uint4*>(snrm + b * SNs);
-              int col = 0;
-              for (int c = 0; c < AUp / 8; ++c, col += 4) tmem_st4(t_r1 + col, sb[c]);
-              for (; col < tl.KXg / 2; col += 4) tmem_st4(t_r1 + col, make_uint4(0u, 0u, 0u, 0u));
-              uint32_t hreg[HD / 2];
+              // A operand of the global tile (row of trajectory b == lane (b, 0)): [hdr] -> R1, sum over all edges -> R2
+              {
+                const uint4 h0 = sb[0], h1 = sb[1];
+                const uint32_t v8[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                tmem_st8(t_r1, v8);
+                uint32_t hreg[HD / 2];
 #pragma unroll
-              for (int c = 0; c < CH; ++c) {
-                const uint4 g4 = *reinterpret_cast<const uint4*>(s_glob + (size_t)b * (HD * 2) + ((c ^ (b & 7)) * 16));
-                hreg[4 * c] = g4.x; hreg[4 * c + 1] = g4.y; hreg[4 * c + 2] = g4.z; hreg[4 * c + 3] = g4.w;
+                for (int c = 0; c < CH; ++c) {
+                  const uint4 g4 = *reinterpret_cast<const uint4*>(s_glob + (size_t)b * (HD * 2) + ((c ^ (b & 7)) * 16));
+                  hreg[4 * c] = g4.x; hreg[4 * c + 1] = g4.y; hreg[4 * c + 2] = g4.z; hreg[4 * c + 3] = g4.w;
+                }
+                store_hidden<HD>(t_r2, hreg);
               }
-              store_hidden<HD>(t_r2, hreg);
             }
             signal_a(cx, s, lane);
             mma_stage(TC_G1);
           } else {
-            // ------------------ global output: agent delta, next action, trailing observation part ------------------
-            if (__any_sync(FULL, live_g)) {
+            // ------------------ global output: agent delta, next action ------------------
+            if (warp_on) {
               uint32_t v[16];
               tmem_ld16(t_acc, v);
               tmem_wait_ld();
               if (live_g) {
-                __half* dsth = snrm + row * SNs;
+                __half* dsth = snrm + b * SNs;
                 uint32_t* dst = reinterpret_cast<uint32_t*>(dsth);
-                float* og = outp + (size_t)row * O;
                 const float4* tb = reinterpret_cast<const float4*>(sOut + 64);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -664,10 +627,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                     const float n2 = agent[4 * j4 + 2] + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
                     const float n3 = agent[4 * j4 + 3] + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
                     agent[4 * j4] = n0; agent[4 * j4 + 1] = n1; agent[4 * j4 + 2] = n2; agent[4 * j4 + 3] = n3;
-                    if (4 * j4 < A) og[4 * j4] = n0;
-                    if (4 * j4 + 1 < A) og[4 * j4 + 1] = n1;
-                    if (4 * j4 + 2 < A) og[4 * j4 + 2] = n2;
-                    if (4 * j4 + 3 < A) og[4 * j4 + 3] = n3;
                     // the agent part is followed by the action in the header: only whole pairs may be written as 32 bits
                     if (4 * j4 + 1 < A) dst[2 * j4] = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y);
                     else dsth[4 * j4] = __float2half_rn((n0 - mi.x) * is.x);
@@ -681,16 +640,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                     if (j < U)
                       dsth[A + j] = __float2half_rn((act_next[j] - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]);
                 }
-                // trailing part of the observation (static features + goal, env.obs_postproc): constant along the horizon
-                for (int c = 0; c < tail; ++c) og[(sd - N * S) + c] = s_tail[row * tail + c];
               }
             }
-            tc_fence_before();
           }
         }
-        wg_sync(s);  // snrm of the next step is complete
+        __syncwarp();  // snrm of the next step is complete (all rows of a trajectory live in this warp)
         stamp(60);
       }
+      flush_outputs(ra.H - 1);
     }
   }
   // ---- teardown ----
@@ -699,6 +656,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
   cluster_sync();
   if (warp == 0) tmem_dealloc<2>(tmem_base, 512);
 }
+
 
 // ---- epilogue micro-benchmark: the hidden-layer epilogue alone (no barriers), 1..3 warps per scheduler; optionally one
 // extra warp keeps the tensor core busy with back-to-back MMAs into other TMEM columns (with_mma) ----
@@ -939,26 +897,20 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
   TcLayout t{};
   if (md.kind != CEEUS_MODEL_GNN || (md.Hd != 64 && md.Hd != 128) || md.L != 2) return false;
   if (md.D > 16 || md.A > 16 || md.U > 8 || md.N < 2) return false;
-  const int N = md.N, NA = md.D + md.S, NE = N * (N - 1), Hd = md.Hd;
+  const int N = md.N, NA = md.D + md.S, Hd = md.Hd;
   t.HD = Hd;
   t.NS = 512 / (2 * Hd);
-  t.AUp = round_up(md.A + md.U + 1, 8);
-  t.NAp = round_up(NA, 8);
+  // fixed operand geometry: 16-half header [agent | action | 1], 16-half node blocks -> KE1 = 48, KXn = 32, KXg = 16
+  if (md.A + md.U + 1 > 16 || NA > 16 || N > 32) return false;
+  t.AUp = 16;
+  t.NAp = 16;
   t.SNs = t.AUp + N * t.NAp;
-  t.KE1 = round_up(t.AUp + 2 * t.NAp, 16);
-  t.KXn = round_up(t.AUp + t.NAp, 16);
-  t.KXg = round_up(t.AUp, 16);
-  if (t.KE1 > Hd || NE > 128) return false;  // R1 holds the edge input (KE1/2 columns) and the hidden row (Hd/2)
-  t.Te = 128 / NE;
-  if (N == 2) {
-    t.q_n = 32; t.n_pass_max = 1; t.Tmax = t.Te;
-  } else {
-    t.q_n = (t.Te * N + 3) / 4;
-    t.n_pass_max = 32 / t.q_n;
-    if (t.n_pass_max < 1) return false;
-    t.Tmax = t.n_pass_max * t.Te;
-  }
-  if (t.Tmax > 128) t.Tmax = 128;
+  t.KE1 = t.AUp + 2 * t.NAp;
+  t.KXn = t.AUp + t.NAp;
+  t.KXg = t.AUp;
+  if (t.KE1 > Hd) return false;  // R1 holds the edge input (KE1/2 columns) and the hidden row (Hd/2)
+  t.tpw = 32 / N;       // whole trajectories per warp: every row of a trajectory lives in one warp
+  t.Tmax = 4 * t.tpw;   // trajectories per group (one 128-row tile per CTA and slot)
   t.tail = N * md.S + md.G;
   auto mat = [&](int m, int kx, int kagg, int n, int lnf) {
     t.mat[m].K = kx + kagg; t.mat[m].kx = kx; t.mat[m].N = n; t.mat[m].nloc = n / 2; t.mat[m].ln = lnf;
@@ -1015,8 +967,8 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
       if (t.mat[m].K > Hd) kmap_host[t.mat[m].kmap_off + Hd] = -2;  // bias row behind the constant-one column
     }
   }
-  // shared memory carve-up; the group size shrinks (fewer edge passes per group) until two slots fit
-  for (;;) {
+  // shared memory carve-up
+  {
     int sm = 0;
     t.sm_w = sm; sm += round_up(t.image_bytes, 1024);
     t.sm_par = sm; sm += round_up(t.par_floats * 4, 16);
@@ -1024,20 +976,15 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
     t.sm_nrm = sm; sm += round_up(t.nrm_floats * 4, 16);
     t.sm_out = sm; sm += 2 * 4 * 16 * 4;
     int so = 0;
-    t.so_h2 = so; so += N == 2 ? 0 : 128 * Hd * 2;
-    t.so_agg = so; so += N == 2 ? 0 : round_up(t.Te * N, 8) * Hd * 2;
+    t.so_stage = so; so += 4 * 32 * Hd;  // per warp: 32 rows x half a hidden row (fp16)
     t.so_glob = so; so += round_up(t.Tmax, 8) * Hd * 2;
     t.so_snrm = so; so += round_up(t.Tmax * t.SNs * 2, 16);
     t.so_tail = so; so += round_up(t.Tmax * t.tail * 4, 16);
-    t.so_first = so; so += round_up(t.Te * N * 2, 16);
     so = round_up(so, 128);
     for (int i = 0; i < t.NS; ++i) { t.sm_slot[i] = sm; sm += so; }
     t.sm_bar = sm; sm += 128;
     t.smem_bytes = sm;
-    if (t.smem_bytes <= 227 * 1024) break;
-    if (N == 2 || t.n_pass_max <= 1) return false;
-    t.n_pass_max -= 1;
-    t.Tmax = t.n_pass_max * t.Te;
+    if (t.smem_bytes > 227 * 1024) return false;
   }
   t.pairs = num_sms / 2;
   if (t.pairs < md.E) return false;
@@ -1056,23 +1003,16 @@ cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout
   return cudaGetLastError();
 }
 
-template <int HD, bool RELU, bool N2>
-static cudaError_t launch_tc_t(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
+template <int HD, bool RELU>
+static cudaError_t launch_tc_n(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                const float* wpar, int* err_flag, long long* dbg, bool all_fold, cudaStream_t st) {
-  auto kern = rollout_gnn_tc_kernel<HD, RELU, N2, false, false>;
-  if (dbg != nullptr) kern = rollout_gnn_tc_kernel<HD, RELU, N2, true, false>;
-  else if (RELU && all_fold) kern = rollout_gnn_tc_kernel<HD, RELU, N2, false, RELU>;
+  auto kern = rollout_gnn_tc_kernel<HD, RELU, false, false>;
+  if (dbg != nullptr) kern = rollout_gnn_tc_kernel<HD, RELU, true, false>;
+  else if (RELU && all_fold) kern = rollout_gnn_tc_kernel<HD, RELU, false, RELU>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
   if (e != cudaSuccess) return e;
   kern<<<dim3(2 * tl.pairs), 128 * TcSlots<HD>::value, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
   return cudaGetLastError();
-}
-
-template <int HD, bool RELU>
-static cudaError_t launch_tc_n(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
-                               const float* wpar, int* err_flag, long long* dbg, bool all_fold, cudaStream_t st) {
-  return md.N == 2 ? launch_tc_t<HD, RELU, true>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st)
-                   : launch_tc_t<HD, RELU, false>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st);
 }
 
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
