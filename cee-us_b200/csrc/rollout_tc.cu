@@ -23,6 +23,8 @@
 //     LayerNorm statistics stay fp32.  Parity bar: 1e-3 (BASELINE.json north_star, tf32/bf16 mode).
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -329,7 +331,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     const int row = tid & 127;     // tile row == TMEM lane
     const int worker = (lp * 2 + (int)rank) * NS + s;
     uint8_t* slot = smem + tl.sm_slot[s];
-    uint8_t* s_stage = slot + tl.so_stage + q * (32 * HD);  // this warp's staging rows: [32][HD/2] fp16 (half a hidden row)
+    float* s_obs = reinterpret_cast<float*>(slot + tl.so_obs + q * tl.obs_bytes);  // this warp's next observations [tpw][O] fp32
     uint8_t* s_glob = slot + tl.so_glob;  // [Tmax][HD] fp16 sums over all edges of a trajectory
     __half* snrm = reinterpret_cast<__half*>(slot + tl.so_snrm);  // [Tmax][SNs] normalised [hdr | node blocks]
     float* s_tail = reinterpret_cast<float*>(slot + tl.so_tail);  // [Tmax][tail] static features + goal (fp32)
@@ -361,12 +363,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     // ---- MMA issue: the last-filled warp of the warpgroup in the leader CTA waits for both CTAs' A operands and issues ----
     const bool issuer_warp = rank == 0 && qf == 3;
     uint32_t aph = 0;
-    const uint32_t idesc_h = make_idesc_f16(256, HD);
-    const uint32_t idesc_o = make_idesc_f16(256, 16);
     const uint32_t wbase = smem_u32(sW);
     const uint32_t m_acc = tmem_base + (uint32_t)(s * 2 * HD), m_r1 = m_acc + HD, m_r2 = m_r1 + HD / 2;
-    auto mma_stage = [&](int kind) {
-      if (!issuer_warp) return;
+    // compile-time stage kind: K extents are fixed by the operand geometry (KE1 = 48, KXn = 32, KXg = 16), so descriptors and
+    // TMEM addresses are uniform-register arithmetic and the K loop is fully unrolled
+    auto mma_issue = [&](auto kind_c) {
+      constexpr int kind = decltype(kind_c)::value;
       stamp(70 + kind);
       const bool ok = wait_bar(cx, &a_ready[s], aph, 2);
       aph ^= 1u;
@@ -374,21 +376,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       stamp(80 + kind);
       if (ok) {  // warp-converged: one elected lane issues, operands stay warp uniform
         const uint32_t elected = elect_one();
-        const TcMat& mm = tl.mat[kind];
-        const int kx = mm.kx / 16, kall = mm.K / 16;
-        const uint32_t idesc = (kind == TC_N3 || kind == TC_G3) ? idesc_o : idesc_h;
-        const uint32_t lbo_b = (uint32_t)mm.nloc * 16;
-        const uint64_t db0 = make_smem_desc(wbase + (uint32_t)mm.off, lbo_b, 128);
-        const uint32_t db_step = (2u * lbo_b) >> 4;  // descriptor start-address field advances by two 16-byte-chunk rows per K step
-#pragma unroll 2
-        for (int ks = 0; ks < kall; ++ks) {
-          const uint32_t a_col = ks < kx ? m_r1 + (uint32_t)(8 * ks) : m_r2 + (uint32_t)(8 * (ks - kx));
-          umma_f16_ts_cg2_elect(m_acc, a_col, db0 + (uint64_t)((uint32_t)ks * db_step), idesc, ks > 0 ? 1u : 0u, elected);
+        constexpr bool outl = kind == TC_N3 || kind == TC_G3;
+        constexpr int kx = (kind == TC_E1 ? 48 : kind == TC_N1 ? 32 : kind == TC_G1 ? 16 : HD) / 16;
+        constexpr int kmax = kind == TC_E1 ? 3 : (kind == TC_N3 || kind == TC_G3) ? HD / 16 : kind == TC_N1 ? 2 + HD / 16 : 1 + HD / 16;
+        const int kall = kind == TC_E2 ? HD / 16 + (N == 2 ? 1 : 0) : kmax;  // E2: + the constant-one block only when R2 is free (N == 2)
+        constexpr uint32_t idesc = outl ? make_idesc_f16(256, 16) : make_idesc_f16(256, HD);
+        constexpr uint32_t lbo_b = (uint32_t)(outl ? 8 : HD / 2) * 16;
+        const uint64_t db0 = make_smem_desc(wbase + (uint32_t)tl.mat[kind].off, lbo_b, 128);
+        constexpr uint32_t db_step = (2u * lbo_b) >> 4;  // descriptor start-address field advances by two 16-byte-chunk rows per K step
+#pragma unroll
+        for (int ks = 0; ks < kmax; ++ks) {
+          if (ks < kall) {
+            const uint32_t a_col = ks < kx ? m_r1 + (uint32_t)(8 * ks) : m_r2 + (uint32_t)(8 * (ks - kx));
+            umma_f16_ts_cg2_elect(m_acc, a_col, db0 + (uint64_t)((uint32_t)ks * db_step), idesc, ks > 0 ? 1u : 0u, elected);
+          }
         }
         umma_commit_cg2_mc_elect(&d_ready[s], 0x3, elected);
       }
       __syncwarp();
       stamp(90 + kind);
+    };
+    auto mma_stage = [&](int kind) {
+      if (!issuer_warp) return;
+      switch (kind) {
+        case TC_E1: mma_issue(std::integral_constant<int, TC_E1>{}); break;
+        case TC_E2: mma_issue(std::integral_constant<int, TC_E2>{}); break;
+        case TC_N1: mma_issue(std::integral_constant<int, TC_N1>{}); break;
+        case TC_N2: mma_issue(std::integral_constant<int, TC_N2>{}); break;
+        case TC_N3: mma_issue(std::integral_constant<int, TC_N3>{}); break;
+        case TC_G1: mma_issue(std::integral_constant<int, TC_G1>{}); break;
+        case TC_G2: mma_issue(std::integral_constant<int, TC_G2>{}); break;
+        default: mma_issue(std::integral_constant<int, TC_G3>{}); break;
+      }
     };
     auto kind_of = [&](int st) { return st < 2 * (N - 1) ? (st & 1) : 2 + (st - 2 * (N - 1)); };
     auto parp = [&](int off) -> const float* { return off >= 0 ? sPar + off : nullptr; };
@@ -420,10 +439,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                                 : __ldg(ra.goal + (size_t)((p0 + bb) / ra.traj_per_goal) * md.G + (c - N * S));
       }
       wg_sync(s);
-      // static features + goal (env.obs_postproc) are constant along the horizon: written here, outside the step loop
-      for (int hh = 1; hh <= ra.H; ++hh) {
-        float* oh = ra.traj + (((size_t)hh * md.E + e) * ra.n + p0) * O + (A + N * D);
-        for (int idx = row; idx < Gc * tail; idx += 128) oh[(size_t)(idx / tail) * O + idx % tail] = s_tail[idx];
+      // static features + goal (env.obs_postproc) are constant along the horizon: placed once in the staged observation rows
+      for (int idx = lane; idx < tpw * tail; idx += 32) {
+        const int tb = idx / tail, c = idx % tail;
+        s_obs[tb * O + (A + N * D) + c] = qf * tpw + tb < Gc ? s_tail[(qf * tpw + tb) * tail + c] : 0.f;
       }
       if (live) {
         const float* so = ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O;
@@ -465,19 +484,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
         tmem_st16(t_r1, v);
         tmem_st8(t_r1 + 16, w);
       };
-      // state after model step hh -> traj[hh + 1] (issued while an MMA stage runs, off the dependency chain)
+      // state after model step hh -> traj[hh + 1]: the warp's trajectories are contiguous in global memory, so the staged rows
+      // go out as one coalesced copy (issued while an MMA stage runs, off the dependency chain)
+      const int n_out = max(0, min(tpw, Gc - qf * tpw)) * O;
       auto flush_outputs = [&](int hh) {
-        float* og = ra.traj + (((size_t)(hh + 1) * md.E + e) * ra.n + p0 + b) * O;
-        if (live) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < D) og[A + ni * D + j] = dyn[j];
-        }
-        if (live_g) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < A) og[j] = agent[j];
-        }
+        float* og = ra.traj + (((size_t)(hh + 1) * md.E + e) * ra.n + p0 + qf * tpw) * O;
+#pragma unroll 4
+        for (int i = lane; i < n_out; i += 32) og[i] = s_obs[i];
       };
 
       for (int h = 0; h < ra.H; ++h) {
@@ -529,26 +542,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                 }
                 store_hidden<HD>(t_r2, hreg);
                 if (jj == N - 2) {
-                  // global aggregate: sum of the N node aggregates of every trajectory of this warp, half a hidden row at a time
-                  // through the warp's staging rows; parked in s_glob until the global tile is built
+                  // global aggregate: sum of the N node aggregates of a trajectory (adjacent lanes) by a segmented shuffle tree;
+                  // lane (b, 0) parks it in s_glob until the global tile is built
+                  for (int off = 1; off < N; off <<= 1) {
+                    const bool take = ni + off < N;
 #pragma unroll
-                  for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-                    for (int c = 0; c < CH / 2; ++c)
-                      *reinterpret_cast<uint4*>(s_stage + lane * HD + ((c ^ (lane & (CH / 2 - 1))) * 16)) =
-                          make_uint4(hreg[hf * (HD / 4) + 4 * c], hreg[hf * (HD / 4) + 4 * c + 1], hreg[hf * (HD / 4) + 4 * c + 2], hreg[hf * (HD / 4) + 4 * c + 3]);
-                    __syncwarp();
-                    for (int it = lane; it < tpw * (CH / 2); it += 32) {
-                      const int tb = it / (CH / 2), c = it % (CH / 2);
-                      float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                      for (int i2 = 0; i2 < N; ++i2) {
-                        const int r = tb * N + i2;
-                        add8(acc8, *reinterpret_cast<const uint4*>(s_stage + r * HD + ((c ^ (r & (CH / 2 - 1))) * 16)));
-                      }
-                      const int gb = qf * tpw + tb, cg = hf * (CH / 2) + c;
-                      *reinterpret_cast<uint4*>(s_glob + (size_t)gb * (HD * 2) + ((cg ^ (gb & 7)) * 16)) = pack8(acc8);
+                    for (int j = 0; j < HD / 2; ++j) {
+                      uint32_t o = __shfl_down_sync(FULL, hreg[j], off);
+                      o = take ? o : 0u;
+                      const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&hreg[j]), *reinterpret_cast<const __half2*>(&o));
+                      hreg[j] = *reinterpret_cast<const uint32_t*>(&sum);
                     }
-                    __syncwarp();
+                  }
+                  if (live_g) {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c)
+                      *reinterpret_cast<uint4*>(s_glob + (size_t)b * (HD * 2) + ((c ^ (b & 7)) * 16)) =
+                          make_uint4(hreg[4 * c], hreg[4 * c + 1], hreg[4 * c + 2], hreg[4 * c + 3]);
                   }
                 }
               }
@@ -574,6 +584,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
               tmem_wait_ld();
               if (live) {
                 uint32_t* dst = reinterpret_cast<uint32_t*>(snrm + b * SNs + kAU + ni * kNA);
+                float* og = s_obs + bw * O + A + ni * D;
                 const float4* tb = reinterpret_cast<const float4*>(sOut);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -584,6 +595,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                     const float n2 = dyn[4 * j4 + 2] + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
                     const float n3 = dyn[4 * j4 + 3] + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
                     dyn[4 * j4] = n0; dyn[4 * j4 + 1] = n1; dyn[4 * j4 + 2] = n2; dyn[4 * j4 + 3] = n3;
+                    if (4 * j4 < D) og[4 * j4] = n0;
+                    if (4 * j4 + 1 < D) og[4 * j4 + 1] = n1;
+                    if (4 * j4 + 2 < D) og[4 * j4 + 2] = n2;
+                    if (4 * j4 + 3 < D) og[4 * j4 + 3] = n3;
                     // padded entries have c1 = c0 = mi = is = 0 -> exact zeros, like the zero padding of the node block
                     if (4 * j4 + 1 < D || S == 0) dst[2 * j4] = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y);
                     else reinterpret_cast<__half*>(dst)[4 * j4] = __float2half_rn((n0 - mi.x) * is.x);
@@ -617,6 +632,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
               if (live_g) {
                 __half* dsth = snrm + b * SNs;
                 uint32_t* dst = reinterpret_cast<uint32_t*>(dsth);
+                float* og = s_obs + bw * O;
                 const float4* tb = reinterpret_cast<const float4*>(sOut + 64);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) {
@@ -627,6 +643,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                     const float n2 = agent[4 * j4 + 2] + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
                     const float n3 = agent[4 * j4 + 3] + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
                     agent[4 * j4] = n0; agent[4 * j4 + 1] = n1; agent[4 * j4 + 2] = n2; agent[4 * j4 + 3] = n3;
+                    if (4 * j4 < A) og[4 * j4] = n0;
+                    if (4 * j4 + 1 < A) og[4 * j4 + 1] = n1;
+                    if (4 * j4 + 2 < A) og[4 * j4 + 2] = n2;
+                    if (4 * j4 + 3 < A) og[4 * j4 + 3] = n3;
                     // the agent part is followed by the action in the header: only whole pairs may be written as 32 bits
                     if (4 * j4 + 1 < A) dst[2 * j4] = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y);
                     else dsth[4 * j4] = __float2half_rn((n0 - mi.x) * is.x);
@@ -976,7 +996,8 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
     t.sm_nrm = sm; sm += round_up(t.nrm_floats * 4, 16);
     t.sm_out = sm; sm += 2 * 4 * 16 * 4;
     int so = 0;
-    t.so_stage = so; so += 4 * 32 * Hd;  // per warp: 32 rows x half a hidden row (fp16)
+    t.obs_bytes = round_up(t.tpw * md.O * 4, 16);  // per warp: staged next observations of its trajectories
+    t.so_obs = so; so += 4 * t.obs_bytes;
     t.so_glob = so; so += round_up(t.Tmax, 8) * Hd * 2;
     t.so_snrm = so; so += round_up(t.Tmax * t.SNs * 2, 16);
     t.so_tail = so; so += round_up(t.Tmax * t.tail * 4, 16);
