@@ -225,6 +225,40 @@ __device__ __forceinline__ uint4 pack8(const float (&acc)[8]) {
   return o;
 }
 
+// MMA issue of one stage (leader CTA, one warp): wait for both CTAs' A operands, issue the K steps, commit to both CTAs.
+// (Out of line it was slower: the call spills the 255-register frame of the issuing warp.)  The stage
+// kind is a compile-time constant: K extents are fixed by the operand geometry (KE1 = 48, KXn = 32, KXg = 16), so descriptors
+// and TMEM addresses are uniform-register arithmetic and the K loop is fully unrolled.
+template <int HD, int KIND>
+__device__ __forceinline__ void tc_issue_stage(volatile int* abort_flag, int* err, uint64_t* a_bar, uint32_t aph, uint64_t* d_bar,
+                                            uint32_t wdesc_addr, uint32_t m_acc, int n2) {
+  Ctx cx;
+  cx.abort = abort_flag; cx.err = err;
+  const bool ok = wait_bar(cx, a_bar, aph, 2);
+  tc_fence_after();
+  if (ok) {  // warp-converged: one elected lane issues, operands stay warp uniform
+    const uint32_t elected = elect_one();
+    constexpr bool outl = KIND == TC_N3 || KIND == TC_G3;
+    constexpr int kx = (KIND == TC_E1 ? 48 : KIND == TC_N1 ? 32 : KIND == TC_G1 ? 16 : HD) / 16;
+    constexpr int kmax = KIND == TC_E1 ? 3 : outl ? HD / 16 : KIND == TC_N1 ? 2 + HD / 16 : 1 + HD / 16;
+    const int kall = KIND == TC_E2 ? HD / 16 + (n2 ? 1 : 0) : kmax;  // E2: + the constant-one block only when R2 is free (N == 2)
+    constexpr uint32_t idesc = outl ? make_idesc_f16(256, 16) : make_idesc_f16(256, HD);
+    constexpr uint32_t lbo_b = (uint32_t)(outl ? 8 : HD / 2) * 16;
+    const uint64_t db0 = make_smem_desc(wdesc_addr, lbo_b, 128);
+    constexpr uint32_t db_step = (2u * lbo_b) >> 4;  // descriptor start-address field advances by two 16-byte-chunk rows per K step
+    const uint32_t m_r1 = m_acc + HD, m_r2 = m_r1 + HD / 2;
+#pragma unroll
+    for (int ks = 0; ks < kmax; ++ks) {
+      if (ks < kall) {
+        const uint32_t a_col = ks < kx ? m_r1 + (uint32_t)(8 * ks) : m_r2 + (uint32_t)(8 * (ks - kx));
+        umma_f16_ts_cg2_elect(m_acc, a_col, db0 + (uint64_t)((uint32_t)ks * db_step), idesc, ks > 0 ? 1u : 0u, elected);
+      }
+    }
+    umma_commit_cg2_mc_elect(d_bar, 0x3, elected);
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Row layout ("node major"): TMEM lane == tile row == (trajectory b, node i); a warp owns 32 / N whole trajectories, so every
 // exchange between the rows of a trajectory stays inside one warp (__syncwarp, no block barriers in the step loop).
@@ -364,51 +398,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     const bool issuer_warp = rank == 0 && qf == 3;
     uint32_t aph = 0;
     const uint32_t wbase = smem_u32(sW);
-    const uint32_t m_acc = tmem_base + (uint32_t)(s * 2 * HD), m_r1 = m_acc + HD, m_r2 = m_r1 + HD / 2;
-    // compile-time stage kind: K extents are fixed by the operand geometry (KE1 = 48, KXn = 32, KXg = 16), so descriptors and
-    // TMEM addresses are uniform-register arithmetic and the K loop is fully unrolled
-    auto mma_issue = [&](auto kind_c) {
-      constexpr int kind = decltype(kind_c)::value;
-      stamp(70 + kind);
-      const bool ok = wait_bar(cx, &a_ready[s], aph, 2);
-      aph ^= 1u;
-      tc_fence_after();
-      stamp(80 + kind);
-      if (ok) {  // warp-converged: one elected lane issues, operands stay warp uniform
-        const uint32_t elected = elect_one();
-        constexpr bool outl = kind == TC_N3 || kind == TC_G3;
-        constexpr int kx = (kind == TC_E1 ? 48 : kind == TC_N1 ? 32 : kind == TC_G1 ? 16 : HD) / 16;
-        constexpr int kmax = kind == TC_E1 ? 3 : (kind == TC_N3 || kind == TC_G3) ? HD / 16 : kind == TC_N1 ? 2 + HD / 16 : 1 + HD / 16;
-        const int kall = kind == TC_E2 ? HD / 16 + (N == 2 ? 1 : 0) : kmax;  // E2: + the constant-one block only when R2 is free (N == 2)
-        constexpr uint32_t idesc = outl ? make_idesc_f16(256, 16) : make_idesc_f16(256, HD);
-        constexpr uint32_t lbo_b = (uint32_t)(outl ? 8 : HD / 2) * 16;
-        const uint64_t db0 = make_smem_desc(wbase + (uint32_t)tl.mat[kind].off, lbo_b, 128);
-        constexpr uint32_t db_step = (2u * lbo_b) >> 4;  // descriptor start-address field advances by two 16-byte-chunk rows per K step
-#pragma unroll
-        for (int ks = 0; ks < kmax; ++ks) {
-          if (ks < kall) {
-            const uint32_t a_col = ks < kx ? m_r1 + (uint32_t)(8 * ks) : m_r2 + (uint32_t)(8 * (ks - kx));
-            umma_f16_ts_cg2_elect(m_acc, a_col, db0 + (uint64_t)((uint32_t)ks * db_step), idesc, ks > 0 ? 1u : 0u, elected);
-          }
-        }
-        umma_commit_cg2_mc_elect(&d_ready[s], 0x3, elected);
-      }
-      __syncwarp();
-      stamp(90 + kind);
-    };
+    const uint32_t m_acc = tmem_base + (uint32_t)(s * 2 * HD);
     auto mma_stage = [&](int kind) {
       if (!issuer_warp) return;
+      stamp(70 + kind);
+      const uint32_t wd = wbase + (uint32_t)tl.mat[kind].off;
+      const int n2 = N == 2;
       switch (kind) {
-        case TC_E1: mma_issue(std::integral_constant<int, TC_E1>{}); break;
-        case TC_E2: mma_issue(std::integral_constant<int, TC_E2>{}); break;
-        case TC_N1: mma_issue(std::integral_constant<int, TC_N1>{}); break;
-        case TC_N2: mma_issue(std::integral_constant<int, TC_N2>{}); break;
-        case TC_N3: mma_issue(std::integral_constant<int, TC_N3>{}); break;
-        case TC_G1: mma_issue(std::integral_constant<int, TC_G1>{}); break;
-        case TC_G2: mma_issue(std::integral_constant<int, TC_G2>{}); break;
-        default: mma_issue(std::integral_constant<int, TC_G3>{}); break;
+        case TC_E1: tc_issue_stage<HD, TC_E1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+        case TC_E2: tc_issue_stage<HD, TC_E2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+        case TC_N1: tc_issue_stage<HD, TC_N1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+        case TC_N2: tc_issue_stage<HD, TC_N2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+        case TC_N3: tc_issue_stage<HD, TC_N3>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+        case TC_G1: tc_issue_stage<HD, TC_G1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+        case TC_G2: tc_issue_stage<HD, TC_G2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+        default: tc_issue_stage<HD, TC_G3>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
       }
+      aph ^= 1u;
+      stamp(90 + kind);
     };
+    // stages whose successor takes its bias from a constant-one K block parked in R2 (bit = stage kind)
+    uint32_t cb_mask = 0;
+    for (int k = 0; k + 1 < TC_NMAT; ++k)
+      if (tl.mat[k + 1].K > tl.mat[k + 1].kx && tl.mat[k + 1].kx == HD) cb_mask |= 1u << k;
     auto kind_of = [&](int st) { return st < 2 * (N - 1) ? (st & 1) : 2 + (st - 2 * (N - 1)); };
     auto parp = [&](int off) -> const float* { return off >= 0 ? sPar + off : nullptr; };
 
@@ -520,10 +532,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
             if (warp_on) {
               uint32_t hreg[HD / 2];
               epi_row<HD, RELU, FOLD>(t_acc, parp(m.par_bias), parp(m.par_gamma), parp(m.par_beta), ln && m.ln, fold, act, hreg);
+              stamp(110 + kind);
               if (kind != TC_E2) {
                 store_hidden<HD>(t_r1, hreg);
                 // the next layer's bias rides in a constant-one K column that lives in R2 (free once this layer's MMA is done)
-                if (tl.mat[kind + 1].K > tl.mat[kind + 1].kx && tl.mat[kind + 1].kx == HD) tmem_st4(t_r2, make_uint4(0x00003c00u, 0u, 0u, 0u)), tmem_st4(t_r2 + 4, make_uint4(0u, 0u, 0u, 0u));
+                if ((cb_mask >> kind) & 1u) tmem_st4(t_r2, make_uint4(0x00003c00u, 0u, 0u, 0u)), tmem_st4(t_r2 + 4, make_uint4(0u, 0u, 0u, 0u));
               } else {
                 // ---------- aggregation of the hidden edge activations (models/utils.py:42-51; W3 folded) ----------
                 // node aggregate: running sum over this row's outgoing edges, kept in the row's own TMEM lane (R2)
@@ -575,6 +588,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
               }
             }
             signal_a(cx, s, lane);
+            stamp(120 + kind);
             mma_stage(kind_of(st + 1));
           } else if (kind == TC_N3) {
             // ------------------ node output: delta -> de-normalise, residual update (gnn_ensemble.py:302-334, 935-939) ------------------
@@ -1028,7 +1042,7 @@ template <int HD, bool RELU>
 static cudaError_t launch_tc_n(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                const float* wpar, int* err_flag, long long* dbg, bool all_fold, cudaStream_t st) {
   auto kern = rollout_gnn_tc_kernel<HD, RELU, false, false>;
-  if (dbg != nullptr) kern = rollout_gnn_tc_kernel<HD, RELU, true, false>;
+  if (dbg != nullptr) kern = (RELU && all_fold) ? rollout_gnn_tc_kernel<HD, RELU, true, RELU> : rollout_gnn_tc_kernel<HD, RELU, true, false>;
   else if (RELU && all_fold) kern = rollout_gnn_tc_kernel<HD, RELU, false, RELU>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
   if (e != cudaSuccess) return e;
