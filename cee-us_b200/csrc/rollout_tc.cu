@@ -251,7 +251,9 @@ __device__ __forceinline__ void tc_issue_stage(volatile int* abort_flag, int* er
     for (int ks = 0; ks < kmax; ++ks) {
       if (ks < kall) {
         const uint32_t a_col = ks < kx ? m_r1 + (uint32_t)(8 * ks) : m_r2 + (uint32_t)(8 * (ks - kx));
-        umma_f16_ts_cg2_elect(m_acc, a_col, db0 + (uint64_t)((uint32_t)ks * db_step), idesc, ks > 0 ? 1u : 0u, elected);
+        // E2 with N >= 3: the accumulator was pre-initialised with the bias by the E1 epilogue (no constant-one block: R2 is busy)
+        const uint32_t accum = ks > 0 ? 1u : (KIND == TC_E2 && !n2) ? 1u : 0u;
+        umma_f16_ts_cg2_elect(m_acc, a_col, db0 + (uint64_t)((uint32_t)ks * db_step), idesc, accum, elected);
       }
     }
     umma_commit_cg2_mc_elect(d_bar, 0x3, elected);
@@ -531,10 +533,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
             // ------------------ hidden layer: LayerNorm + activation -> fp16 ------------------
             if (warp_on) {
               uint32_t hreg[HD / 2];
-              epi_row<HD, RELU, FOLD>(t_acc, parp(m.par_bias), parp(m.par_gamma), parp(m.par_beta), ln && m.ln, fold, act, hreg);
+              // (no bias operand: hidden-layer biases ride in a constant-one K column, or -- E2 with N >= 3 -- in the accumulator)
+              epi_row<HD, RELU, FOLD>(t_acc, nullptr, parp(m.par_gamma), parp(m.par_beta), ln && m.ln, fold, act, hreg);
               stamp(110 + kind);
               if (kind != TC_E2) {
                 store_hidden<HD>(t_r1, hreg);
+                if (kind == TC_E1 && N != 2) {
+                  // E2's bias goes into the accumulator this thread has just read out; the E2 MMA accumulates on top of it
+                  const float* pb2 = sPar + tl.mat[TC_E2].par_bias;
+#pragma unroll
+                  for (int c0 = 0; c0 < HD; c0 += 32) {
+                    uint32_t bv[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float4 b4 = *reinterpret_cast<const float4*>(pb2 + c0 + 4 * j);
+                      bv[4 * j] = __float_as_uint(b4.x); bv[4 * j + 1] = __float_as_uint(b4.y);
+                      bv[4 * j + 2] = __float_as_uint(b4.z); bv[4 * j + 3] = __float_as_uint(b4.w);
+                    }
+                    tmem_st32(t_acc + c0, bv);
+                  }
+                }
                 // the next layer's bias rides in a constant-one K column that lives in R2 (free once this layer's MMA is done)
                 if ((cb_mask >> kind) & 1u) tmem_st4(t_r2, make_uint4(0x00003c00u, 0u, 0u, 0u)), tmem_st4(t_r2 + 4, make_uint4(0u, 0u, 0u, 0u));
               } else {
