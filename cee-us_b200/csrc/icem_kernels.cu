@@ -311,9 +311,26 @@ __global__ void __launch_bounds__(kTopkThreads) topk_kernel(const TopkArgs a) {
   const float* costs = a.costs + (size_t)env * a.P;
   Key last{-CUDART_INF_F, -1};
   float* cand = a.cand + (size_t)env * a.k * a.rec;
+  // the costs are read once: up to kTopkLocal per thread stay in registers for all k selection rounds (larger populations
+  // fall back to re-reading the tail from L2)
+  constexpr int kTopkLocal = 8;
+  float cl[kTopkLocal];
+#pragma unroll
+  for (int j = 0; j < kTopkLocal; ++j) {
+    const int i = tid + j * kTopkThreads;
+    float c = i < a.P ? __ldg(costs + i) : CUDART_INF_F;
+    if (c != c) c = CUDART_INF_F;
+    cl[j] = c;
+  }
   for (int r = 0; r < a.k; ++r) {
     Key best{CUDART_INF_F, 0x7fffffff};
-    for (int i = tid; i < a.P; i += kTopkThreads) {
+#pragma unroll
+    for (int j = 0; j < kTopkLocal; ++j) {
+      const int i = tid + j * kTopkThreads;
+      const Key k{cl[j], i};
+      if (i < a.P && key_less(last, k)) best = key_min(best, k);
+    }
+    for (int i = tid + kTopkLocal * kTopkThreads; i < a.P; i += kTopkThreads) {
       float c = __ldg(costs + i);
       if (c != c) c = CUDART_INF_F;
       const Key k{c, i};

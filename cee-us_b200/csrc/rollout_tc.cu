@@ -524,17 +524,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
           const int kind = kind_of(st);
           const int jj = st >> 1;  // edge pass (kinds E1 / E2)
           stamp(10 + kind);
+          // stage parameters are fetched before the wait, so their (indexed constant bank) latency hides behind the MMA
+          const TcMat& m = tl.mat[kind];
+          const float* pg = parp(m.par_gamma);
+          const float* pbe = parp(m.par_beta);
+          const bool lnm = ln && m.ln;
+          const bool cb = (cb_mask >> kind) & 1u;
           wait_bar(cx, &d_ready[s], dph, 10 + kind);
           dph ^= 1u;
           tc_fence_after();
           stamp(20 + kind);
-          const TcMat& m = tl.mat[kind];
           if (kind != TC_N3 && kind != TC_G3) {
             // ------------------ hidden layer: LayerNorm + activation -> fp16 ------------------
             if (warp_on) {
               uint32_t hreg[HD / 2];
               // (no bias operand: hidden-layer biases ride in a constant-one K column, or -- E2 with N >= 3 -- in the accumulator)
-              epi_row<HD, RELU, FOLD>(t_acc, nullptr, parp(m.par_gamma), parp(m.par_beta), ln && m.ln, fold, act, hreg);
+              epi_row<HD, RELU, FOLD>(t_acc, nullptr, pg, pbe, lnm, fold, act, hreg);
               stamp(110 + kind);
               if (kind != TC_E2) {
                 store_hidden<HD>(t_r1, hreg);
@@ -554,7 +559,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                   }
                 }
                 // the next layer's bias rides in a constant-one K column that lives in R2 (free once this layer's MMA is done)
-                if ((cb_mask >> kind) & 1u) tmem_st4(t_r2, make_uint4(0x00003c00u, 0u, 0u, 0u)), tmem_st4(t_r2 + 4, make_uint4(0u, 0u, 0u, 0u));
+                if (cb) tmem_st4(t_r2, make_uint4(0x00003c00u, 0u, 0u, 0u)), tmem_st4(t_r2 + 4, make_uint4(0u, 0u, 0u, 0u));
               } else {
                 // ---------- aggregation of the hidden edge activations (models/utils.py:42-51; W3 folded) ----------
                 // node aggregate: running sum over this row's outgoing edges, kept in the row's own TMEM lane (R2)
