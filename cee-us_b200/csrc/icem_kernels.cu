@@ -307,6 +307,7 @@ constexpr int kTopkThreads = 1024;
 __global__ void __launch_bounds__(kTopkThreads) topk_kernel(const TopkArgs a) {
   __shared__ Key wbest[32];
   __shared__ Key chosen;
+  __shared__ Key picked[64];
   const int env = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float* costs = a.costs + (size_t)env * a.P;
   Key last{-CUDART_INF_F, -1};
@@ -354,16 +355,22 @@ __global__ void __launch_bounds__(kTopkThreads) topk_kernel(const TopkArgs a) {
     }
     __syncthreads();
     last = chosen;
-    float* rec = cand + (size_t)r * a.rec;
-    const bool valid = last.i != 0x7fffffff;  // fewer than k finite candidates cannot happen for P >= k
-    const int li = valid ? last.i : 0;
-    if (tid == 0) {
-      rec[0] = valid ? last.c : CUDART_INF_F;
-      rec[1] = __int_as_float((int)(a.first_index + (long long)env * 0 + li));
-    }
-    for (int i = tid; i < a.E; i += kTopkThreads) rec[2 + i] = __ldg(a.cpm + ((size_t)env * a.P + li) * a.E + i);
-    for (int i = tid; i < a.HU; i += kTopkThreads) rec[2 + a.E + i] = __ldg(a.actions + ((size_t)env * a.P + li) * a.HU + i);
+    if (tid == 0) picked[r] = last;
     __syncthreads();
+  }
+  // the k records are copied together once the selection is complete (one round trip to L2 instead of k dependent ones)
+  const int body = a.E + a.HU;
+  for (int t = tid; t < a.k * (2 + body); t += kTopkThreads) {
+    const int r = t / (2 + body), c = t % (2 + body);
+    const Key pk = picked[r];
+    const bool valid = pk.i != 0x7fffffff;  // fewer than k finite candidates cannot happen for P >= k
+    const int li = valid ? pk.i : 0;
+    float v;
+    if (c == 0) v = valid ? pk.c : CUDART_INF_F;
+    else if (c == 1) v = __int_as_float((int)(a.first_index + (long long)li));
+    else if (c < 2 + a.E) v = __ldg(a.cpm + ((size_t)env * a.P + li) * a.E + (c - 2));
+    else v = __ldg(a.actions + ((size_t)env * a.P + li) * a.HU + (c - 2 - a.E));
+    cand[(size_t)r * a.rec + c] = v;
   }
 }
 
@@ -511,6 +518,7 @@ cudaError_t launch_costs(const CostArgs& a, const CostDesc& cd, cudaStream_t st)
 }
 
 cudaError_t launch_topk(const TopkArgs& a, cudaStream_t st) {
+  if (a.k > 64) return cudaErrorInvalidValue;  // picked[] in shared memory; update_kernel has the same bound
   topk_kernel<<<a.nE, kTopkThreads, 0, st>>>(a);
   return cudaGetLastError();
 }
