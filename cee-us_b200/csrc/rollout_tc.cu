@@ -3,22 +3,26 @@
 //
 // Execution model (DESIGN.md "rollout_gnn_tc_kernel"):
 //   * grid = CTA PAIRS (cluster of 2, tcgen05 cta_group::2, M = 256).  A pair owns one ensemble member; every B operand
-//     of the member (8 fp16 matrices, 96 KB per CTA thanks to the split by output column) is resident in shared memory
+//     of the member (8 fp16 matrices, ~100 KB per CTA thanks to the split by output column) is resident in shared memory
 //     for the whole kernel, staged by one bulk TMA copy.
-//   * per CTA two warpgroups ("slots"), each owning 2*HD TMEM columns: the fp32 accumulator (HD columns) and two fp16
-//     A-operand regions R1, R2 (HD/2 columns each).  The A operand of EVERY MMA comes from TMEM (tcgen05.mma "TS" form):
-//     the epilogue threads write the next layer's input with tcgen05.st, so activations never touch shared memory.
-//     Thread == tile row == TMEM lane in every epilogue.  Warps 8/9 lane 0 of the leader CTA issue the MMAs of slot 0/1;
-//     completion is multicast-committed to both CTAs.
-//   * a warpgroup takes a group of T trajectories through all H steps.  Per step: edge rows in passes of Te trajectories
-//     (E1, E2), aggregation of the hidden edge activations, node tile (N1, N2, N3), global tile (G1, G2, G3).
+//   * per CTA two (Hd = 128) or four (Hd = 64) warpgroups ("slots"), each owning 2*HD TMEM columns: the fp32 accumulator
+//     (HD columns) and two fp16 A-operand regions R1, R2 (HD/2 columns each).  The A operand of EVERY MMA comes from TMEM
+//     (tcgen05.mma "TS" form): the epilogue threads write the next layer's input with tcgen05.st, so activations never
+//     touch shared memory.  Thread == tile row == TMEM lane in every epilogue.  One warp per slot of the leader CTA issues
+//     the MMAs; completion is multicast-committed to both CTAs.
+//   * tile rows are "node major": row == (trajectory, node), a warp owns 32 / N whole trajectories.  A slot takes its group of
+//     trajectories through all H steps; per step N-1 edge passes (E1, E2; row (b, i) carries edge i -> j), the node tile
+//     (N1, N2, N3) on the same rows and the global tile (G1, G2, G3) on the rows (b, 0).  The node aggregate is a running
+//     fp16 sum in the row's own TMEM lane, the global aggregate a segmented warp-shuffle sum: no block barrier in the step loop.
 //   * algebra done at pack time (tc_logical_kernel): the edge output layer has no LayerNorm / activation and the
 //     aggregation is linear, so  aggr_j(h2_j W3 + b3) W_agg = aggr_j(h2_j) (W3 W_agg) + b3 W_agg  -- W3 is folded into the
 //     first node / global layer and the E3 stage disappears; mean-aggregation scales are folded too.  Weights feeding a
 //     LayerNorm are centred over the output columns, so the MMA result already has zero row mean and the epilogue only
-//     needs the second moment.  First-layer biases ride in a constant-one K column.
-//   * fp32 object states live in REGISTERS of the row-owner threads (node row: D dynamic features, global row: agent);
-//     shared memory only holds the normalised fp16 copy the A tiles are built from.
+//     needs the second moment; the LayerNorm affine is folded into the weights where every gamma != 0.  Biases ride in a
+//     constant-one K column (or, for E2 of the N >= 3 graphs, are pre-loaded into the accumulator).
+//   * fp32 object states live in REGISTERS of the row-owner threads (node row: D dynamic features, row (b, 0): agent);
+//     shared memory holds the normalised fp16 copy the A tiles are built from and the warp's staged next observations,
+//     which leave as one coalesced copy per step while an MMA stage runs.
 //   * operands are fp16 (10-bit mantissa, TF32 class) with fp32 accumulation; states, residual update, normalisers and
 //     LayerNorm statistics stay fp32.  Parity bar: 1e-3 (BASELINE.json north_star, tf32/bf16 mode).
 #include <cuda_fp16.h>
@@ -55,93 +59,6 @@ template <int HD>
 __device__ __forceinline__ void store_hidden(uint32_t taddr, const uint32_t (&h)[HD / 2]) {
 #pragma unroll
   for (int c0 = 0; c0 < HD / 2; c0 += 32) tmem_st32(taddr + c0, *reinterpret_cast<const uint32_t(*)[32]>(&h[c0]));
-}
-
-// One 32-column chunk of the accumulator row: (+ bias) and either the second-moment accumulation (pass 1) or
-// LayerNorm scale / shift + activation + fp16 packing (pass 2).
-__device__ __forceinline__ void chunk_bias(float (&x)[32], const float* __restrict__ pb) {
-  float4 b[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) b[j] = *reinterpret_cast<const float4*>(pb + 4 * j);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { x[4 * j] += b[j].x; x[4 * j + 1] += b[j].y; x[4 * j + 2] += b[j].z; x[4 * j + 3] += b[j].w; }
-}
-__device__ __forceinline__ void chunk_moment(const float (&x)[32], float (&v8)[8]) {
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v8[j & 7] = fmaf(x[j], x[j], v8[j & 7]);
-}
-template <bool RELU>
-__device__ __forceinline__ void chunk_finish(float (&x)[32], const float* __restrict__ pg, const float* __restrict__ pbe, bool ln,
-                                             float rstd, int act, uint32_t (&hc)[16]) {
-  if (ln) {
-    float4 g[8], be[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { g[j] = *reinterpret_cast<const float4*>(pg + 4 * j); be[j] = *reinterpret_cast<const float4*>(pbe + 4 * j); }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      x[4 * j] = fmaf(x[4 * j] * rstd, g[j].x, be[j].x); x[4 * j + 1] = fmaf(x[4 * j + 1] * rstd, g[j].y, be[j].y);
-      x[4 * j + 2] = fmaf(x[4 * j + 2] * rstd, g[j].z, be[j].z); x[4 * j + 3] = fmaf(x[4 * j + 3] * rstd, g[j].w, be[j].w);
-    }
-  }
-  if constexpr (RELU) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) hc[j / 2] = pack_half2_relu(x[j], x[j + 1]);
-  } else {
-#pragma unroll 4
-    for (int j = 0; j < 32; j += 2) hc[j / 2] = pack_half2(act_fn(x[j], act), act_fn(x[j + 1], act));
-  }
-}
-
-// bias + LayerNorm (second moment only: the weights are centred) + activation on the accumulator row -> packed fp16,
-// handed to `sink(c0, hc)` 32 columns (16 packed registers) at a time.  Two passes over the accumulator (TMEM reads are
-// cheap: ~140 cycles latency, > 1 KB/clk per SM); the next chunk's tcgen05.ld is in flight while the current one is
-// processed, and only 64 fp32 values are live, so the parameter loads of a chunk are issued together.  The chunk loop is
-// NOT unrolled beyond the buffer pair and there is exactly one call site: the hot code must stay inside the
-// instruction cache (the fully unrolled version was 800 KB of SASS and stalled on instruction fetch).
-template <int HD, bool RELU, class Sink, class Probe>
-__device__ __forceinline__ void epi_hidden(uint32_t tacc, const float* __restrict__ pb, const float* __restrict__ pg,
-                                           const float* __restrict__ pbe, bool ln, int act, Sink&& sink, Probe&& probe) {
-  constexpr int NC = HD / 32;
-  static_assert(NC % 2 == 0, "chunk pairs");
-  float xa[32], xb[32];
-  float rstd = 1.f;
-  if (ln) {
-    float v8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    tmem_ld32(tacc, *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
-#pragma unroll 1
-    for (int k = 0; k < NC; k += 2) {
-      tmem_wait_ld();
-      probe(110 + k);
-      tmem_ld32(tacc + 32 * (k + 1), *reinterpret_cast<uint32_t(*)[32]>(&xb[0]));
-      if (pb != nullptr) chunk_bias(xa, pb + 32 * k);
-      chunk_moment(xa, v8);
-      probe(111 + k);
-      tmem_wait_ld();
-      if (k + 2 < NC) tmem_ld32(tacc + 32 * (k + 2), *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
-      if (pb != nullptr) chunk_bias(xb, pb + 32 * (k + 1));
-      chunk_moment(xb, v8);
-    }
-    const float v = ((v8[0] + v8[1]) + (v8[2] + v8[3])) + ((v8[4] + v8[5]) + (v8[6] + v8[7]));
-    rstd = rsqrtf(v * (1.f / HD) + 1e-5f);
-    probe(119);
-  }
-  uint32_t hc[16];
-  tmem_ld32(tacc, *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
-#pragma unroll 1
-  for (int k = 0; k < NC; k += 2) {
-    tmem_wait_ld();
-    tmem_ld32(tacc + 32 * (k + 1), *reinterpret_cast<uint32_t(*)[32]>(&xb[0]));
-    if (pb != nullptr) chunk_bias(xa, pb + 32 * k);
-    chunk_finish<RELU>(xa, pg + 32 * k, pbe + 32 * k, ln, rstd, act, hc);
-    probe(120 + k);
-    sink(32 * k, hc);
-    probe(121 + k);
-    tmem_wait_ld();
-    if (k + 2 < NC) tmem_ld32(tacc + 32 * (k + 2), *reinterpret_cast<uint32_t(*)[32]>(&xa[0]));
-    if (pb != nullptr) chunk_bias(xb, pb + 32 * (k + 1));
-    chunk_finish<RELU>(xb, pg + 32 * (k + 1), pbe + 32 * (k + 1), ln, rstd, act, hc);
-    sink(32 * (k + 1), hc);
-  }
 }
 
 // One-pass hidden-layer epilogue on the whole accumulator row held in registers (255 registers per thread are available with
@@ -205,24 +122,6 @@ __device__ __forceinline__ void epi_row(uint32_t tacc, const float* __restrict__
 #pragma unroll 4
     for (int j = 0; j < HD; j += 2) h[j / 2] = pack_half2(act_fn(x[j], act), act_fn(x[j + 1], act));
   }
-}
-
-__device__ __forceinline__ void add8(float (&acc)[8], const uint4& m) {
-  const __half2* hp = reinterpret_cast<const __half2*>(&m);
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const float2 f = __half22float2(hp[t]);
-    acc[2 * t] += f.x;
-    acc[2 * t + 1] += f.y;
-  }
-}
-__device__ __forceinline__ uint4 pack8(const float (&acc)[8]) {
-  uint4 o;
-  o.x = pack_half2(acc[0], acc[1]);
-  o.y = pack_half2(acc[2], acc[3]);
-  o.z = pack_half2(acc[4], acc[5]);
-  o.w = pack_half2(acc[6], acc[7]);
-  return o;
 }
 
 // MMA issue of one stage (leader CTA, one warp): wait for both CTAs' A operands, issue the K steps, commit to both CTAs.
