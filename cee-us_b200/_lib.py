@@ -6,13 +6,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libceeus_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE = 0, -1, -2, -3
 MODEL_GNN, MODEL_MLP = 0, 1
 ACT = {"none": 0, None: 0, "relu": 1, "silu": 2, "swish": 2, "tanh": 3}
 PREC = {"fp32": 0, "tc": 1, "tf32": 1}
 ENV_NONE, ENV_CONSTRUCTION, ENV_PLAYGROUND = 0, 1, 2
-CASE_TOWER, CASE_PICKANDPLACE = 0, 1
+CASE_TOWER, CASE_PICKANDPLACE, CASE_FLIP, CASE_SLIDE = 0, 1, 2, 3
 COST = {"sum": 0, "best": 1}
 
 
@@ -26,6 +26,8 @@ class CeeusConfig(C.Structure):
         ("alpha", C.c_float), ("init_std", C.c_float), ("noise_beta", C.c_float), ("extrinsic_scale", C.c_float),
         ("env_kind", C.c_int32), ("cost_case", C.c_int32), ("sparse", C.c_int32), ("shaped_reward", C.c_int32),
         ("threshold", C.c_float), ("buffer_threshold", C.c_float),
+        ("coord_weights", C.c_float * 3), ("buffer_xyz", C.c_float * 3), ("cost_thres", C.c_float * 3),
+        ("gripper_init", C.c_float * 3),
         ("world_size", C.c_int32), ("rank", C.c_int32), ("seed", C.c_uint64)]
 
 

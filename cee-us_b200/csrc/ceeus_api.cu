@@ -238,6 +238,10 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
   cd.env_kind = c.env_kind; cd.cost_case = c.cost_case; cd.sparse = c.sparse; cd.shaped = c.shaped_reward;
   cd.use_std = c.use_ensemble_cost_std; cd.extrinsic_scale = c.extrinsic_scale; cd.threshold = c.threshold;
   cd.buffer_threshold = c.buffer_threshold;
+  for (int i = 0; i < 3; ++i) {
+    cd.coord_weights[i] = c.coord_weights[i]; cd.buffer_xyz[i] = c.buffer_xyz[i];
+    cd.cost_thres[i] = c.cost_thres[i]; cd.gripper_init[i] = c.gripper_init[i];
+  }
 
   h->F = c.horizon / 2 + 1;
   auto alloc = [&](float** p, size_t n) { return cudaMalloc(p, (n ? n : 1) * sizeof(float)); };

@@ -48,6 +48,7 @@ struct CostDesc {
   int env_kind, cost_case, sparse, shaped;
   int use_std;
   float extrinsic_scale, threshold, buffer_threshold;
+  float coord_weights[3], buffer_xyz[3], cost_thres[3], gripper_init[3];  // Flip / Slide
 };
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

@@ -172,7 +172,7 @@ __device__ __forceinline__ float norm3(const float* a, const float* b) {
 }
 
 // env.cost_fn on one predicted observation row.
-// construction: fpp_construction_env.py:404-511 (non Flip/Slide); playground: playground_env_wgoals.py:108-157
+// construction: fpp_construction_env.py:404-511; playground: playground_env_wgoals.py:108-157
 __device__ float env_cost_row(const float* __restrict__ row, const CostArgs& a, const CostDesc& cd, int kstar) {
   if (cd.env_kind == CEEUS_ENV_PLAYGROUND) {
     float s = 0.f;
@@ -182,6 +182,26 @@ __device__ float env_cost_row(const float* __restrict__ row, const CostArgs& a, 
         s += d * d;
       }
     return sqrtf(s);
+  }
+  if (cd.cost_case == CEEUS_CASE_FLIP || cd.cost_case == CEEUS_CASE_SLIDE) {
+    // per-coordinate distances (:297-355): achieved goal = euler angles (Flip, dims 3..5 of a block) or positions (Slide)
+    const int ao = cd.cost_case == CEEUS_CASE_FLIP ? 3 : 0;
+    float n_sparse = 0.f, dense_exp = 0.f;
+    for (int i = 0; i < a.N; ++i) {
+      bool any = false;
+      float es = 0.f;
+      for (int c = 0; c < 3; ++c) {
+        const float v = fmaxf(fabsf(row[a.A + a.D * i + ao + c] - row[a.sd + 3 * i + c]), cd.buffer_xyz[c]) * cd.coord_weights[c];
+        any = any || v > cd.cost_thres[c];
+        es += 1.f - expf(-0.5f * v);
+      }
+      n_sparse += any ? 1.f : 0.f;
+      dense_exp += es * (1.f / 3.f);
+    }
+    float g = 0.f;
+    if (cd.shaped && cd.cost_case == CEEUS_CASE_FLIP) g = norm3(row, cd.gripper_init);  // :457-458
+    if (cd.sparse) return n_sparse + g * 0.001f;
+    return dense_exp * 1e-3f + n_sparse + g * 0.01f;
   }
   int unsolved = 0;
   float dense = 0.f;
@@ -214,7 +234,8 @@ __global__ void __launch_bounds__(256) cost_kernel(const CostArgs a, const CostD
   const bool need_env = !cd.curiosity || cd.extrinsic;
 
   int kstar = 0;
-  if (need_env && cd.env_kind == CEEUS_ENV_CONSTRUCTION && cd.shaped) {  // get_next_block_id, :365-383 (start obs)
+  if (need_env && cd.env_kind == CEEUS_ENV_CONSTRUCTION && cd.shaped && cd.cost_case != CEEUS_CASE_FLIP &&
+      cd.cost_case != CEEUS_CASE_SLIDE) {  // get_next_block_id, :365-383 (start obs)
     int unsolved = 0;
     for (int i = 0; i < a.N; ++i) unsolved += norm3(base + a.A + a.D * i, base + a.sd + 3 * i) > cd.threshold ? 1 : 0;
     kstar = a.N - unsolved;

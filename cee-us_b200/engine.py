@@ -59,6 +59,8 @@ class Engine:
         need_env = (not curiosity) or extrinsic_reward
         if need_env and not d["task_cost_supported"]:
             raise NotImplementedError(f"task cost for env kind={d['kind']} case={d['case']} is not implemented on device")
+        if need_env and d["case"] == "Slide" and d["shaped_reward"]:
+            raise AssertionError("Shaped reward cannot be used with Slide!")  # as upstream, fpp_construction_env.py:455
         cfg = _lib.CeeusConfig()
         cfg.abi_version = _lib.ABI_VERSION
         cfg.model_kind = _lib.MODEL_GNN if model_kind == "gnn" else _lib.MODEL_MLP
@@ -85,6 +87,8 @@ class Engine:
         cfg.env_kind = d["env_kind"] if need_env else _lib.ENV_NONE
         cfg.cost_case, cfg.sparse, cfg.shaped_reward = d["cost_case"], d["sparse"], d["shaped_reward"]
         cfg.threshold, cfg.buffer_threshold = d["threshold"], d["buffer_threshold"]
+        for name in ("coord_weights", "buffer_xyz", "cost_thres", "gripper_init"):
+            getattr(cfg, name)[:] = [float(v) for v in d[name]]
         cfg.world_size, cfg.rank, cfg.seed = world_size, rank, seed
         self.cfg = cfg
         self.model_kind, self.num_layers, self.layer_norm = model_kind, num_layers, bool(layer_norm)

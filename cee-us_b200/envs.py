@@ -16,13 +16,23 @@ from . import _lib
 
 class TensorEnv:
     def __init__(self, *, name, kind, n_obj, agent_dim, dyn_dim, stat_dim, action_dim, goal_dim, case="Singletower",
-                 sparse=False, shaped_reward=True, threshold=0.02, buffer_threshold=0.025):
+                 sparse=False, shaped_reward=True, threshold=0.02, buffer_threshold=0.025, height_offset=0.42):
         self.name = name
         self.kind = kind
         self.nObj = self.num_blocks = self.num_objs = n_obj
         self.agent_dim, self.object_dyn_dim, self.object_stat_dim = agent_dim, dyn_dim, stat_dim
         self.case, self.sparse, self.shaped_reward = case, sparse, shaped_reward
         self.threshold, self.buffer_threshold = threshold, buffer_threshold
+        self.height_offset = height_offset
+        self.gripper_init = np.array([1.344, 0.749, 0.5319])  # fpp_construction_env.py:119
+        if case == "Flip":  # :93-105
+            self.coord_weights = np.array([1.0, 0.0, 0.0], np.float32)
+            self.buffer_threshold = np.float32(1e-4)
+            self.cost_thres = self.coord_weights * np.float32(0.087)
+        elif case == "Slide":
+            self.coord_weights = np.ones(3, np.float32)
+            self.buffer_threshold = np.array([0.1, 0.1, height_offset], np.float32)
+            self.cost_thres = np.array([0.1, 0.1, height_offset], np.float32)
         sd = agent_dim + n_obj * (dyn_dim + stat_dim)
         self.observation_space_size_preproc = sd
         self.goal_space_size = goal_dim
@@ -33,7 +43,7 @@ class TensorEnv:
         self.goal = np.zeros(goal_dim, np.float32)
 
 
-def construction_env(num_blocks, case="Singletower", sparse=False, shaped_reward=True):
+def construction_env(num_blocks, case="Singletower", sparse=False, shaped_reward=True, height_offset=0.42):
     """fpp_construction_env.py:32-35 (dims), :59-68 (thresholds)."""
     if "tower" in case or case == "Pyramid":
         thr = 0.02
@@ -47,13 +57,19 @@ def construction_env(num_blocks, case="Singletower", sparse=False, shaped_reward
         thr = 0.05
     return TensorEnv(name="FetchPickAndPlaceConstruction", kind="construction", n_obj=num_blocks, agent_dim=10,
                      dyn_dim=12, stat_dim=0, action_dim=4, goal_dim=3 * num_blocks + 3, case=case, sparse=sparse,
-                     shaped_reward=shaped_reward, threshold=thr, buffer_threshold=0.025)
+                     shaped_reward=shaped_reward, threshold=thr, buffer_threshold=0.025, height_offset=height_offset)
 
 
 def playground_env(num_objs):
     """playground_env_wgoals.py:24-27."""
     return TensorEnv(name="PlaygroundwGoals", kind="playground", n_obj=num_objs, agent_dim=4, dyn_dim=6, stat_dim=3,
                      action_dim=2, goal_dim=2 * num_objs, case="playground", threshold=0.23, buffer_threshold=0.23)
+
+
+def _arr(x):
+    if hasattr(x, "detach"):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x, np.float32)
 
 
 def describe_env(env):
@@ -72,11 +88,17 @@ def describe_env(env):
     d["env_kind"] = {"construction": _lib.ENV_CONSTRUCTION, "playground": _lib.ENV_PLAYGROUND}.get(kind, _lib.ENV_NONE)
     case = getattr(env, "case", "")
     d["case"] = case
-    d["task_cost_supported"] = kind in ("construction", "playground") and case not in ("Flip", "Slide")
-    d["cost_case"] = _lib.CASE_TOWER if ("tower" in case or case == "Pyramid") else _lib.CASE_PICKANDPLACE
+    d["task_cost_supported"] = kind in ("construction", "playground")
+    d["cost_case"] = (_lib.CASE_FLIP if case == "Flip" else _lib.CASE_SLIDE if case == "Slide" else
+                      _lib.CASE_TOWER if ("tower" in case or case == "Pyramid") else _lib.CASE_PICKANDPLACE)
     d["sparse"] = int(bool(getattr(env, "sparse", False)))
     d["shaped_reward"] = int(bool(getattr(env, "shaped_reward", False)))
     d["threshold"] = float(getattr(env, "threshold", 0.0))
-    bt = getattr(env, "buffer_threshold", 0.025)
-    d["buffer_threshold"] = float(bt) if np.ndim(bt) == 0 else 0.025
+    bt = _arr(getattr(env, "buffer_threshold", 0.025))
+    d["buffer_threshold"] = float(bt.reshape(-1)[0]) if bt.size == 1 else 0.025
+    # Flip / Slide (fpp_construction_env.py:93-105): tensors on a reference env, arrays on a TensorEnv
+    d["coord_weights"] = np.broadcast_to(_arr(getattr(env, "coord_weights", np.ones(3))).reshape(-1), (3,)).astype(np.float32)
+    d["buffer_xyz"] = np.broadcast_to(bt.reshape(-1), (3,)).astype(np.float32)
+    d["cost_thres"] = np.broadcast_to(_arr(getattr(env, "cost_thres", np.zeros(3))).reshape(-1), (3,)).astype(np.float32)
+    d["gripper_init"] = _arr(getattr(env, "gripper_init", np.zeros(3))).reshape(3).astype(np.float32)
     return d

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define CEEUS_ABI_VERSION 1
+#define CEEUS_ABI_VERSION 2
 
 enum {
   CEEUS_OK = 0,
@@ -58,7 +58,12 @@ enum { CEEUS_ACT_NONE = 0, CEEUS_ACT_RELU = 1, CEEUS_ACT_SILU = 2, CEEUS_ACT_TAN
 enum { CEEUS_PREC_FP32 = 0, CEEUS_PREC_TC = 1 };
 enum { CEEUS_ENV_NONE = 0, CEEUS_ENV_CONSTRUCTION = 1, CEEUS_ENV_PLAYGROUND = 2 };
 /* construction cost branches, fpp_construction_env.py:475-508 */
-enum { CEEUS_CASE_TOWER = 0 /* "*tower*" and "Pyramid" */, CEEUS_CASE_PICKANDPLACE = 1 /* every other non Flip/Slide case */ };
+enum {
+  CEEUS_CASE_TOWER = 0 /* "*tower*" and "Pyramid" */,
+  CEEUS_CASE_PICKANDPLACE = 1 /* every other non Flip/Slide case */,
+  CEEUS_CASE_FLIP = 2 /* per-coordinate distances on the euler angles, :422-439, :498-503 */,
+  CEEUS_CASE_SLIDE = 3 /* per-coordinate distances on the positions */
+};
 enum { CEEUS_COST_SUM = 0, CEEUS_COST_BEST = 1 }; /* cost_along_trajectory */
 
 typedef struct CeeusConfig {
@@ -106,6 +111,12 @@ typedef struct CeeusConfig {
   int32_t shaped_reward;
   float threshold;
   float buffer_threshold;
+  /* Flip / Slide only (fpp_construction_env.py:93-105, :297-355): per-coordinate weights, buffer zone, sparse thresholds;
+   * Flip with shaped_reward measures the gripper's distance from gripper_init (:457-458) */
+  float coord_weights[3];
+  float buffer_xyz[3];
+  float cost_thres[3];
+  float gripper_init[3];
   /* ---- multi GPU: trajectories are sharded, rank r owns global indices [r*P, (r+1)*P) of every env ---- */
   int32_t world_size;
   int32_t rank;

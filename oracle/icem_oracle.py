@@ -49,6 +49,7 @@ class EnvSpec:
     shaped_reward: bool = True
     threshold: float = 0.02
     buffer_threshold: float = 0.025
+    height_offset: float = 0.42  # Slide only (attribute of the simulator env, fpp_construction_env.py:101-105)
 
     @property
     def state_dim(self) -> int:  # observation without goal (obs_preproc)
@@ -385,12 +386,30 @@ def disagreement_bonus(next_obs_pehd: torch.Tensor) -> torch.Tensor:
 
 
 def construction_cost(spec: EnvSpec, obs: torch.Tensor, next_obs: torch.Tensor) -> torch.Tensor:
-    """FetchPickAndPlaceConstruction.cost_fn (fpp_construction_env.py:404-511), non Flip/Slide cases.
+    """FetchPickAndPlaceConstruction.cost_fn (fpp_construction_env.py:404-511).
     obs, next_obs: [P,E,H,O] -> [P,E,H]."""
-    if spec.case in ("Flip", "Slide"):
-        raise NotImplementedError("Flip/Slide cost branches are out of scope this round (SURVEY.md 8f rank 2)")
     N, A, D = spec.n_obj, spec.agent_dim, spec.dyn_dim
     sd = spec.state_dim
+    if spec.case in ("Flip", "Slide"):
+        # per-coordinate distances (:297-355, :422-439): the achieved goal is the euler-angle triple of every block for Flip
+        # (:42-44), its position for Slide; parameters :93-105
+        flip = spec.case == "Flip"
+        ao = 3 if flip else 0
+        w = torch.tensor([1.0, 0.0, 0.0] if flip else [1.0, 1.0, 1.0])
+        buf = torch.tensor(1e-4) if flip else torch.tensor([0.1, 0.1, spec.height_offset])
+        thres = w * 0.087 if flip else torch.tensor([0.1, 0.1, spec.height_offset])
+        goal = next_obs[..., sd:sd + 3 * N + 3]
+        per = [torch.maximum(torch.abs(next_obs[..., A + D * i + ao:A + D * i + ao + 3] - goal[..., 3 * i:3 * i + 3]), buf) * w
+               for i in range(N)]
+        sparse_obj = torch.stack([torch.any(p > thres, dim=-1).float() for p in per])          # :429-432
+        exp_dense = torch.stack([torch.mean(1.0 - torch.exp(-0.5 * p), dim=-1) for p in per])   # :323-338, :434-439
+        g = torch.zeros(next_obs.shape[:-1], dtype=torch.float32)
+        if spec.shaped_reward:
+            assert not spec.case == "Slide", "Shaped reward cannot be used with Slide!"          # :455
+            g = torch.linalg.norm(next_obs[..., 0:3] - torch.tensor([1.344, 0.749, 0.5319]), dim=-1)  # :457-458, :119
+        if spec.sparse:
+            return sparse_obj.sum(dim=0) + g * 0.001                                              # :476-480
+        return exp_dense.sum(dim=0) * 1e-3 + sparse_obj.sum(dim=0) + g * 0.01                     # :498-503
 
     def goal_of(o):
         return o[..., sd:sd + 3 * N + 3]

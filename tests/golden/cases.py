@@ -48,6 +48,13 @@ CASES = {
     "rollout_gnn_c3_pp_sparse": dict(kind="rollout", env="construction", n_obj=3, model="gnn", hidden=128, layers=2,
                                      P=9, H=4, wseed=15, identity_norm=True, running=False, oseed=7,
                                      case="PickAndPlace", sparse=False),
+    "rollout_gnn_c2_flip": dict(kind="rollout", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=16, H=5,
+                                wseed=16, identity_norm=True, running=False, oseed=13, case="Flip", sparse=False),
+    "rollout_gnn_c2_flip_sparse": dict(kind="rollout", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=16,
+                                       H=5, wseed=16, identity_norm=True, running=False, oseed=13, case="Flip", sparse=True),
+    "rollout_gnn_c3_slide": dict(kind="rollout", env="construction", n_obj=3, model="gnn", hidden=128, layers=2, P=12, H=5,
+                                 wseed=17, identity_norm=True, running=False, oseed=14, case="Slide", sparse=False,
+                                 shaped=False),
     # full MPC steps (3 consecutive get_action calls after beginning_of_rollout)
     "mpc_gnn_c2_curious": dict(kind="mpc", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=128, H=20,
                                wseed=21, identity_norm=True, running=False, oseed=8, nseed=100, steps=3,
@@ -73,7 +80,8 @@ CASES = {
 def build_inputs(c):
     """Everything derivable from the case dict (used by the generator *and* by the tests)."""
     if c["env"] == "construction":
-        spec = orc.construction_spec(c["n_obj"], case=c.get("case", "Singletower"), sparse=c.get("sparse", False))
+        spec = orc.construction_spec(c["n_obj"], case=c.get("case", "Singletower"), sparse=c.get("sparse", False),
+                                     shaped_reward=c.get("shaped", True))
     else:
         spec = orc.playground_spec(c["n_obj"])
     E = 5
@@ -86,6 +94,15 @@ def build_inputs(c):
     weights = orc.synth_weights(shapes, c["wseed"])
     norms = orc.synth_normalizers(ndims, c["wseed"], identity=c["identity_norm"])
     obs, goal = orc.synth_start_obs(spec, c["oseed"])
+    if c.get("case") in ("Flip", "Slide"):
+        # per-coordinate tasks: goals within a few thresholds of the achieved values, so that both sides of every
+        # comparison in the cost occur (Flip compares euler angles, dims 3..5 of a block; Slide positions)
+        rs = np.random.RandomState(c["oseed"] + 500)
+        ao = 3 if c["case"] == "Flip" else 0
+        for i in range(c["n_obj"]):
+            ach = obs[spec.agent_dim + spec.dyn_dim * i + ao:spec.agent_dim + spec.dyn_dim * i + ao + 3]
+            goal[3 * i:3 * i + 3] = ach + rs.uniform(-0.25, 0.25, 3).astype(np.float32)
+        obs[spec.state_dim:] = goal
     return spec, weights, norms, obs, goal
 
 

@@ -54,7 +54,7 @@ def load_into_reference_mlp(model, weights, normalizers, running_stats):
 def build_reference(c, spec, weights, norms, goal):
     if c["env"] == "construction":
         env = rh.make_construction_env(c["n_obj"], case=c.get("case", "Singletower"), sparse=c.get("sparse", False),
-                                       goal=goal)
+                                       shaped_reward=c.get("shaped", True), goal=goal)
     else:
         env = rh.make_playground_env(c["n_obj"], goal=goal)
     if c["model"] == "gnn":
@@ -156,20 +156,24 @@ def gen_noise_case():
     return out
 
 
-def generate_all():
+def generate_all(only=None):
     res = {}
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         res[name] = gen_rollout_case(c) if c["kind"] == "rollout" else gen_mpc_case(c)
-    res["colored_noise"] = gen_noise_case()
+    if not only or "colored_noise" in only:
+        res["colored_noise"] = gen_noise_case()
     return res
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--only", nargs="*", default=None, help="fixture names to (re)generate; default: all")
     args = ap.parse_args()
     torch.set_num_threads(8)
-    data = generate_all()
+    data = generate_all(args.only)
     for name, arrays in data.items():
         path = os.path.join(HERE, name + ".npz")
         if args.check:

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert declared == set(ceeus_b200._lib.SIGNATURES), declared ^ set(ceeus_b200._lib.SIGNATURES)
     for name in declared:
         assert hasattr(built_lib, name), name
-    assert built_lib.ceeus_abi_version() == 1
+    assert built_lib.ceeus_abi_version() == ceeus_b200._lib.ABI_VERSION == 2
 
 
 def test_ctypes_structs_match_c_layout(built_lib):
@@ -97,7 +97,13 @@ def test_env_description_and_registry(built_lib):
     assert d["threshold"] == 0.02 and d["task_cost_supported"]
     d = ceeus_b200.describe_env(ceeus_b200.playground_env(4))
     assert (d["obs_dim"], d["state_dim"], d["goal_dim"], d["action_dim"]) == (48, 40, 8, 2)
-    assert not ceeus_b200.describe_env(ceeus_b200.construction_env(2, case="Flip"))["task_cost_supported"]
+    f = ceeus_b200.describe_env(ceeus_b200.construction_env(2, case="Flip"))  # fpp_construction_env.py:93-99
+    assert f["task_cost_supported"] and f["cost_case"] == ceeus_b200._lib.CASE_FLIP
+    assert f["coord_weights"].tolist() == [1.0, 0.0, 0.0] and np.allclose(f["cost_thres"], [0.087, 0, 0])
+    assert np.allclose(f["buffer_xyz"], 1e-4) and np.allclose(f["gripper_init"], [1.344, 0.749, 0.5319])
+    sl = ceeus_b200.describe_env(ceeus_b200.construction_env(3, case="Slide", shaped_reward=False))  # :100-105
+    assert sl["cost_case"] == ceeus_b200._lib.CASE_SLIDE and np.allclose(sl["buffer_xyz"], [0.1, 0.1, 0.42])
+    assert np.allclose(sl["cost_thres"], [0.1, 0.1, 0.42]) and sl["threshold"] == 0.1
     assert registry.controller_from_string("mpc-curiosity-icem-b200") is ceeus_b200.B200CuriosityMpcICem
     assert registry.forward_model_from_string("ParallelGNNDeterministicEnsembleB200") is ceeus_b200.B200GNNEnsemble
     with pytest.raises(ImportError):
