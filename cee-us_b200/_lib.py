@@ -11,7 +11,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_STATE = 0, -1, -2, -3
 MODEL_GNN, MODEL_MLP = 0, 1
 ACT = {"none": 0, None: 0, "relu": 1, "silu": 2, "swish": 2, "tanh": 3}
 PREC = {"fp32": 0, "tc": 1, "tf32": 1}
-ENV_NONE, ENV_CONSTRUCTION, ENV_PLAYGROUND = 0, 1, 2
+ENV_NONE, ENV_CONSTRUCTION, ENV_PLAYGROUND, ENV_EXTERNAL = 0, 1, 2, 3
 CASE_TOWER, CASE_PICKANDPLACE, CASE_FLIP, CASE_SLIDE = 0, 1, 2, 3
 COST = {"sum": 0, "best": 1}
 
@@ -61,6 +61,8 @@ SIGNATURES = {
                                C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "ceeus_begin_rollout": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ceeus_plan_iter_local": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ceeus_plan_iter_rollout": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ceeus_plan_iter_costs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ceeus_plan_iter_update": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ceeus_plan_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ceeus_plan_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -142,7 +142,7 @@ class B200MpcICem:
         e.set_goal(np.asarray(self.env.goal, np.float32))  # env.goal changes on every env.reset (obs_postproc)
         obs = np.asarray(obs, np.float32)
         single = obs.ndim == 1
-        if e.world_size == 1:
+        if e.world_size == 1 and not e.external_cost:
             action = e.plan_step(obs, noise)
         else:
             action = self._distributed_step(obs, noise)
@@ -171,7 +171,14 @@ class B200MpcICem:
                 if i == 0 and shifting:
                     ns = flat[off:off + per_shift]
                     off += per_shift
-            e.plan_iter_local(i, ni, ns)
+            if e.external_cost:
+                # the environment's own cost_fn on the materialised rollout (mpc_torch.py:121-125); everything else stays on
+                # the device path
+                e.plan_iter_rollout(i, ni, ns)
+                view = RolloutView.from_device_buffers(e.traj_, e.actions_)
+                e.plan_iter_costs(self.env.cost_fn(view["observations"], view["actions"], view["next_observations"]))
+            else:
+                e.plan_iter_local(i, ni, ns)
             e.plan_iter_update(i, gather_candidates(e.cand_).contiguous() if e.world_size > 1 else e.cand_)
         e.plan_finish()
         self._iterated = True

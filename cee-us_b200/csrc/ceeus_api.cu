@@ -168,6 +168,7 @@ int validate(const CeeusConfig& c, std::string& why) {
   if (c.precision != CEEUS_PREC_FP32 && c.precision != CEEUS_PREC_TC) return bad("precision");
   const bool need_env = !c.curiosity || c.extrinsic_reward;
   if (need_env && c.env_kind == CEEUS_ENV_NONE) return bad("task cost requested but env_kind is NONE");
+  if (c.env_kind < CEEUS_ENV_NONE || c.env_kind > CEEUS_ENV_EXTERNAL) return bad("env_kind");
   if (c.env_kind == CEEUS_ENV_CONSTRUCTION && (c.goal_dim != 3 * c.n_obj + 3 || c.dyn_dim < 3 || c.agent_dim < 3))
     return bad("construction layout: goal_dim must be 3N+3");
   if (c.env_kind == CEEUS_ENV_PLAYGROUND && (c.goal_dim != 2 * c.n_obj || c.dyn_dim < 2)) return bad("playground layout: goal_dim must be 2N");
@@ -425,8 +426,14 @@ int ceeus_rollout(CeeusHandle h, const float* start_obs_dev, int n_start, const 
   return do_rollout(h, start_obs_dev, n / n_start, actions_dev, n, n / h->cfg.num_envs, traj_dev, S(stream));
 }
 
-static int do_costs(CeeusHandle h, const float* traj_dev, int n, float* cpm, float* costs, cudaStream_t st) {
+static int do_costs(CeeusHandle h, const float* traj_dev, int n, float* cpm, float* costs, cudaStream_t st,
+                    const float* env_cost_ext = nullptr) {
+  const bool need_env = !h->cd.curiosity || h->cd.extrinsic;
+  if (need_env && h->cd.env_kind == CEEUS_ENV_EXTERNAL && env_cost_ext == nullptr)
+    return fail(h, CEEUS_ERR_STATE, "this environment's task cost is evaluated by the caller: use ceeus_plan_iter_rollout + "
+                                    "ceeus_plan_iter_costs(env_cost_dev)");
   CostArgs ca{};
+  ca.env_cost_ext = env_cost_ext;
   ca.traj = traj_dev; ca.cpm = cpm; ca.costs = costs; ca.n = n; ca.H = h->cfg.horizon; ca.E = h->md.E; ca.O = h->md.O;
   ca.N = h->md.N; ca.A = h->md.A; ca.D = h->md.D; ca.S = h->md.S; ca.G = h->md.G; ca.sd = h->md.sd;
   LAUNCH(h, launch_costs(ca, h->cd, st));
@@ -473,6 +480,12 @@ int ceeus_has_elites(CeeusHandle h) { return h && h->has_elites ? 1 : 0; }
 
 int ceeus_plan_iter_local(CeeusHandle h, int iter, const float* obs_dev, const float* noise_dev, const float* shift_noise_dev,
                           void* stream) {
+  if (int rc = ceeus_plan_iter_rollout(h, iter, obs_dev, noise_dev, shift_noise_dev, stream)) return rc;
+  return ceeus_plan_iter_costs(h, nullptr, stream);
+}
+
+int ceeus_plan_iter_rollout(CeeusHandle h, int iter, const float* obs_dev, const float* noise_dev, const float* shift_noise_dev,
+                            void* stream) {
   if (!h || !obs_dev) return fail(h, CEEUS_ERR_INVALID, "plan_iter_local: null argument");
   if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
   const CeeusConfig& c = h->cfg;
@@ -501,9 +514,17 @@ int ceeus_plan_iter_local(CeeusHandle h, int iter, const float* obs_dev, const f
     if (f.write_mean_row || f.shift_elites) LAUNCH(h, launch_fixup(f, st));
   }
   // 3. predict_n_steps
-  if (int rc = do_rollout(h, obs_dev, c.num_traj, h->bufs.actions, n, c.num_traj, h->bufs.traj, st)) return rc;
+  return do_rollout(h, obs_dev, c.num_traj, h->bufs.actions, n, c.num_traj, h->bufs.traj, st);
+}
+
+int ceeus_plan_iter_costs(CeeusHandle h, const float* env_cost_dev, void* stream) {
+  if (!h) return CEEUS_ERR_INVALID;
+  if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
+  const CeeusConfig& c = h->cfg;
+  cudaStream_t st = S(stream);
+  const int n = c.num_envs * c.num_traj;
   // 4. trajectory costs
-  if (int rc = do_costs(h, h->bufs.traj, n, h->bufs.costs_per_model, h->bufs.costs, st)) return rc;
+  if (int rc = do_costs(h, h->bufs.traj, n, h->bufs.costs_per_model, h->bufs.costs, st, env_cost_dev)) return rc;
   // 5. this rank's elite candidates
   TopkArgs t{};
   t.costs = h->bufs.costs; t.cpm = h->bufs.costs_per_model; t.actions = h->bufs.actions; t.cand = h->bufs.cand;

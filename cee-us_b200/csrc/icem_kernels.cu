@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) cost_kernel(const CostArgs a, const CostD
   const bool need_env = !cd.curiosity || cd.extrinsic;
 
   int kstar = 0;
-  if (need_env && cd.env_kind == CEEUS_ENV_CONSTRUCTION && cd.shaped && cd.cost_case != CEEUS_CASE_FLIP &&
+  if (need_env && a.env_cost_ext == nullptr && cd.env_kind == CEEUS_ENV_CONSTRUCTION && cd.shaped && cd.cost_case != CEEUS_CASE_FLIP &&
       cd.cost_case != CEEUS_CASE_SLIDE) {  // get_next_block_id, :365-383 (start obs)
     int unsolved = 0;
     for (int i = 0; i < a.N; ++i) unsolved += norm3(base + a.A + a.D * i, base + a.sd + 3 * i) > cd.threshold ? 1 : 0;
@@ -285,7 +285,9 @@ __global__ void __launch_bounds__(256) cost_kernel(const CostArgs a, const CostD
         float c = 0.f;
         if (lane < a.E) {
           float envc = 0.f;
-          if (need_env) envc = env_cost_row(nx + lane * es, a, cd, kstar);
+          if (need_env)
+            envc = a.env_cost_ext != nullptr ? __ldg(a.env_cost_ext + ((size_t)p * a.E + lane) * a.H + h)
+                                             : env_cost_row(nx + lane * es, a, cd, kstar);
           c = cd.curiosity ? (cd.extrinsic ? __fadd_rn(-bs, __fmul_rn(cd.extrinsic_scale, envc)) : -bs) : envc;
         }
         if (cd.cost_along == CEEUS_COST_BEST) {

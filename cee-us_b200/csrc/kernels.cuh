@@ -121,6 +121,7 @@ struct CostArgs {
   const float* traj;  // [H+1,E,n,O]
   float* cpm;         // [n,E]
   float* costs;       // [n]
+  const float* env_cost_ext;  // [n,E,H] task cost evaluated by the caller, or null (built-in env cost)
   int n, H, E, O, N, A, D, S, G, sd;
 };
 cudaError_t launch_costs(const CostArgs& a, const CostDesc& cd, cudaStream_t st);

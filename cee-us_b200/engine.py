@@ -57,8 +57,10 @@ class Engine:
             num_elites = 2
         num_kept = int(num_elites * float(sp["fraction_elites_reused"]))
         need_env = (not curiosity) or extrinsic_reward
-        if need_env and not d["task_cost_supported"]:
-            raise NotImplementedError(f"task cost for env kind={d['kind']} case={d['case']} is not implemented on device")
+        self.external_cost = bool(need_env and d["external_cost"])
+        if need_env and not d["task_cost_supported"] and not self.external_cost:
+            raise NotImplementedError(f"task cost for env kind={d['kind']} case={d['case']} is not built in and the "
+                                      "environment has no cost_fn to call")
         if need_env and d["case"] == "Slide" and d["shaped_reward"]:
             raise AssertionError("Shaped reward cannot be used with Slide!")  # as upstream, fpp_construction_env.py:455
         cfg = _lib.CeeusConfig()
@@ -223,6 +225,20 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ceeus_plan_iter_local(self.handle, it, _ptr(self.obs_dev_), _ptr(noise),
                                                       _ptr(shift_noise), _stream()), self.handle)
+
+    def plan_iter_rollout(self, it, noise=None, shift_noise=None):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ceeus_plan_iter_rollout(self.handle, it, _ptr(self.obs_dev_), _ptr(noise),
+                                                        _ptr(shift_noise), _stream()), self.handle)
+
+    def plan_iter_costs(self, env_cost=None):
+        """env_cost: [nE*P,E,H] float32 cuda tensor (env.cost_fn on the materialised trajectories) or None."""
+        if env_cost is not None:
+            env_cost = env_cost.to(self.device, torch.float32).contiguous()
+            if tuple(env_cost.shape) != (self.nE * self.P, self.E, self.H):
+                raise ValueError(f"env.cost_fn returned {tuple(env_cost.shape)}, expected {(self.nE * self.P, self.E, self.H)}")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ceeus_plan_iter_costs(self.handle, _ptr(env_cost), _stream()), self.handle)
 
     def plan_iter_update(self, it, cand_all):
         with torch.cuda.device(self.device):

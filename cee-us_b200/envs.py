@@ -89,6 +89,11 @@ def describe_env(env):
     case = getattr(env, "case", "")
     d["case"] = case
     d["task_cost_supported"] = kind in ("construction", "playground")
+    # any other environment: its own cost_fn is called on the materialised trajectories (SURVEY.md 8b "Env hand-off")
+    d["external_cost"] = (not d["task_cost_supported"] or bool(getattr(env, "force_external_cost", False))) and \
+        callable(getattr(env, "cost_fn", None))
+    if d["external_cost"]:
+        d["env_kind"] = _lib.ENV_EXTERNAL
     d["cost_case"] = (_lib.CASE_FLIP if case == "Flip" else _lib.CASE_SLIDE if case == "Slide" else
                       _lib.CASE_TOWER if ("tower" in case or case == "Pyramid") else _lib.CASE_PICKANDPLACE)
     d["sparse"] = int(bool(getattr(env, "sparse", False)))

@@ -21,6 +21,7 @@
  *                                                                                 mbrl/controllers/colored_noise.py:115-218
  *   ceeus_begin_rollout               beginning_of_rollout (reset mean/std/elites) mbrl/controllers/mpc_torch.py:159-202
  *   ceeus_plan_iter_local /           one iCEM iteration of get_action            mbrl/controllers/mpc_torch.py:300-359
+ *   ceeus_plan_iter_rollout / _costs  the same iteration split around env.cost_fn mbrl/controllers/mpc_torch.py:116-137
  *   ceeus_plan_iter_update            update_distributions (top-k, refit)         mbrl/controllers/mpc_torch.py:445-478
  *   ceeus_plan_finish                 action pick + shift-initialisation          mbrl/controllers/mpc_torch.py:383-421
  *   ceeus_plan_step                   TorchMpcICem.get_action (single GPU)        mbrl/controllers/mpc_torch.py:282-439
@@ -56,7 +57,9 @@ enum { CEEUS_ACT_NONE = 0, CEEUS_ACT_RELU = 1, CEEUS_ACT_SILU = 2, CEEUS_ACT_TAN
 /* arithmetic of the rollout GEMMs: fp32 FMA (parity 1e-5) or tcgen05 tensor cores with 10-bit-mantissa
  * operands and fp32 accumulation (parity 1e-3). */
 enum { CEEUS_PREC_FP32 = 0, CEEUS_PREC_TC = 1 };
-enum { CEEUS_ENV_NONE = 0, CEEUS_ENV_CONSTRUCTION = 1, CEEUS_ENV_PLAYGROUND = 2 };
+/* CEEUS_ENV_EXTERNAL: the task cost of this environment is not built in; the caller evaluates env.cost_fn on the
+ * materialised trajectories and hands the [nE*P,E,H] result to ceeus_plan_iter_costs (SURVEY.md 8b "Env hand-off") */
+enum { CEEUS_ENV_NONE = 0, CEEUS_ENV_CONSTRUCTION = 1, CEEUS_ENV_PLAYGROUND = 2, CEEUS_ENV_EXTERNAL = 3 };
 /* construction cost branches, fpp_construction_env.py:475-508 */
 enum {
   CEEUS_CASE_TOWER = 0 /* "*tower*" and "Pyramid" */,
@@ -188,6 +191,14 @@ int ceeus_begin_rollout(CeeusHandle h, void* stream);
  * (only read in iteration 0 when elites are shifted over time). */
 int ceeus_plan_iter_local(CeeusHandle h, int iter, const float* obs_dev, const float* noise_dev,
                           const float* shift_noise_dev, void* stream);
+/* The same iteration in two halves, for environments whose cost_fn runs in the caller (CEEUS_ENV_EXTERNAL):
+ * ceeus_plan_iter_rollout = sample (+ insertions) and predict_n_steps into bufs.traj (mpc_torch.py:301-317);
+ * ceeus_plan_iter_costs = trajectory_cost_fn + ensemble reduce + local top-k (mpc_torch.py:323-337, 445-460) with
+ * env_cost_dev [nE*P,E,H] = env.cost_fn(observations, actions, next_observations) evaluated by the caller on bufs.traj
+ * (NULL = the built-in cost of env_kind).  ceeus_plan_iter_local == rollout + costs(NULL). */
+int ceeus_plan_iter_rollout(CeeusHandle h, int iter, const float* obs_dev, const float* noise_dev,
+                            const float* shift_noise_dev, void* stream);
+int ceeus_plan_iter_costs(CeeusHandle h, const float* env_cost_dev, void* stream);
 /* Merge candidate records of all ranks (cand_all_dev [world,nE,k,rec]; world=1: pass bufs.cand) with the kept elites,
  * select the global top-k (ties: lower global index first), refit mean/std. Identical result on every rank. */
 int ceeus_plan_iter_update(CeeusHandle h, int iter, const float* cand_all_dev, void* stream);

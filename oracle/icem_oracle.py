@@ -395,18 +395,19 @@ def construction_cost(spec: EnvSpec, obs: torch.Tensor, next_obs: torch.Tensor) 
         # (:42-44), its position for Slide; parameters :93-105
         flip = spec.case == "Flip"
         ao = 3 if flip else 0
-        w = torch.tensor([1.0, 0.0, 0.0] if flip else [1.0, 1.0, 1.0])
-        buf = torch.tensor(1e-4) if flip else torch.tensor([0.1, 0.1, spec.height_offset])
-        thres = w * 0.087 if flip else torch.tensor([0.1, 0.1, spec.height_offset])
+        dev = next_obs.device
+        w = torch.tensor([1.0, 0.0, 0.0] if flip else [1.0, 1.0, 1.0], device=dev)
+        buf = torch.tensor(1e-4, device=dev) if flip else torch.tensor([0.1, 0.1, spec.height_offset], device=dev)
+        thres = w * 0.087 if flip else torch.tensor([0.1, 0.1, spec.height_offset], device=dev)
         goal = next_obs[..., sd:sd + 3 * N + 3]
         per = [torch.maximum(torch.abs(next_obs[..., A + D * i + ao:A + D * i + ao + 3] - goal[..., 3 * i:3 * i + 3]), buf) * w
                for i in range(N)]
         sparse_obj = torch.stack([torch.any(p > thres, dim=-1).float() for p in per])          # :429-432
         exp_dense = torch.stack([torch.mean(1.0 - torch.exp(-0.5 * p), dim=-1) for p in per])   # :323-338, :434-439
-        g = torch.zeros(next_obs.shape[:-1], dtype=torch.float32)
+        g = torch.zeros(next_obs.shape[:-1], dtype=torch.float32, device=dev)
         if spec.shaped_reward:
             assert not spec.case == "Slide", "Shaped reward cannot be used with Slide!"          # :455
-            g = torch.linalg.norm(next_obs[..., 0:3] - torch.tensor([1.344, 0.749, 0.5319]), dim=-1)  # :457-458, :119
+            g = torch.linalg.norm(next_obs[..., 0:3] - torch.tensor([1.344, 0.749, 0.5319], device=dev), dim=-1)  # :457-458, :119
         if spec.sparse:
             return sparse_obj.sum(dim=0) + g * 0.001                                              # :476-480
         return exp_dense.sum(dim=0) * 1e-3 + sparse_obj.sum(dim=0) + g * 0.01                     # :498-503
@@ -425,7 +426,7 @@ def construction_cost(spec: EnvSpec, obs: torch.Tensor, next_obs: torch.Tensor) 
     d = dists(ach, goal)  # [N,P,E,H]
     grip = ach[..., -3:]
     block_pos = torch.cat([ach[..., :-3], goal[..., -3:]], dim=-1)
-    g = torch.zeros(next_obs.shape[:-1], dtype=torch.float32)
+    g = torch.zeros(next_obs.shape[:-1], dtype=torch.float32, device=next_obs.device)
     if spec.shaped_reward:
         unsolved = (d > spec.threshold).float()
         start = obs[..., 0:1, :]
@@ -438,7 +439,7 @@ def construction_cost(spec: EnvSpec, obs: torch.Tensor, next_obs: torch.Tensor) 
         return (d > spec.threshold).float().sum(dim=0) + (g > spec.threshold).float() * 0.5
     if "tower" in spec.case or spec.case == "Pyramid":
         return (d > spec.threshold).float().sum(dim=0) + g * 0.01
-    return torch.maximum(d, torch.tensor(spec.buffer_threshold)).sum(dim=0) + g * 0.01
+    return torch.maximum(d, torch.tensor(spec.buffer_threshold, device=next_obs.device)).sum(dim=0) + g * 0.01
 
 
 def playground_cost(spec: EnvSpec, next_obs: torch.Tensor) -> torch.Tensor:

@@ -102,6 +102,41 @@ def test_mpc_steps_match_reference_fixture(name):
         np.testing.assert_allclose(ctrl.mean_.cpu().numpy(), g[f"s{s}_mean_after"], rtol=1e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("name", ["mpc_gnn_c2_task", "mpc_gnn_c6_stack_extr"])
+def test_mpc_steps_with_env_cost_fn_called_on_materialised_rollouts(name):
+    """An environment without a built-in device cost (SURVEY.md 8b "Env hand-off"): the controller materialises the rollout
+    views and calls env.cost_fn itself (mpc_torch.py:121-125); everything else stays on the device.  Same fixtures as the
+    built-in path: the result must not depend on where the task cost was evaluated."""
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    calls = []
+
+    def cost_fn(observations, actions, next_observations):
+        assert observations.is_cuda and tuple(observations.shape) == (c["P"], 5, c["H"], spec.obs_dim)
+        assert tuple(actions.shape) == (c["P"], 5, c["H"], spec.action_dim)
+        calls.append(1)
+        return orc.construction_cost(spec, observations, next_observations)  # torch ops on the CUDA views
+
+    env.cost_fn, env.force_external_cost = cost_fn, True
+    model = product_model(c, env, weights, norms)
+    ctrl = product_controller(c, env, model)
+    assert ctrl.engine.external_cost
+    noise = SeededNoise(c["nseed"], 3.5)
+    ctrl.beginning_of_rollout(observation=g["s0_obs"], state=None, mode="train")
+    e = ctrl.engine
+    for s in range(c["steps"]):
+        flat, _ = step_noise(noise, c, spec, e.has_elites(), e.n_kept, DEV)
+        a = ctrl.get_action(g[f"s{s}_obs"], None, noise=flat)
+        i = ctrl.opt_iter - 1
+        np.testing.assert_array_equal(e.elite_idx_[0].cpu().numpy(), g[f"s{s}_i{i}_elite_idx"])
+        assert rel_err(ctrl.costs_.cpu().numpy(), g[f"s{s}_i{i}_costs"][:c["P"]]) < 5e-5
+        np.testing.assert_allclose(a, g[f"s{s}_action"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ctrl.mean_.cpu().numpy(), g[f"s{s}_mean_after"], rtol=1e-5, atol=2e-6)
+    assert len(calls) == c["steps"] * ctrl.opt_iter
+
+
 def _where(got, want):
     """Failure message: where the two trajectories [H+1,E,P,O] differ most."""
     d = np.abs(got - want)
