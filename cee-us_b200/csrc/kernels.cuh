@@ -68,7 +68,7 @@ struct TcMlpLayout {
   int HD, L, K1, NOUT;      // hidden width, hidden layers, padded input K, padded output width
   TcMlpMat mat[kMaxLayers];
   int image_bytes, nrm_floats;
-  int sm_w, sm_nrm, sm_state, sm_snrm, sm_act, sm_bar, smem_bytes;
+  int sm_w, sm_nrm, sm_state, sm_snrm, sm_tab, sm_act, sm_bar, smem_bytes;
   int pairs;
 };
 bool make_mlp_tc_layout(const ModelDesc& md, int num_sms, TcMlpLayout* out);

@@ -21,6 +21,7 @@ namespace {
 using namespace tc;
 
 constexpr int kMlpThreads = 256;
+constexpr int kMaxOW = 64;  // output columns per thread (NOUT / 2; state dim <= 128)
 
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
@@ -47,6 +48,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1;
   const int U = md.U, sd = md.sd, O = md.O, in = sd + U, L = tl.L, K1 = tl.K1;
+  const int SNS = K1 + 8;  // snrm row stride in halves: 16 bytes of padding keep the per-row 16-byte accesses conflict free
 
   int e, lp, np;
   {
@@ -62,7 +64,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
   uint8_t* sW = smem + tl.sm_w;
   float* sNrm = reinterpret_cast<float*>(smem + tl.sm_nrm);
   float* s_state = reinterpret_cast<float*>(smem + tl.sm_state);  // [128][sd] raw fp32 state
-  __half* snrm = reinterpret_cast<__half*>(smem + tl.sm_snrm);    // [128][K1] normalised [state | action | 1 | 0..]
+  __half* snrm = reinterpret_cast<__half*>(smem + tl.sm_snrm);    // [128][SNS] normalised [state | action | 1 | 0..]
+  float4* s_tab = reinterpret_cast<float4*>(smem + tl.sm_tab);    // [NOUT] output-layer table (std_out, mean_out, mean_in, 1/std_in)
   float* s_act = reinterpret_cast<float*>(smem + tl.sm_act);      // [128][8] next step's raw action
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + tl.sm_bar);
   uint64_t* wbar = bars;
@@ -90,6 +93,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
     const float v = __ldg(ra.norm + i);
     sNrm[i] = (i >= md.nrm.in_all + in && i < md.nrm.out_all) ? 1.f / v : v;
   }
+  for (int d = tid; d < tl.NOUT; d += kMlpThreads)
+    s_tab[d] = d < sd ? make_float4(__ldg(ra.norm + md.nrm.out_all + sd + d), __ldg(ra.norm + md.nrm.out_all + d),
+                                    __ldg(ra.norm + md.nrm.in_all + d), 1.f / __ldg(ra.norm + md.nrm.in_all + in + d))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
   tc_fence_before();
   __syncthreads();
   Ctx cx;
@@ -145,7 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
     const bool live = row < Gc;
     cta_sync();
     // ---- tile init: start observation -> state, snrm, traj[0] ----
-    for (int idx = tid; idx < (128 * K1) / 8; idx += kMlpThreads) reinterpret_cast<uint4*>(snrm)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    for (int idx = tid; idx < (128 * SNS) / 8; idx += kMlpThreads) reinterpret_cast<uint4*>(snrm)[idx] = make_uint4(0u, 0u, 0u, 0u);
     for (int idx = tid; idx < Gc * O; idx += kMlpThreads) {
       const int b = idx / O, c = idx % O;
       const float v = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
@@ -156,9 +163,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
     for (int idx = tid; idx < Gc * in; idx += kMlpThreads) {
       const int b = idx / in, c = idx % in;
       const float x = c < sd ? s_state[b * sd + c] : __ldg(ra.actions + ((size_t)(p0 + b) * ra.H) * U + (c - sd));
-      snrm[b * K1 + c] = __float2half_rn((x - nrm[md.nrm.in_all + c]) * nrm[md.nrm.in_all + in + c]);
+      snrm[b * SNS + c] = __float2half_rn((x - nrm[md.nrm.in_all + c]) * nrm[md.nrm.in_all + in + c]);
     }
-    if (tid < 128 && live) snrm[tid * K1 + in] = __float2half_rn(1.f);
+    if (tid < 128 && live) snrm[tid * SNS + in] = __float2half_rn(1.f);
+    // the goal part of every predicted observation (env.obs_postproc) is constant along the horizon: written here, once
+    for (int idx = tid; idx < Gc * md.G; idx += kMlpThreads) {
+      const int b = idx / md.G, c = idx % md.G;
+      const float gv = __ldg(ra.goal + (size_t)((p0 + b) / ra.traj_per_goal) * md.G + c);
+      for (int hh = 1; hh <= ra.H; ++hh) ra.traj[(((size_t)hh * md.E + e) * ra.n + p0 + b) * O + sd + c] = gv;
+    }
+    // this thread's half of the raw state lives in registers for the whole horizon
+    float st[kMaxOW];
+#pragma unroll
+    for (int c = 0; c < kMaxOW; ++c) {
+      const int d = hf * (tl.NOUT / 2) + c;
+      st[c] = (live && c < tl.NOUT / 2 && d < sd) ? s_state[row * sd + d] : 0.f;
+    }
     cta_sync();
 
     for (int h = 0; h < ra.H; ++h) {
@@ -170,7 +190,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
       }
       // A operand of layer 0: this row's normalised input, the two halves write alternate 16-byte chunks
       {
-        const uint4* sb = reinterpret_cast<const uint4*>(snrm + row * K1);
+        const uint4* sb = reinterpret_cast<const uint4*>(snrm + row * SNS);
         for (int c = hf; c < K1 / 8; c += 2) tmem_st4(t_a + 4 * c, sb[c]);
       }
       signal_a(cx, 0, lane);
@@ -203,33 +223,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
           // ---------------- output layer: delta -> de-normalise, residual update (mlp_ensemble.py:530-573) ----------------
           const int OW = tl.NOUT / 2;  // output columns per thread
           if (warp_on) {
-            for (int c0 = 0; c0 < OW; c0 += 16) {
-              uint32_t v[16];
-              tmem_ld16(t_acc + hf * OW + c0, v);
-              tmem_wait_ld();
-              if (live) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int d = hf * OW + c0 + j;
-                  if (d < sd) {
-                    const float nv = s_state[row * sd + d] + fmaf(nrm[md.nrm.out_all + sd + d], __uint_as_float(v[j]), nrm[md.nrm.out_all + d]);
-                    s_state[row * sd + d] = nv;
-                    outp[(size_t)row * O + d] = nv;
-                    snrm[row * K1 + d] = __float2half_rn((nv - nrm[md.nrm.in_all + d]) * nrm[md.nrm.in_all + in + d]);
+            for (int cc = 0; cc < kMaxOW / 16; ++cc) {
+              const int c0 = 16 * cc;
+              if (c0 < OW) {
+                uint32_t v[16];
+                tmem_ld16(t_acc + hf * OW + c0, v);
+                tmem_wait_ld();
+                if (live) {
+                  const int d0 = hf * OW + c0;
+                  uint32_t pk[8];
+#pragma unroll
+                  for (int j = 0; j < 16; j += 2) {
+                    // padded columns (d >= sd) have an all-zero table entry: state and normalised copy stay exactly 0
+                    const float4 ta = s_tab[d0 + j], tb = s_tab[d0 + j + 1];
+                    const float na = st[c0 + j] + fmaf(ta.x, __uint_as_float(v[j]), ta.y);
+                    const float nb = st[c0 + j + 1] + fmaf(tb.x, __uint_as_float(v[j + 1]), tb.y);
+                    st[c0 + j] = na; st[c0 + j + 1] = nb;
+                    if (d0 + j < sd) outp[(size_t)row * O + d0 + j] = na;
+                    if (d0 + j + 1 < sd) outp[(size_t)row * O + d0 + j + 1] = nb;
+                    pk[j / 2] = pack_half2((na - ta.z) * ta.w, (nb - tb.z) * tb.w);
+                  }
+                  __half* dst = snrm + row * SNS + d0;
+                  if (d0 + 16 <= sd) {
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                  } else {  // the chunk that runs into the action / constant-one columns: element-wise
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                      if (d0 + j < sd) dst[j] = reinterpret_cast<const __half*>(pk)[j];
                   }
                 }
               }
             }
           }
-          if (hf == 1 && live) {
-            if (h + 1 < ra.H) {
-              asm volatile("cp.async.wait_all;" ::: "memory");
-              for (int j = 0; j < U; ++j)
-                snrm[row * K1 + sd + j] = __float2half_rn((s_act[row * 8 + j] - nrm[md.nrm.in_all + sd + j]) * nrm[md.nrm.in_all + in + sd + j]);
-            }
-            // goal part of the observation (env.obs_postproc)
-            const float* g = ra.goal + (size_t)((p0 + row) / ra.traj_per_goal) * md.G;
-            for (int c = 0; c < md.G; ++c) outp[(size_t)row * O + sd + c] = __ldg(g + c);
+          if (hf == 1 && live && h + 1 < ra.H) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            for (int j = 0; j < U; ++j)
+              snrm[row * SNS + sd + j] = __float2half_rn((s_act[row * 8 + j] - nrm[md.nrm.in_all + sd + j]) * nrm[md.nrm.in_all + in + sd + j]);
           }
           tc_fence_before();
         }
@@ -305,7 +336,8 @@ bool make_mlp_tc_layout(const ModelDesc& md, int num_sms, TcMlpLayout* out) {
   t.sm_w = sm; sm += round_up(t.image_bytes, 1024);
   t.sm_nrm = sm; sm += round_up(t.nrm_floats * 4, 16);
   t.sm_state = sm; sm += round_up(128 * md.sd * 4, 16);
-  t.sm_snrm = sm; sm += 128 * t.K1 * 2;
+  t.sm_snrm = sm; sm += 128 * (t.K1 + 8) * 2;
+  t.sm_tab = sm; sm += t.NOUT * 16;
   t.sm_act = sm; sm += 128 * 8 * 4;
   t.sm_bar = sm; sm += 64;
   t.smem_bytes = sm;
