@@ -116,7 +116,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
   const uint32_t t_acc = lane_base, t_a = lane_base + HD, t_one = lane_base + HD + HD / 2;
   const float* __restrict__ nrm = sNrm;
   const int act = md.act;
-  const bool issuer_warp = rank == 0 && warp == 0;
+  const bool issuer_warp = rank == 0 && warp == 3;  // the warp of the last rows: idle (no epilogue of its own) whenever the tile is not full
   uint32_t aph = 0, dph = 0;
   const uint32_t wbase = smem_u32(sW);
   auto mma_layer = [&](int m) {
