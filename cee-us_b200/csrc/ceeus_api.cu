@@ -152,7 +152,8 @@ int validate(const CeeusConfig& c, std::string& why) {
   if (c.model_kind == CEEUS_MODEL_GNN) {
     if (c.hidden_dim == 256) return bad("GNN hidden_dim must be 64 or 128");
     if (c.n_obj < 2) return bad("GNN needs n_obj >= 2 (gnn_modules.py:190-241: row undefined for one node)");
-    if (c.n_obj * (c.n_obj - 1) > kTileRows) return bad("n_obj too large: N(N-1) must be <= 64");
+    // the fp32 path tiles whole trajectories' edges into 64 rows; the tensor-core path (node-major rows) takes N <= 32
+    if (c.precision == CEEUS_PREC_FP32 && c.n_obj * (c.n_obj - 1) > kTileRows) return bad("n_obj too large for fp32 mode: N(N-1) must be <= 64");
     if (c.dyn_dim > 64 || c.agent_dim > 64) return bad("dyn_dim / agent_dim must be <= 64");
     if (c.agent_dim < 1) return bad("agent_dim must be >= 1 (agent_as_global_node)");
   } else {
@@ -222,7 +223,7 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
     md.nrm.out_dyn = o; o += 2 * md.D;
     h->norm_floats = o;
     const GnnTiling tl = make_gnn_tiling(md);
-    if (tl.G < 1 || tl.smem_bytes > 227 * 1024) {
+    if (c.precision == CEEUS_PREC_FP32 && (tl.G < 1 || tl.smem_bytes > 227 * 1024)) {
       delete h;
       return fail(nullptr, CEEUS_ERR_INVALID, "GNN tiling does not fit shared memory");
     }
