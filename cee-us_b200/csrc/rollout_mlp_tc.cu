@@ -121,7 +121,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
   const uint32_t wbase = smem_u32(sW);
   auto mma_layer = [&](int m) {
     if (!issuer_warp) return;
-    const bool ok = wait_bar(cx, a_ready, aph, 2);
+    const bool ok = wait_bar_spin(cx, a_ready, aph, 2);
     aph ^= 1u;
     tc_fence_after();
     if (ok) {

@@ -133,7 +133,7 @@ __device__ __forceinline__ void tc_issue_stage(volatile int* abort_flag, int* er
                                             uint32_t wdesc_addr, uint32_t m_acc, int n2) {
   Ctx cx;
   cx.abort = abort_flag; cx.err = err;
-  const bool ok = wait_bar(cx, a_bar, aph, 2);
+  const bool ok = wait_bar_spin(cx, a_bar, aph, 2);
   tc_fence_after();
   if (ok) {  // warp-converged: one elected lane issues, operands stay warp uniform
     const uint32_t elected = elect_one();

@@ -34,6 +34,17 @@ __device__ __forceinline__ bool wait_bar(const Ctx& cx, uint64_t* bar, uint32_t 
   return false;
 }
 
+// Spinning variant for the MMA-issuing warp (reacts within a few cycles of the last arrival).
+__device__ __forceinline__ bool wait_bar_spin(const Ctx& cx, uint64_t* bar, uint32_t parity, int code) {
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
+    if (mbar_test_wait(bar, parity)) return true;
+    if ((it & 4095u) == 4095u && *cx.abort) return false;
+  }
+  *cx.abort = 1;
+  atomicExch(cx.err, code);
+  return false;
+}
+
 // The A operand of this warpgroup's next MMA stage is complete in TMEM: retire the tcgen05.st, order them (and the
 // earlier tcgen05.ld of the accumulator) before the barrier, one arrival per warp on the leader's barrier.
 __device__ __forceinline__ void signal_a(const Ctx& cx, int s, int lane) {
