@@ -224,6 +224,8 @@ __device__ float env_cost_row(const float* __restrict__ row, const CostArgs& a, 
 // trajectory_cost_fn (mpc_torch.py:116-137, mpc_torch_curiosity.py:45-80) + ensemble mean / std (:327-332).
 // One warp per trajectory: lanes stride over the observation dims for the disagreement term, lane e evaluates the
 // task cost of member e.
+// EM: compile-time bound of the member loops (the reference's ensemble size 5 gets its own instantiation: no dead registers)
+template <int EM>
 __global__ void __launch_bounds__(256) cost_kernel(const CostArgs a, const CostDesc cd) {
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -250,28 +252,38 @@ __global__ void __launch_bounds__(256) cost_kernel(const CostArgs a, const CostD
 #pragma unroll
     for (int hb = 0; hb < HB; ++hb) bonus[hb] = 0.f;
     if (cd.curiosity) {
-      for (int d = lane; d < a.O; d += 32) {
-        float x[HB][kMaxEnsemble];
+      // two 32-feature column blocks per pass: 2 x HB x E independent loads in flight per lane
+      for (int d = lane; d < a.O; d += 64) {
+        float x[2][HB][EM];
+        const bool second = d + 32 < a.O;
 #pragma unroll
         for (int hb = 0; hb < HB; ++hb)
 #pragma unroll
-          for (int e = 0; e < kMaxEnsemble; ++e)
-            if (e < a.E && h0 + hb < a.H) x[hb][e] = __ldg(base + (size_t)(h0 + hb + 1) * hs + e * es + d);
+          for (int e = 0; e < EM; ++e)
+            if (e < a.E && h0 + hb < a.H) {
+              const float* src = base + (size_t)(h0 + hb + 1) * hs + e * es + d;
+              x[0][hb][e] = __ldg(src);
+              x[1][hb][e] = second ? __ldg(src + 32) : 0.f;
+            }
 #pragma unroll
-        for (int hb = 0; hb < HB; ++hb) {
-          if (h0 + hb < a.H) {
-            // Welford, as torch.std does (exactly 0 for dims identical across members, e.g. the goal)
-            float mean = 0.f, m2 = 0.f;
+        for (int c = 0; c < 2; ++c) {
+          if (c == 1 && !second) continue;
 #pragma unroll
-            for (int e = 0; e < kMaxEnsemble; ++e)
-              if (e < a.E) {
-                // 1/(e+1) as a compile-time constant multiply: <= 1 ulp from torch's division, and still exactly 0 for
-                // identical members; the IEEE divisions made this kernel instruction-bound (126 us for 105 MB)
-                const float dl = x[hb][e] - mean;
-                mean = fmaf(dl, 1.f / (float)(e + 1), mean);
-                m2 = fmaf(dl, x[hb][e] - mean, m2);
-              }
-            bonus[hb] += sqrtf(m2 * inv_em1);
+          for (int hb = 0; hb < HB; ++hb) {
+            if (h0 + hb < a.H) {
+              // Welford, as torch.std does (exactly 0 for dims identical across members, e.g. the goal)
+              float mean = 0.f, m2 = 0.f;
+#pragma unroll
+              for (int e = 0; e < EM; ++e)
+                if (e < a.E) {
+                  // 1/(e+1) as a compile-time constant multiply: <= 1 ulp from torch's division, and still exactly 0 for
+                  // identical members; the IEEE divisions made this kernel instruction-bound (126 us for 105 MB)
+                  const float dl = x[c][hb][e] - mean;
+                  mean = fmaf(dl, 1.f / (float)(e + 1), mean);
+                  m2 = fmaf(dl, x[c][hb][e] - mean, m2);
+                }
+              bonus[hb] += sqrtf(m2 * inv_em1);
+            }
           }
         }
       }
@@ -536,7 +548,8 @@ cudaError_t launch_fixup(const FixupArgs& a, cudaStream_t st) {
 cudaError_t launch_costs(const CostArgs& a, const CostDesc& cd, cudaStream_t st) {
   if (a.n == 0) return cudaSuccess;
   const int wpb = 8;
-  cost_kernel<<<(a.n + wpb - 1) / wpb, wpb * 32, 0, st>>>(a, cd);
+  if (a.E <= 5) cost_kernel<5><<<(a.n + wpb - 1) / wpb, wpb * 32, 0, st>>>(a, cd);
+  else cost_kernel<kMaxEnsemble><<<(a.n + wpb - 1) / wpb, wpb * 32, 0, st>>>(a, cd);
   return cudaGetLastError();
 }
 
