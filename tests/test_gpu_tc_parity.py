@@ -53,7 +53,8 @@ def test_tc_rollout_matches_reference_fixture(name):
     ("construction", 2, 128, 300, 30), ("construction", 2, 128, 41, 3), ("construction", 4, 128, 130, 7),
     ("construction", 6, 128, 77, 30), ("construction", 3, 64, 64, 5), ("construction", 5, 128, 19, 4),
     ("playground", 4, 64, 200, 30), ("playground", 2, 128, 33, 4), ("construction", 2, 128, 3000, 10),
-    ("construction", 8, 128, 50, 3), ("construction", 12, 128, 9, 2), ("playground", 7, 64, 70, 4)])
+    ("construction", 8, 128, 50, 3), ("construction", 12, 128, 9, 2), ("playground", 7, 64, 70, 4),
+    ("construction", 2, 128, 40, 1), ("construction", 6, 128, 5, 1), ("playground", 4, 64, 2, 1)])
 def test_tc_rollout_matches_oracle_fresh_inputs(env_kind, n_obj, hidden, P, H):
     """Ragged populations (partial groups, empty lock-step groups), every N / hidden width, per-trajectory start states."""
     c = dict(kind="rollout", env=env_kind, n_obj=n_obj, model="gnn", hidden=hidden, layers=2, P=P, H=H,
