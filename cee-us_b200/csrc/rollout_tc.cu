@@ -192,6 +192,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
   const int per_worker = (ra.n + 2 * NS * np - 1) / (2 * NS * np);
   const int rounds = (per_worker + tl.Tmax - 1) / tl.Tmax;
   const int T = (per_worker + rounds - 1) / rounds;  // trajectories per group, <= Tmax
+  // Uneven split: the MMA-issuing warp is the last-filled warp of the leader CTA's slots.  Where the even split would keep it busy
+  // and the same number of rounds also fits with that warp left empty (leader slots 3 warps' worth of trajectories, the other
+  // CTA's slots 4), the issuer stays a pure issuer that reacts at once.  q = trajectories per warp and round.
+  const int q_un = (ra.n + np * NS * 7 * rounds - 1) / (np * NS * 7 * rounds);
+  const bool uneven = T > 3 * tl.tpw && q_un <= tl.tpw;
   const int n_stage = 2 * (N - 1) + 6;
 
   uint8_t* sW = smem + tl.sm_w;
@@ -330,9 +335,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     for (int j = 0; j < 16; ++j) { dyn[j] = 0.f; agent[j] = 0.f; }  // padded entries take part in the vectorised output update
 
     for (int rd = 0; rd < rounds; ++rd) {
-      const int w_lo = min(ra.n, worker * per_worker), w_hi = min(ra.n, w_lo + per_worker);
-      const int p0 = w_lo + rd * T;
-      int Gc = max(0, min(T, w_hi - p0));  // live trajectories of this group (0: pure lock-step filler)
+      int w_lo, w_hi, Tw;
+      if (uneven) {
+        const int units = rank == 0 ? 3 : 4;  // warps' worth of trajectories of this worker
+        const int u_off = lp * NS * 7 + (rank == 0 ? 3 * s : 3 * NS + 4 * s);
+        Tw = units * q_un;
+        w_lo = min(ra.n, u_off * q_un * rounds);
+        w_hi = min(ra.n, w_lo + Tw * rounds);
+      } else {
+        Tw = T;
+        w_lo = min(ra.n, worker * per_worker);
+        w_hi = min(ra.n, w_lo + per_worker);
+      }
+      const int p0 = w_lo + rd * Tw;
+      int Gc = max(0, min(Tw, w_hi - p0));  // live trajectories of this group (0: pure lock-step filler)
       if (DBG && dbg != nullptr && dbg[499] == 1 && s == 1) Gc = 0;  // profiling aid: slot 1 idles, slot 0 runs without SIMT contention
       const bool live = lane_ok && b < Gc;
       const bool live_g = live && ni == 0;
