@@ -279,8 +279,8 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
     if (c.model_kind != CEEUS_MODEL_GNN || !make_tc_layout(md, h->num_sms, &h->tc, kmap.data())) {
       ceeus_destroy(h);
       return fail(nullptr, CEEUS_ERR_INVALID,
-                  "CEEUS_PREC_TC supports the GNN ensemble with hidden_dim 64/128, 2 hidden layers, dyn/agent dim <= 16, "
-                  "action dim <= 8 and a trajectory group that fits shared memory");
+                  "CEEUS_PREC_TC supports the GNN ensemble with hidden_dim 64/128, 2 hidden layers, n_obj <= 32, "
+                  "agent_dim + action_dim <= 15, dyn_dim + stat_dim <= 16 and a trajectory group that fits shared memory");
     }
     e = cudaMalloc(&h->d_wimg, (size_t)md.E * 2 * h->tc.image_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_wpar, (size_t)md.E * h->tc.par_floats * sizeof(float));
