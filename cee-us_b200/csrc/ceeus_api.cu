@@ -428,13 +428,15 @@ int ceeus_rollout(CeeusHandle h, const float* start_obs_dev, int n_start, const 
 }
 
 static int do_costs(CeeusHandle h, const float* traj_dev, int n, float* cpm, float* costs, cudaStream_t st,
-                    const float* env_cost_ext = nullptr) {
+                    const float* env_cost_ext = nullptr, bool own_rollout = false) {
   const bool need_env = !h->cd.curiosity || h->cd.extrinsic;
   if (need_env && h->cd.env_kind == CEEUS_ENV_EXTERNAL && env_cost_ext == nullptr)
     return fail(h, CEEUS_ERR_STATE, "this environment's task cost is evaluated by the caller: use ceeus_plan_iter_rollout + "
                                     "ceeus_plan_iter_costs(env_cost_dev)");
   CostArgs ca{};
   ca.env_cost_ext = env_cost_ext;
+  // GNN: static features and goal are copied into every member's prediction; dense MLP: it predicts the whole state, only the goal is copied
+  ca.Ostd = !own_rollout ? h->md.O : h->md.kind == CEEUS_MODEL_GNN ? h->md.A + h->md.N * h->md.D : h->md.sd;
   ca.traj = traj_dev; ca.cpm = cpm; ca.costs = costs; ca.n = n; ca.H = h->cfg.horizon; ca.E = h->md.E; ca.O = h->md.O;
   ca.N = h->md.N; ca.A = h->md.A; ca.D = h->md.D; ca.S = h->md.S; ca.G = h->md.G; ca.sd = h->md.sd;
   LAUNCH(h, launch_costs(ca, h->cd, st));
@@ -525,7 +527,7 @@ int ceeus_plan_iter_costs(CeeusHandle h, const float* env_cost_dev, void* stream
   cudaStream_t st = S(stream);
   const int n = c.num_envs * c.num_traj;
   // 4. trajectory costs
-  if (int rc = do_costs(h, h->bufs.traj, n, h->bufs.costs_per_model, h->bufs.costs, st, env_cost_dev)) return rc;
+  if (int rc = do_costs(h, h->bufs.traj, n, h->bufs.costs_per_model, h->bufs.costs, st, env_cost_dev, true)) return rc;
   // 5. this rank's elite candidates
   TopkArgs t{};
   t.costs = h->bufs.costs; t.cpm = h->bufs.costs_per_model; t.actions = h->bufs.actions; t.cand = h->bufs.cand;

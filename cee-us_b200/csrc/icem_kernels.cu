@@ -253,9 +253,10 @@ __global__ void __launch_bounds__(256) cost_kernel(const CostArgs a, const CostD
     for (int hb = 0; hb < HB; ++hb) bonus[hb] = 0.f;
     if (cd.curiosity) {
       // two 32-feature column blocks per pass: 2 x HB x E independent loads in flight per lane
-      for (int d = lane; d < a.O; d += 64) {
+      // (dims >= Ostd are known to be identical across the members -- see CostArgs::Ostd -- their std is exactly 0)
+      for (int d = lane; d < a.Ostd; d += 64) {
         float x[2][HB][EM];
-        const bool second = d + 32 < a.O;
+        const bool second = d + 32 < a.Ostd;
 #pragma unroll
         for (int hb = 0; hb < HB; ++hb)
 #pragma unroll

@@ -123,6 +123,9 @@ struct CostArgs {
   float* costs;       // [n]
   const float* env_cost_ext;  // [n,E,H] task cost evaluated by the caller, or null (built-in env cost)
   int n, H, E, O, N, A, D, S, G, sd;
+  int Ostd;  // observation dims that enter the ensemble std: O for caller-supplied trajectories; for the planner's own rollouts
+             // only the predicted dims (GNN: A + N*D, dense MLP: sd) -- the rest is copied identically into every member, its
+             // std is exactly 0 either way
 };
 cudaError_t launch_costs(const CostArgs& a, const CostDesc& cd, cudaStream_t st);
 

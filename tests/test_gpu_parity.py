@@ -170,10 +170,11 @@ def test_rollout_matches_oracle_fresh_inputs(env_kind, n_obj, model, hidden, P, 
     got = pm._rollout_engine(P, H).traj_.cpu().numpy()
     assert got.shape == want.shape
     if not rel_err(got, want) < TOL_FP32:
-        # Seen about once in 40 fresh processes (most often the first process on a fresh box), never in 400 in-process
-        # repetitions nor in 45 stand-alone processes (tests/flake_diag*.py): a handful of trajectories off by ~1e-4.
-        # Recompute both sides once and record which side moved, so that the cause can be pinned down; a difference that
-        # persists is a failure.
+        # The torch-CPU ORACLE is not run-to-run reproducible at this tolerance: in about 1 of 30 fresh processes its first
+        # evaluation comes out 2e-5 .. 5e-5 (rel_err) away from every later evaluation of the same inputs (digests recorded
+        # over 80 processes on a B200 box: the oracle's first result took one of two alternative values, its recomputation
+        # and all other processes the usual one; the CUDA result was bit-identical in all 80).  So: recompute the oracle once
+        # and record the event; a mismatch that persists is a failure of the product.
         import hashlib
         import warnings
         md5 = lambda a: hashlib.md5(np.ascontiguousarray(a).tobytes()).hexdigest()[:10]
@@ -184,7 +185,8 @@ def test_rollout_matches_oracle_fresh_inputs(env_kind, n_obj, model, hidden, P, 
         got2 = pm._rollout_engine(P, H).traj_.cpu().numpy()
         warnings.warn(f"transient fp32 rollout mismatch: {first}; digests want {md5(want)} -> {md5(want2)}, "
                       f"got {md5(got)} -> {md5(got2)}")
-        got, want = got2, want2
+        np.testing.assert_array_equal(got2, got)  # the product is deterministic
+        want = want2
     assert rel_err(got, want) < TOL_FP32, _where(got, want)
 
 
