@@ -52,7 +52,7 @@ struct TcLayout {
   int kmap_len;
   int NS;                  // warpgroups (slots) per CTA: 2 at Hd = 128, 4 at Hd = 64
   int sm_w, sm_par, sm_nrm, sm_out, nrm_floats, sm_slot[4], sm_bar, smem_bytes;
-  int so_obs, obs_bytes, so_glob, so_snrm, so_tail;  // offsets inside a slot region; bytes of one warp's observation staging
+  int so_obs, obs_bytes, so_glob, so_snrm, so_tail, so_actn;  // offsets inside a slot region; bytes of one warp's observation staging
   int pairs;               // CTA pairs in the grid
   int scratch_floats;      // per member: logical fp32 matrices built by the pack kernels
 };
