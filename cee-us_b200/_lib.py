@@ -10,7 +10,9 @@ ABI_VERSION = 2
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE = 0, -1, -2, -3
 MODEL_GNN, MODEL_MLP = 0, 1
 ACT = {"none": 0, None: 0, "relu": 1, "silu": 2, "swish": 2, "tanh": 3}
-PREC = {"fp32": 0, "tc": 1, "tf32": 1}
+# "tc" = tcgen05 tensor cores with fp16 operands (10-bit mantissa, the TF32 mantissa width) and fp32 accumulation; it is NOT
+# TF32 (5-bit exponent: the kernels saturate and raise a range flag, ceeus_tc_status), so no "tf32" alias is offered.
+PREC = {"fp32": 0, "tc": 1, "fp16": 1}
 ENV_NONE, ENV_CONSTRUCTION, ENV_PLAYGROUND, ENV_EXTERNAL = 0, 1, 2, 3
 CASE_TOWER, CASE_PICKANDPLACE, CASE_FLIP, CASE_SLIDE = 0, 1, 2, 3
 COST = {"sum": 0, "best": 1}
@@ -69,6 +71,7 @@ SIGNATURES = {
     "ceeus_kernel_launches": (C.c_int64, [C.c_void_p]),
     "ceeus_has_elites": (C.c_int, [C.c_void_p]),
     "ceeus_tc_status": (C.c_int, [C.c_void_p]),
+    "ceeus_tc_tiling": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ceeus_selftest_epilogue": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ceeus_tc_debug_flag": (C.c_int, [C.c_void_p, C.c_longlong]),
     "ceeus_tc_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),

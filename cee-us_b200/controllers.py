@@ -53,6 +53,8 @@ class B200MpcICem:
         self.forward_model.horizon = self.horizon
         self.forward_model.preallocate_memory()
         self._engine = None
+        self._last_obs = None
+        self._iterated = False
         self.preallocate_memory()
 
     # -- engine -------------------------------------------------------------------------------------------------
@@ -95,12 +97,14 @@ class B200MpcICem:
             return None
         acts = e.elite_actions_[0]
         model = self.forward_model
+        last_obs = self._last_obs  # the observation the elites were planned from (the library keeps its own device copy)
 
         class _Lazy(RolloutView):
             def _materialise(inner):
                 if "observations" not in inner.buffer:
                     eng = model._rollout_engine(acts.shape[0], e.H)
-                    traj = eng.rollout(e.obs_dev_[:1].contiguous(), acts.contiguous())
+                    start = torch.from_numpy(np.ascontiguousarray(last_obs.reshape(-1, e.O)[:1])).to(e.device)
+                    traj = eng.rollout(start, acts.contiguous())
                     full = RolloutView.from_device_buffers(traj.clone(), acts)
                     inner.buffer.update(full.buffer)
 
@@ -123,6 +127,7 @@ class B200MpcICem:
         self._engine.begin_rollout()
         self.was_reset = True
         self._iterated = False
+        self._last_obs = np.asarray(observation, np.float32).copy()
 
     def end_of_rollout(self, total_time=None, total_return=None, mode="train"):
         pass
@@ -142,6 +147,7 @@ class B200MpcICem:
         e.set_goal(np.asarray(self.env.goal, np.float32))  # env.goal changes on every env.reset (obs_postproc)
         obs = np.asarray(obs, np.float32)
         single = obs.ndim == 1
+        self._last_obs = obs.copy()
         if e.world_size == 1 and not e.external_cost:
             action = e.plan_step(obs, noise)
         else:

@@ -161,6 +161,8 @@ int validate(const CeeusConfig& c, std::string& why) {
     if (round_up(sd, 64) > c.hidden_dim || sd > 128) return bad("MLP state dim too large for this build");
   }
   if (c.num_envs < 1 || c.num_traj < 2 || c.horizon < 1 || c.horizon > 256) return bad("num_envs/num_traj/horizon");
+  if (sample_smem_bytes(c.horizon, c.colored_noise) > 227 * 1024)
+    return bad("horizon too long for the colored-noise sampler (the [2F x H] irDFT matrix must fit shared memory: H <= 224)");
   if (c.opt_iterations < 1) return bad("opt_iterations");
   if (c.num_elites < 1 || c.num_elites > 64 || c.num_elites > c.num_traj) return bad("num_elites must be in [1,64] and <= num_traj");
   if (c.num_kept < 0 || c.num_kept > c.num_elites) return bad("num_kept");
@@ -343,6 +345,8 @@ int ceeus_weight_tensor_shape(CeeusHandle h, int i, int32_t* rows, int32_t* cols
 int ceeus_set_weights(CeeusHandle h, const float* const* dev_ptrs, int n, void* stream) {
   if (!h || !dev_ptrs) return fail(h, CEEUS_ERR_INVALID, "set_weights: null argument");
   if (n != (int)h->wspec.size()) return fail(h, CEEUS_ERR_INVALID, "set_weights: expected " + std::to_string(h->wspec.size()) + " tensors");
+  // the captured plan-step graphs hold the rollout kernel VARIANT chosen from tc_all_fold (recomputed below): re-capture
+  drop_graphs(h);
   for (int i = 0; i < n; ++i) {
     if (!dev_ptrs[i]) return fail(h, CEEUS_ERR_INVALID, "set_weights: null tensor pointer");
     const TensorSpec& t = h->wspec[i];
@@ -638,6 +642,7 @@ int64_t ceeus_kernel_launches(CeeusHandle h) { return h ? h->launches : 0; }
 
 int ceeus_tc_debug_timeline(CeeusHandle h, int enable, long long* out_host, int n_pairs) {
   if (!h || h->cfg.precision != CEEUS_PREC_TC) return CEEUS_ERR_INVALID;
+  drop_graphs(h);  // captured launches hold the kernel variant and the d_tc_dbg pointer
   if (enable && !h->d_tc_dbg) {
     if (cudaMalloc(&h->d_tc_dbg, 512 * sizeof(long long)) != cudaSuccess) return CEEUS_ERR_CUDA;
     cudaMemset(h->d_tc_dbg, 0, 512 * sizeof(long long));
@@ -669,6 +674,25 @@ int ceeus_selftest_epilogue(int warps_per_scheduler, int with_bias, int with_mma
 int ceeus_tc_debug_flag(CeeusHandle h, long long flag) {
   if (!h || !h->d_tc_dbg) return CEEUS_ERR_INVALID;
   return cudaMemcpy(h->d_tc_dbg + 499, &flag, sizeof(flag), cudaMemcpyHostToDevice) == cudaSuccess ? CEEUS_OK : CEEUS_ERR_CUDA;
+}
+
+int ceeus_tc_tiling(CeeusHandle h, int n, int32_t* rounds_out, int32_t* uneven_out) {
+  if (!h || n < 1 || !rounds_out || !uneven_out) return fail(h, CEEUS_ERR_INVALID, "tc_tiling: bad argument");
+  if (h->cfg.precision != CEEUS_PREC_TC) return fail(h, CEEUS_ERR_INVALID, "tc_tiling: not a CEEUS_PREC_TC handle");
+  const int E = h->md.E;
+  for (int e = 0; e < E; ++e) { rounds_out[e] = 0; uneven_out[e] = 0; }
+  const int pairs = h->md.kind == CEEUS_MODEL_MLP ? h->tcm.pairs : h->tc.pairs;
+  for (int pair = 0; pair < pairs; ++pair) {
+    if (h->md.kind == CEEUS_MODEL_MLP) {
+      const TcTile t = tc_tile(pairs, E, pair, n, 1, 128, 32);  // one 128-trajectory tile per CTA (rollout_mlp_tc.cu)
+      rounds_out[t.e] = t.rounds;
+    } else {
+      const TcTile t = tc_tile(pairs, E, pair, n, h->tc.NS, h->tc.Tmax, h->tc.tpw);
+      rounds_out[t.e] = t.rounds;
+      uneven_out[t.e] = t.uneven;
+    }
+  }
+  return CEEUS_OK;
 }
 
 int ceeus_tc_status(CeeusHandle h) {

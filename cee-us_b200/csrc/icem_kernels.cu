@@ -530,12 +530,24 @@ __global__ void repack_kernel(const float* __restrict__ src, float* __restrict__
 
 }  // namespace
 
+// dynamic shared memory of sample_kernel: 32 rows of normals + (colored noise only) the [2F x H] irDFT matrix
+size_t sample_smem_bytes(int H, int colored) {
+  const int F = H / 2 + 1;
+  const int nz = colored ? 2 * F : H;
+  const int nzp = (nz + 3) & ~3;
+  return ((size_t)kPairsPerBlock * nzp + (colored ? (size_t)2 * F * H : 0)) * sizeof(float);
+}
+
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st) {
   const long long npairs = (long long)a.n * a.U;
   if (npairs == 0) return cudaSuccess;
   const int nz = a.colored ? 2 * a.F : a.H;
   const int nzp = (nz + 3) & ~3;
-  const size_t smem = ((size_t)kPairsPerBlock * nzp + (size_t)2 * a.F * a.H) * sizeof(float);
+  const size_t smem = sample_smem_bytes(a.H, a.colored);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
   const int blocks = (int)((npairs + kPairsPerBlock - 1) / kPairsPerBlock);
   sample_kernel<<<blocks, kSampleThreads, smem, st>>>(a);
   return cudaGetLastError();

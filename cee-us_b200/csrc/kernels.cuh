@@ -56,6 +56,27 @@ struct TcLayout {
   int pairs;               // CTA pairs in the grid
   int scratch_floats;      // per member: logical fp32 matrices built by the pack kernels
 };
+// How the n trajectories of one launch are dealt to the CTA pairs / slots of one ensemble member (shared by the kernel and by
+// ceeus_tc_tiling, so the parity tests can assert which tiling branch a case exercises).
+struct TcTile {
+  int e, lp, np;        // member, index of the pair inside the member, pairs of the member
+  int per_worker, rounds, T;  // trajectories per worker (= slot), groups per worker, trajectories per group (<= Tmax)
+  int q_un;             // uneven split: trajectories per warp and round
+  int uneven;           // leader-CTA slots get 3 warps' worth, the other CTA's slots 4 (the issuing warp stays empty)
+};
+__host__ __device__ inline TcTile tc_tile(int pairs, int E, int pair, int n, int NS, int Tmax, int tpw) {
+  TcTile t;
+  const int base = pairs / E, rem = pairs % E;
+  if (pair < rem * (base + 1)) { t.e = pair / (base + 1); t.lp = pair % (base + 1); t.np = base + 1; }
+  else { const int q = pair - rem * (base + 1); t.e = rem + q / base; t.lp = q % base; t.np = base; }
+  t.per_worker = (n + 2 * NS * t.np - 1) / (2 * NS * t.np);
+  t.rounds = (t.per_worker + Tmax - 1) / Tmax;
+  if (t.rounds < 1) t.rounds = 1;
+  t.T = (t.per_worker + t.rounds - 1) / t.rounds;
+  t.q_un = (n + t.np * NS * 7 * t.rounds - 1) / (t.np * NS * 7 * t.rounds);
+  t.uneven = (t.T > 3 * tpw && t.q_un <= tpw) ? 1 : 0;
+  return t;
+}
 bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_host /* [kmap_len] or null */);
 cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, const int* kmap_dev, float* scratch,
                            uint8_t* wimg, float* wpar, cudaStream_t st);
@@ -98,6 +119,7 @@ struct SampleArgs {
   long long global_rows_per_env;
 };
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st);
+size_t sample_smem_bytes(int H, int colored);
 
 struct FixupArgs {  // mean-action row and elites shifted over time (mpc_torch.py:238-267, 304-310)
   float* actions;            // [nE*P,H,U]

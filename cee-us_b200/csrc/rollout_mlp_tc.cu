@@ -50,15 +50,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
   const int U = md.U, sd = md.sd, O = md.O, in = sd + U, L = tl.L, K1 = tl.K1;
   const int SNS = K1 + 8;  // snrm row stride in halves: 16 bytes of padding keep the per-row 16-byte accesses conflict free
 
-  int e, lp, np;
-  {
-    const int base = tl.pairs / md.E, rem = tl.pairs % md.E;
-    if (pair < rem * (base + 1)) { e = pair / (base + 1); lp = pair % (base + 1); np = base + 1; }
-    else { const int q2 = pair - rem * (base + 1); e = rem + q2 / base; lp = q2 % base; np = base; }
-  }
-  const int per_worker = (ra.n + 2 * np - 1) / (2 * np);
-  const int rounds = (per_worker + 127) / 128;
-  const int T = (per_worker + rounds - 1) / rounds;  // trajectories per tile, <= 128
+  const TcTile tt = tc_tile(tl.pairs, md.E, pair, ra.n, 1, 128, 32);  // one 128-trajectory tile per CTA
+  const int e = tt.e, lp = tt.lp, per_worker = tt.per_worker, rounds = tt.rounds;
+  const int T = tt.T;  // trajectories per tile, <= 128
   const int worker = lp * 2 + (int)rank;
 
   uint8_t* sW = smem + tl.sm_w;

@@ -183,20 +183,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
   const int N = md.N, A = md.A, D = md.D, S = md.S, U = md.U, O = md.O;
 
   // ---- member / trajectory range of this pair: pairs are dealt to members as evenly as the count allows ----
-  int e, lp, np;
-  {
-    const int base = tl.pairs / md.E, rem = tl.pairs % md.E;
-    if (pair < rem * (base + 1)) { e = pair / (base + 1); lp = pair % (base + 1); np = base + 1; }
-    else { const int q = pair - rem * (base + 1); e = rem + q / base; lp = q % base; np = base; }
-  }
-  const int per_worker = (ra.n + 2 * NS * np - 1) / (2 * NS * np);
-  const int rounds = (per_worker + tl.Tmax - 1) / tl.Tmax;
-  const int T = (per_worker + rounds - 1) / rounds;  // trajectories per group, <= Tmax
   // Uneven split: the MMA-issuing warp is the last-filled warp of the leader CTA's slots.  Where the even split would keep it busy
   // and the same number of rounds also fits with that warp left empty (leader slots 3 warps' worth of trajectories, the other
   // CTA's slots 4), the issuer stays a pure issuer that reacts at once.  q = trajectories per warp and round.
-  const int q_un = (ra.n + np * NS * 7 * rounds - 1) / (np * NS * 7 * rounds);
-  const bool uneven = T > 3 * tl.tpw && q_un <= tl.tpw;
+  const TcTile tt = tc_tile(tl.pairs, md.E, pair, ra.n, NS, tl.Tmax, tl.tpw);
+  const int e = tt.e, lp = tt.lp, np = tt.np, per_worker = tt.per_worker, rounds = tt.rounds, T = tt.T, q_un = tt.q_un;
+  const bool uneven = tt.uneven != 0;
   const int n_stage = 2 * (N - 1) + 6;
 
   uint8_t* sW = smem + tl.sm_w;

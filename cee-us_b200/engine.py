@@ -72,6 +72,9 @@ class Engine:
         cfg.hidden_dim, cfg.num_layers = hidden_dim, num_layers
         cfg.act_fn, cfg.layer_norm = _lib.ACT[act_fn], int(bool(layer_norm))
         cfg.aggr_mean = 1 if aggr_fn == "mean" else 0
+        if precision not in _lib.PREC:
+            raise ValueError(f"precision must be one of {sorted(_lib.PREC)} ('tc' = fp16 operands / fp32 accumulate on tcgen05; "
+                             f"there is no tf32 / bf16 mode), got {precision!r}")
         cfg.precision = _lib.PREC[precision]
         cfg.num_envs, cfg.num_traj, cfg.horizon = num_envs, num_traj, horizon
         cfg.opt_iterations, cfg.num_elites, cfg.num_kept = int(sp["opt_iterations"]), num_elites, num_kept
@@ -250,6 +253,12 @@ class Engine:
 
     def tc_status(self):
         return int(self.lib.ceeus_tc_status(self.handle))
+
+    def tc_tiling(self, n):
+        """(rounds[E], uneven[E]) of a tensor-core launch over n trajectories (ceeus_tc_tiling)."""
+        r, u = (C.c_int32 * self.E)(), (C.c_int32 * self.E)()
+        _lib.check(self.lib.ceeus_tc_tiling(self.handle, int(n), r, u), self.handle)
+        return list(r), list(u)
 
     def kernel_launches(self):
         return int(self.lib.ceeus_kernel_launches(self.handle))

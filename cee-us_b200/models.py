@@ -46,6 +46,8 @@ class _B200Ensemble:
         self.memory_is_preallocated = False
         self._state = None          # state_dict (reference key names) of torch tensors
         self._normalizers = None    # name -> (mean, std) numpy
+        self._norm_extra = {}       # name -> remaining fields of a loaded normaliser state_dict (running sums, count)
+        self._ckpt_extra = {}       # other checkpoint entries carried through load() -> save() unchanged (optimizer)
         self.weights_version = 0
         self._engines = {}
         self._reset_normalizers()
@@ -75,6 +77,22 @@ class _B200Ensemble:
             assert m.shape[0] == want and s.shape[0] == want, (k, m.shape, want)
             self._normalizers[k] = (m, s)
         self.weights_version += 1
+
+    # -- checkpoint format of the reference (gnn_ensemble.py:756-808, mlp_ensemble.py:613-638) -------------------
+    def _normalizer_state(self, k):
+        """state_dict of normaliser group ``k`` in the reference's format: Normalizer_v2 {mean, std} as [1,dim] arrays
+        (torch_helpers.py:793-797); running Normalizer {mean, std, sum, sum_of_squares, count} (:870-877) -- the running
+        sums read by load() are written back unchanged so that a reference model continues its statistics."""
+        m, s = self._normalizers[k]
+        if self.normalize_w_running_stats:
+            out = {"mean": m.astype(np.float64), "std": s.astype(np.float64)}
+            out.update(self._norm_extra.get(k, {}))
+            return out
+        return {"mean": m.reshape(1, -1).copy(), "std": s.reshape(1, -1).copy()}
+
+    def _read_normalizer_state(self, k, sd):
+        self._norm_extra[k] = {f: v for f, v in sd.items() if f not in ("mean", "std")}
+        return sd["mean"], sd["std"]
 
     def _normalizer_list(self):
         out = []
@@ -202,13 +220,16 @@ class B200GNNEnsemble(_B200Ensemble):
         """Reads a checkpoint written by GNNForwardEnsembleModel.save (gnn_ensemble.py:756-808)."""
         sd = torch.load(path, map_location="cpu", weights_only=False)
         self.load_state_dict(sd["model"])
-        self.set_normalizers({k: (sd[v]["mean"], sd[v]["std"]) for k, v in self._CKPT.items() if v in sd})
+        self.set_normalizers({k: self._read_normalizer_state(k, sd[v]) for k, v in self._CKPT.items() if v in sd})
+        self._ckpt_extra = {k: v for k, v in sd.items() if k == "optimizer"}
 
     def save(self, path):
+        """Writes the reference's checkpoint format: normaliser entries only for the enabled groups (:758-786)."""
         out = {"model": {k: v.cpu() for k, v in self.state_dict().items()}}
         for k, v in self._CKPT.items():
-            m, s = self._normalizers[k]
-            out[v] = {"mean": m.reshape(1, -1), "std": s.reshape(1, -1)}
+            if self.use_input_normalization if k.startswith("in") else self.use_output_normalization:
+                out[v] = self._normalizer_state(k)
+        out.update(self._ckpt_extra)
         torch.save(out, path)
 
 
@@ -239,10 +260,12 @@ class B200MLPEnsemble(_B200Ensemble):
     def load(self, path, for_training=True):
         sd = torch.load(path, map_location="cpu", weights_only=False)  # mlp_ensemble.py:625-638
         self.load_state_dict(sd["nn_state"])
-        self.set_normalizers({"in": (sd["input_normalizer"]["mean"], sd["input_normalizer"]["std"]),
-                              "out": (sd["output_normalizer"]["mean"], sd["output_normalizer"]["std"])})
+        self.set_normalizers({"in": self._read_normalizer_state("in", sd["input_normalizer"]),
+                              "out": self._read_normalizer_state("out", sd["output_normalizer"])})
+        self._ckpt_extra = {k: v for k, v in sd.items() if k == "optimizer"}
 
     def save(self, path):
-        torch.save({"nn_state": {k: v.cpu() for k, v in self.state_dict().items()},
-                    "input_normalizer": dict(zip(("mean", "std"), self._normalizers["in"])),
-                    "output_normalizer": dict(zip(("mean", "std"), self._normalizers["out"]))}, path)
+        out = {"nn_state": {k: v.cpu() for k, v in self.state_dict().items()},
+               "input_normalizer": self._normalizer_state("in"), "output_normalizer": self._normalizer_state("out")}
+        out.update(self._ckpt_extra)
+        torch.save(out, path)

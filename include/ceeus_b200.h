@@ -213,6 +213,11 @@ int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, co
 int64_t ceeus_kernel_launches(CeeusHandle h);
 /* CEEUS_PREC_TC only: 0 = the tensor-core kernel's mbarrier protocol never timed out; synchronises the device. */
 int ceeus_tc_status(CeeusHandle h);
+/* CEEUS_PREC_TC: how a launch over n trajectories is tiled, per ensemble member e: rounds_out[e] = trajectory groups each
+ * warpgroup ("slot") takes through the horizon one after the other, uneven_out[e] = 1 if the member's CTA pairs use the 3/4
+ * split that keeps the MMA-issuing warp empty (GNN kernel only).  The parity tests assert with it that every tiling branch
+ * of the kernels is compared with the oracle. */
+int ceeus_tc_tiling(CeeusHandle h, int n, int32_t* rounds_out /* [E] */, int32_t* uneven_out /* [E] */);
 /* CEEUS_PREC_TC profiling aid: enable=1 makes thread 0 of CTA 0 record (tag, clock64) pairs at every pipeline stage of
  * the next rollouts; out_host (nullable) receives the first n_pairs pairs.  enable=0 releases the buffer. */
 int ceeus_tc_debug_timeline(CeeusHandle h, int enable, long long* out_host, int n_pairs);

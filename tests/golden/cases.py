@@ -55,6 +55,18 @@ CASES = {
     "rollout_gnn_c3_slide": dict(kind="rollout", env="construction", n_obj=3, model="gnn", hidden=128, layers=2, P=12, H=5,
                                  wseed=17, identity_norm=True, running=False, oseed=14, case="Slide", sparse=False,
                                  shaped=False),
+    # task costs on synthetic trajectories close to the goal (a random-init model never gets there): every comparison of
+    # fpp_construction_env.py:404-511 falls on both sides -- solved / unsolved blocks, the gripper mask, the 0.5 term of the
+    # sparse branch, the buffer of PickAndPlace
+    "cost_c3_tower_sparse": dict(kind="cost", env="construction", n_obj=3, model="gnn", hidden=128, layers=2, P=24, H=6,
+                                 wseed=18, identity_norm=True, running=False, oseed=15, case="Singletower", sparse=True),
+    "cost_c3_tower_dense": dict(kind="cost", env="construction", n_obj=3, model="gnn", hidden=128, layers=2, P=24, H=6,
+                                wseed=18, identity_norm=True, running=False, oseed=15, case="Singletower", sparse=False),
+    "cost_c4_pp_dense": dict(kind="cost", env="construction", n_obj=4, model="gnn", hidden=128, layers=2, P=24, H=6,
+                             wseed=18, identity_norm=True, running=False, oseed=19, case="PickAndPlace", sparse=False),
+    "cost_c2_pyramid_unshaped": dict(kind="cost", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=24, H=6,
+                                     wseed=18, identity_norm=True, running=False, oseed=20, case="Pyramid", sparse=False,
+                                     shaped=False),
     # full MPC steps (3 consecutive get_action calls after beginning_of_rollout)
     "mpc_gnn_c2_curious": dict(kind="mpc", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=128, H=20,
                                wseed=21, identity_norm=True, running=False, oseed=8, nseed=100, steps=3,
@@ -71,6 +83,19 @@ CASES = {
                                 curiosity=True, cost="sum",
                                 sampler=dict(keep_previous_elites=False, shift_elites_over_time=False,
                                              fraction_elites_reused=0.1)),  # config 4 hyper-parameters
+    # branches of the sampler / cost reduction no shipped yaml switches on (mpc_torch.py:189-202, 327-332, 392-406)
+    "mpc_gnn_c3_task_coststd": dict(kind="mpc", env="construction", n_obj=3, model="gnn", hidden=128, layers=2, P=64, H=8,
+                                    wseed=26, identity_norm=True, running=False, oseed=16, nseed=105, steps=3,
+                                    curiosity=False, cost="sum",
+                                    sampler=dict(init_std=0.5, use_ensemble_cost_std=True, execute_best_elite=False)),
+    "mpc_gnn_c2_relinit_bounds": dict(kind="mpc", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=64, H=8,
+                                      wseed=27, identity_norm=True, running=False, oseed=17, nseed=106, steps=2,
+                                      curiosity=True, cost="sum", sampler={},
+                                      abounds=([-1.0, -0.5, -0.8, -0.2], [0.6, 1.0, 0.4, 1.0])),
+    "mpc_gnn_c2_absinit_bounds": dict(kind="mpc", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=64, H=8,
+                                      wseed=27, identity_norm=True, running=False, oseed=17, nseed=106, steps=2,
+                                      curiosity=True, cost="sum", sampler=dict(relative_init=False),
+                                      abounds=([-1.0, -0.5, -0.8, -0.2], [0.6, 1.0, 0.4, 1.0])),
     "mpc_mlp_c4_curious": dict(kind="mpc", env="construction", n_obj=4, model="mlp", hidden=256, layers=3, P=64, H=10,
                                wseed=25, identity_norm=False, running=False, oseed=12, nseed=104, steps=2,
                                curiosity=True, cost="sum", sampler={}),  # config 5 style
@@ -93,6 +118,9 @@ def build_inputs(c):
         ndims = orc.mlp_normalizer_dims(spec)
     weights = orc.synth_weights(shapes, c["wseed"])
     norms = orc.synth_normalizers(ndims, c["wseed"], identity=c["identity_norm"])
+    if "abounds" in c:  # asymmetric action bounds: relative_init then differs from absolute init (mpc_torch.py:189-202)
+        spec.action_low = np.asarray(c["abounds"][0], np.float32)
+        spec.action_high = np.asarray(c["abounds"][1], np.float32)
     obs, goal = orc.synth_start_obs(spec, c["oseed"])
     if c.get("case") in ("Flip", "Slide"):
         # per-coordinate tasks: goals within a few thresholds of the achieved values, so that both sides of every
@@ -111,3 +139,26 @@ def rollout_actions(c, spec):
     return np.clip(0.8 * rs.standard_normal((c["P"], c["H"], spec.action_dim)), -1, 1).astype(np.float32)
 
 
+def cost_trajectories(c, spec, obs, goal):
+    """kind == "cost": synthetic trajectories [H+1,E,P,O] around the goal configuration.  traj[0] = the start observation
+    with block 0 already on its goal (-> next block id k* = 1, fpp_construction_env.py:365-383)."""
+    rs = np.random.RandomState(c["oseed"] + 900)
+    E, P, H, O = 5, c["P"], c["H"], spec.obs_dim
+    A, D, N, sd = spec.agent_dim, spec.dyn_dim, spec.n_obj, spec.state_dim
+    start = obs.copy()
+    start[A:A + 3] = goal[0:3] + np.float32(0.004)
+    start[sd:] = goal
+    traj = np.empty((H + 1, E, P, O), np.float32)
+    traj[0] = start
+    nxt = np.tile(start, (H, E, P, 1))
+    for i in range(N):  # block positions within +-2.5 thresholds of their goals, some exactly solved
+        noise = rs.uniform(-0.05, 0.05, (H, E, P, 3)) * rs.choice([0.0, 0.2, 1.0], (H, E, P, 1))
+        nxt[..., A + D * i:A + D * i + 3] = goal[3 * i:3 * i + 3] + noise
+    target = rs.randint(0, N + 1, (H, E, P))  # the gripper hovers near one of the blocks / its own goal
+    centres = np.concatenate([nxt[..., A + D * i:A + D * i + 3][..., None, :] for i in range(N)] +
+                             [np.broadcast_to(goal[3 * N:3 * N + 3], (H, E, P, 1, 3))], axis=-2)
+    pick = np.take_along_axis(centres, target[..., None, None].repeat(3, -1), axis=-2)[..., 0, :]
+    nxt[..., 0:3] = pick + rs.uniform(-0.03, 0.03, (H, E, P, 3)) * rs.choice([0.3, 1.0], (H, E, P, 1))
+    traj[1:] = nxt.astype(np.float32)
+    traj[1:, ..., sd:] = goal
+    return traj

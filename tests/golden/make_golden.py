@@ -25,7 +25,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, HERE)
 import icem_oracle as orc  # noqa: E402
 import ref_harness as rh  # noqa: E402
-from cases import CASES, SeededNoise, build_inputs, rollout_actions  # noqa: E402
+from cases import CASES, SeededNoise, build_inputs, cost_trajectories, rollout_actions  # noqa: E402
 
 
 def load_into_reference_gnn(model, weights, normalizers, running_stats):
@@ -57,6 +57,11 @@ def build_reference(c, spec, weights, norms, goal):
                                        shaped_reward=c.get("shaped", True), goal=goal)
     else:
         env = rh.make_playground_env(c["n_obj"], goal=goal)
+    if "abounds" in c:
+        from gym import spaces
+
+        env.action_space = spaces.Box(np.asarray(c["abounds"][0], np.float32), np.asarray(c["abounds"][1], np.float32),
+                                      dtype="float32")
     if c["model"] == "gnn":
         model = rh.make_gnn_model(env, hidden_dim=c["hidden"], num_layers=c["layers"], running_stats=c["running"])
         load_into_reference_gnn(model, weights, norms, c["running"])
@@ -89,6 +94,17 @@ def gen_rollout_case(c):
     out["disagreement_bonus"] = ctrl._epistemic_bonus_per_path.numpy().copy()
     out["env_cost"] = env.cost_fn(o, a, n).numpy().copy()
     return out
+
+
+def gen_cost_case(c):
+    """env.cost_fn of the reference on the synthetic near-goal trajectories of cases.cost_trajectories."""
+    rh._prepare()
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env, _ = build_reference(c, spec, weights, norms, goal)
+    traj = torch.from_numpy(cost_trajectories(c, spec, obs, goal))
+    o, n = traj[:-1].permute(2, 1, 0, 3), traj[1:].permute(2, 1, 0, 3)
+    a = torch.zeros(c["P"], 5, c["H"], spec.action_dim)
+    return dict(env_cost=env.cost_fn(o, a, n).numpy().copy())
 
 
 def gen_mpc_case(c):
@@ -161,7 +177,7 @@ def generate_all(only=None):
     for name, c in CASES.items():
         if only and name not in only:
             continue
-        res[name] = gen_rollout_case(c) if c["kind"] == "rollout" else gen_mpc_case(c)
+        res[name] = {"rollout": gen_rollout_case, "mpc": gen_mpc_case, "cost": gen_cost_case}[c["kind"]](c)
     if not only or "colored_noise" in only:
         res["colored_noise"] = gen_noise_case()
     return res

@@ -26,6 +26,9 @@ def product_env(c, goal):
     else:
         env = ceeus_b200.playground_env(c["n_obj"])
     env.goal = np.asarray(goal, np.float32).copy()
+    if "abounds" in c:
+        env.action_space.low = np.asarray(c["abounds"][0], np.float32)
+        env.action_space.high = np.asarray(c["abounds"][1], np.float32)
     return env
 
 

@@ -10,11 +10,19 @@ import torch
 
 import icem_oracle as orc
 from cases import CASES
+from cases import cost_trajectories
+from test_oracle_golden import expected_action
 from helpers import (GOLD, SeededNoise, build_inputs, oracle_model, oracle_params, product_controller, product_env,
                      product_model, rel_err, rollout_actions, step_noise)
 
 pytestmark = pytest.mark.gpu
 TOL_FP32 = 1e-5  # BASELINE.json north_star: "1e-5 in fp32 mode" (relative, denominators floored at 1e-3)
+# Costs computed from the product's OWN rollout inherit the state error amplified by the conditioning of the disagreement:
+# std_e(x) is a difference of numbers of magnitude |x| ~ 1..30, so a state error of delta * |x| (delta <= 1e-5, the state
+# bar) moves one std term by up to delta * |x| / std_e(x) relative -- 1e-4 .. 1e-3 for the near-deterministic dims; the sum
+# over H x O terms averages most of it out (worst case measured over the fixtures: see DESIGN.md section 6).  The bar for the cost
+# ARITHMETIC itself is 1e-5 and is checked on identical inputs (the fixture's trajectories) in every test below.
+TOL_COST_OWN_ROLLOUT = 5e-5
 DEV = "cuda:0"
 
 
@@ -45,8 +53,13 @@ def test_rollout_matches_reference_fixture(name):
     bonus = g["disagreement_bonus"]  # [P,H]
     cpm, costs = eng.costs(traj)  # engine default: curiosity, "sum"
     want = -bonus.sum(-1)
-    assert rel_err(cpm.cpu().numpy(), np.repeat(want[:, None], 5, 1)) < 5e-5
-    assert rel_err(costs.cpu().numpy(), want) < 5e-5
+    assert rel_err(cpm.cpu().numpy(), np.repeat(want[:, None], 5, 1)) < TOL_COST_OWN_ROLLOUT
+    assert rel_err(costs.cpu().numpy(), want) < TOL_COST_OWN_ROLLOUT
+    # the cost kernel on the REFERENCE's trajectories (identical inputs): the 1e-5 bar proper
+    ref_traj = torch.from_numpy(np.concatenate([g["first_observation"][:, :, None], g["next_observations"]], axis=2))
+    cpm_r, costs_r = eng.costs(ref_traj.permute(2, 1, 0, 3).contiguous().to(DEV))
+    assert rel_err(costs_r.cpu().numpy(), want) < TOL_FP32
+    assert rel_err(cpm_r.cpu().numpy(), np.repeat(want[:, None], 5, 1)) < TOL_FP32
 
 
 @pytest.mark.parametrize("name", [k for k, c in CASES.items() if c["kind"] == "rollout"])
@@ -71,8 +84,35 @@ def test_task_costs_match_reference_fixture(name, mode):
     envc = g["env_cost"].astype(np.float32)  # [P,E,H]
     path = envc if mode.startswith("task") else (-g["disagreement_bonus"][:, None, :] + np.float32(0.7) * envc)
     want = path[..., 1:].min(-1) if mode.endswith("best") else path.sum(-1)
-    assert rel_err(cpm.cpu().numpy(), want) < 5e-5
-    assert rel_err(costs.cpu().numpy(), want.mean(-1)) < 5e-5
+    assert rel_err(cpm.cpu().numpy(), want) < TOL_COST_OWN_ROLLOUT
+    assert rel_err(costs.cpu().numpy(), want.mean(-1)) < TOL_COST_OWN_ROLLOUT
+    ref_traj = torch.from_numpy(np.concatenate([g["first_observation"][:, :, None], g["next_observations"]], axis=2))
+    cpm_r, costs_r = eng.costs(ref_traj.permute(2, 1, 0, 3).contiguous().to(DEV))
+    assert rel_err(cpm_r.cpu().numpy(), want) < TOL_FP32
+    assert rel_err(costs_r.cpu().numpy(), want.mean(-1)) < TOL_FP32
+
+
+@pytest.mark.parametrize("name", [k for k, c in CASES.items() if c["kind"] == "cost"])
+@pytest.mark.parametrize("along", ["sum", "best"])
+def test_task_cost_branches_on_near_goal_trajectories(name, along):
+    """ceeus_costs on caller-supplied trajectories close to the goal: solved / unsolved blocks, the gripper mask, the sparse
+    tower branch (fpp_construction_env.py:475-488) -- against env.cost_fn of the reference (fixture)."""
+    import ceeus_b200
+
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    model = product_model(c, env, weights, norms)
+    eng = ceeus_b200.Engine(horizon=c["H"], num_traj=c["P"], curiosity=False, cost_along_trajectory=along,
+                            **model.engine_kwargs())
+    eng.set_goal(goal)
+    traj = torch.from_numpy(cost_trajectories(c, spec, obs, goal)).to(DEV)
+    cpm, costs = eng.costs(traj)
+    envc = g["env_cost"].astype(np.float32)
+    want = envc[..., 1:].min(-1) if along == "best" else envc.sum(-1)
+    assert rel_err(cpm.cpu().numpy(), want) < TOL_FP32
+    assert rel_err(costs.cpu().numpy(), want.mean(-1)) < TOL_FP32
 
 
 @pytest.mark.parametrize("name", [k for k, c in CASES.items() if c["kind"] == "mpc"])
@@ -94,11 +134,11 @@ def test_mpc_steps_match_reference_fixture(name):
         np.testing.assert_array_equal(e.elite_idx_[0].cpu().numpy(), g[f"s{s}_i{i}_elite_idx"])
         k = e.k
         want_costs = np.sort(g[f"s{s}_i{i}_costs"], kind="stable")[:k]
-        assert rel_err(e.elite_costs_[0].cpu().numpy(), want_costs) < 5e-5
+        assert rel_err(e.elite_costs_[0].cpu().numpy(), want_costs) < TOL_COST_OWN_ROLLOUT
         assert rel_err(e.elite_actions_[0].cpu().numpy(), g[f"s{s}_i{i}_elite_actions"]) < TOL_FP32
         P = c["P"]
-        assert rel_err(ctrl.costs_.cpu().numpy(), g[f"s{s}_i{i}_costs"][:P]) < 5e-5
-        np.testing.assert_allclose(a, g[f"s{s}_action"], rtol=1e-5, atol=1e-6)
+        assert rel_err(ctrl.costs_.cpu().numpy(), g[f"s{s}_i{i}_costs"][:P]) < TOL_COST_OWN_ROLLOUT
+        np.testing.assert_allclose(a, expected_action(c, g, s), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(ctrl.mean_.cpu().numpy(), g[f"s{s}_mean_after"], rtol=1e-5, atol=2e-6)
 
 
@@ -131,7 +171,7 @@ def test_mpc_steps_with_env_cost_fn_called_on_materialised_rollouts(name):
         a = ctrl.get_action(g[f"s{s}_obs"], None, noise=flat)
         i = ctrl.opt_iter - 1
         np.testing.assert_array_equal(e.elite_idx_[0].cpu().numpy(), g[f"s{s}_i{i}_elite_idx"])
-        assert rel_err(ctrl.costs_.cpu().numpy(), g[f"s{s}_i{i}_costs"][:c["P"]]) < 5e-5
+        assert rel_err(ctrl.costs_.cpu().numpy(), g[f"s{s}_i{i}_costs"][:c["P"]]) < TOL_COST_OWN_ROLLOUT
         np.testing.assert_allclose(a, g[f"s{s}_action"], rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(ctrl.mean_.cpu().numpy(), g[f"s{s}_mean_after"], rtol=1e-5, atol=2e-6)
     assert len(calls) == c["steps"] * ctrl.opt_iter
@@ -169,24 +209,6 @@ def test_rollout_matches_oracle_fresh_inputs(env_kind, n_obj, model, hidden, P, 
                                 policy=_Policy(torch.from_numpy(acts).to(DEV)), horizon=H)
     got = pm._rollout_engine(P, H).traj_.cpu().numpy()
     assert got.shape == want.shape
-    if not rel_err(got, want) < TOL_FP32:
-        # The torch-CPU ORACLE is not run-to-run reproducible at this tolerance: in about 1 of 30 fresh processes its first
-        # evaluation comes out 2e-5 .. 5e-5 (rel_err) away from every later evaluation of the same inputs (digests recorded
-        # over 80 processes on a B200 box: the oracle's first result took one of two alternative values, its recomputation
-        # and all other processes the usual one; the CUDA result was bit-identical in all 80).  So: recompute the oracle once
-        # and record the event; a mismatch that persists is a failure of the product.
-        import hashlib
-        import warnings
-        md5 = lambda a: hashlib.md5(np.ascontiguousarray(a).tobytes()).hexdigest()[:10]
-        first = _where(got, want)
-        want2 = orc.rollout(om, torch.from_numpy(starts), torch.from_numpy(acts), torch.from_numpy(goal)).numpy()
-        pm.predict_n_steps(start_observations=torch.from_numpy(starts).to(DEV), start_states=None,
-                           policy=_Policy(torch.from_numpy(acts).to(DEV)), horizon=H)
-        got2 = pm._rollout_engine(P, H).traj_.cpu().numpy()
-        warnings.warn(f"transient fp32 rollout mismatch: {first}; digests want {md5(want)} -> {md5(want2)}, "
-                      f"got {md5(got)} -> {md5(got2)}")
-        np.testing.assert_array_equal(got2, got)  # the product is deterministic
-        want = want2
     assert rel_err(got, want) < TOL_FP32, _where(got, want)
 
 
@@ -226,7 +248,7 @@ def test_mpc_matches_oracle_larger_population():
         want = oc.get_action(obs)
         it = oc.trace[-1]["iters"][-1]
         np.testing.assert_array_equal(e.elite_idx_[0].cpu().numpy(), it["elite_idx"].numpy())
-        assert rel_err(ctrl.costs_.cpu().numpy(), it["costs"].numpy()[: c["P"]]) < 5e-5
+        assert rel_err(ctrl.costs_.cpu().numpy(), it["costs"].numpy()[: c["P"]]) < TOL_COST_OWN_ROLLOUT
         np.testing.assert_allclose(a, want, rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(ctrl.mean_.cpu().numpy(), oc.mean_.numpy(), rtol=1e-5, atol=2e-6)
         np.testing.assert_allclose(ctrl.std_.cpu().numpy(), oc.std_.numpy(), rtol=1e-5, atol=2e-6)

@@ -15,7 +15,7 @@ from cases import CASES
 from helpers import (GOLD, SeededNoise, build_inputs, elites_consistent, oracle_model, oracle_params, product_controller,
                      product_env, product_model, rel_err, rel_l2, rollout_actions, step_noise)
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.bulk_oracle]
 DEV = "cuda:0"
 TOL_TC = 1e-3
 
@@ -115,30 +115,25 @@ def test_tc_mpc_steps_against_oracle(name):
         assert np.all(np.isfinite(a)) and np.all(np.abs(a) <= 1.0)
 
 
-def test_tc_full_step_config2_and_unsupported():
-    import ceeus_b200
-
+def test_tc_step_is_deterministic_and_unsupported_shapes_are_refused():
+    """(The config-2 tensor-core step is compared with the fp32 path and the oracle in test_gpu_tc_tiling.py.)"""
     c = dict(kind="mpc", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=4096, H=30, wseed=5,
              identity_norm=True, running=False, oseed=1, curiosity=True, cost="sum", sampler={})
     spec, weights, norms, obs, goal = build_inputs(c)
     env = product_env(c, goal)
-    ctrl = product_controller(c, env, product_model(c, env, weights, norms, precision="tc"), precision="tc", seed=11)
-    ctrl.beginning_of_rollout(observation=obs, state=None, mode="train")
-    a1 = ctrl.get_action(obs, None)
-    e = ctrl.engine
-    assert e.tc_status() == 0 and torch.isfinite(e.traj_).all()
-    # same step on the fp32 path with the same device RNG stream: costs agree to the TC tolerance
-    ctrl32 = product_controller(c, env, product_model(c, env, weights, norms), seed=11)
-    ctrl32.beginning_of_rollout(observation=obs, state=None, mode="train")
-    ctrl32.get_action(obs, None)
-    # determinism
-    ctrl_b = product_controller(c, env, product_model(c, env, weights, norms, precision="tc"), precision="tc", seed=11)
-    ctrl_b.beginning_of_rollout(observation=obs, state=None, mode="train")
-    np.testing.assert_array_equal(ctrl_b.get_action(obs, None), a1)
+    acts = []
+    for _ in range(2):
+        ctrl = product_controller(c, env, product_model(c, env, weights, norms, precision="tc"), precision="tc", seed=11)
+        ctrl.beginning_of_rollout(observation=obs, state=None, mode="train")
+        acts.append([ctrl.get_action(obs, None).copy() for _ in range(2)])
+        assert ctrl.engine.tc_status() == 0
+    np.testing.assert_array_equal(acts[0], acts[1])
     c5 = dict(CASES["rollout_mlp_c4"], hidden=64)  # the tensor-core MLP kernel needs hidden_dim 128 / 256
     spec5, w5, n5, o5, g5 = build_inputs(c5)
     with pytest.raises(RuntimeError, match="CEEUS_PREC_TC"):
         product_model(c5, product_env(c5, g5), w5, n5, precision="tc")._rollout_engine(8, 4)
+    with pytest.raises(ValueError, match="precision"):  # there is no tf32 alias: "tc" is fp16 operands / fp32 accumulate
+        product_model(c, env, weights, norms, precision="tf32")._rollout_engine(8, 4)
 
 
 @pytest.mark.parametrize("variant", ["signed_gamma", "zero_gamma"])
