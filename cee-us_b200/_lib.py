@@ -70,6 +70,7 @@ SIGNATURES = {
     "ceeus_plan_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ceeus_kernel_launches": (C.c_int64, [C.c_void_p]),
     "ceeus_has_elites": (C.c_int, [C.c_void_p]),
+    "ceeus_profile_rollouts": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int]),
     "ceeus_tc_status": (C.c_int, [C.c_void_p]),
     "ceeus_tc_tiling": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ceeus_selftest_epilogue": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p]),

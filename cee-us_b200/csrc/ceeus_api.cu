@@ -57,6 +57,10 @@ struct CeeusHandle_t {
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
   int64_t graph_launches[2] = {0, 0};
   bool capturing = false;
+  // optional CUDA-event pairs around every rollout launch of the eager path (ceeus_profile_rollouts): in-step kernel time
+  std::vector<cudaEvent_t> prof_ev;
+  int prof_n = 0;
+  bool prof_on = false;
   int F = 0;
   std::vector<TensorSpec> wspec;
   std::string err;
@@ -323,6 +327,7 @@ void ceeus_destroy(CeeusHandle h) {
   drop_graphs(h);
   if (h->gstream) cudaStreamDestroy(h->gstream);
   if (h->gevent) cudaEventDestroy(h->gevent);
+  for (auto e : h->prof_ev) if (e) cudaEventDestroy(e);
   cudaFree(h->d_step_ctr);
   cudaFree(h->d_weights); cudaFree(h->d_norm); cudaFree(h->d_low); cudaFree(h->d_high);
   cudaFree(h->d_goal); cudaFree(h->d_obs); cudaFree(h->d_irdft);
@@ -414,6 +419,12 @@ static int do_rollout(CeeusHandle h, const float* start_obs_dev, int traj_per_st
   ra.weights = h->d_weights; ra.norm = h->d_norm; ra.start_obs = start_obs_dev; ra.goal = h->d_goal;
   ra.actions = actions_dev; ra.traj = traj_dev; ra.n = n; ra.H = h->cfg.horizon;
   ra.traj_per_start = traj_per_start; ra.traj_per_goal = traj_per_goal;
+  const bool prof = h->prof_on && !h->capturing && 2 * h->prof_n + 2 <= (int)h->prof_ev.size();
+  if (prof) CU_CHECK(h, cudaEventRecord(h->prof_ev[2 * h->prof_n], st));
+  struct ProfStop {  // the closing event is recorded on every exit path
+    CeeusHandle h; cudaStream_t st; bool on;
+    ~ProfStop() { if (on) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], st); h->prof_n += 1; } }
+  } prof_stop{h, st, prof};
   if (h->cfg.precision == CEEUS_PREC_TC && h->md.kind == CEEUS_MODEL_MLP)
     LAUNCH(h, launch_rollout_mlp_tc(h->md, ra, h->tcm, h->d_wimg, h->d_tc_err, st));
   else if (h->cfg.precision == CEEUS_PREC_TC)
@@ -639,6 +650,23 @@ int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, co
 }
 
 int64_t ceeus_kernel_launches(CeeusHandle h) { return h ? h->launches : 0; }
+
+int ceeus_profile_rollouts(CeeusHandle h, int enable, float* ms_out_host, int max_out) {
+  if (!h) return CEEUS_ERR_INVALID;
+  int n = 0;
+  if (ms_out_host && h->prof_n > 0) {
+    CU_CHECK(h, cudaEventSynchronize(h->prof_ev[2 * h->prof_n - 1]));
+    for (; n < h->prof_n && n < max_out; ++n)
+      CU_CHECK(h, cudaEventElapsedTime(&ms_out_host[n], h->prof_ev[2 * n], h->prof_ev[2 * n + 1]));
+  }
+  h->prof_n = 0;
+  if (enable && h->prof_ev.empty()) {
+    h->prof_ev.resize(2 * 256);
+    for (auto& e : h->prof_ev) CU_CHECK(h, cudaEventCreate(&e));
+  }
+  h->prof_on = enable != 0;
+  return n;
+}
 
 int ceeus_tc_debug_timeline(CeeusHandle h, int enable, long long* out_host, int n_pairs) {
   if (!h || h->cfg.precision != CEEUS_PREC_TC) return CEEUS_ERR_INVALID;

@@ -254,6 +254,14 @@ class Engine:
     def tc_status(self):
         return int(self.lib.ceeus_tc_status(self.handle))
 
+    def profile_rollouts(self, enable):
+        """Switches the event pairs around the rollout launches on / off; returns the durations (ms) recorded so far."""
+        buf = (C.c_float * 256)()
+        n = self.lib.ceeus_profile_rollouts(self.handle, int(bool(enable)), buf, 256)
+        if n < 0:
+            _lib.check(n, self.handle)
+        return [float(buf[i]) for i in range(n)]
+
     def tc_tiling(self, n):
         """(rounds[E], uneven[E]) of a tensor-core launch over n trajectories (ceeus_tc_tiling)."""
         r, u = (C.c_int32 * self.E)(), (C.c_int32 * self.E)()

@@ -211,6 +211,10 @@ int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, co
                     void* stream);
 /* counters for bench.py: kernels launched by this handle since creation */
 int64_t ceeus_kernel_launches(CeeusHandle h);
+/* Measurement aid: with enable != 0 every rollout launch of the eager path (ceeus_rollout, ceeus_plan_iter_*) is bracketed by
+ * a CUDA-event pair on its launch stream (up to 256 launches between two reads).  Each call first copies the durations (ms) of
+ * the pairs recorded since the previous call into ms_out_host (may be NULL) and returns their number, then sets the mode. */
+int ceeus_profile_rollouts(CeeusHandle h, int enable, float* ms_out_host, int max_out);
 /* CEEUS_PREC_TC only: 0 = the tensor-core kernel's mbarrier protocol never timed out; synchronises the device. */
 int ceeus_tc_status(CeeusHandle h);
 /* CEEUS_PREC_TC: how a launch over n trajectories is tiled, per ensemble member e: rounds_out[e] = trajectory groups each

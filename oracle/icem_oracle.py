@@ -4,10 +4,10 @@ TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and the 
 ``--impl reference`` legs of ``bench.py`` may import this file; it is the *checker* for the CUDA path in
 ``cee-us_b200/`` and is never on the product path (the product raises if its CUDA library is missing).
 
-Parity pin: every function below is checked against the reference's own, unmodified code run in the build
-container (``oracle/validate_against_reference.py``), and against the committed fixtures in
-``tests/golden/*.npz`` that ``tests/golden/make_golden.py`` produced from the reference
-(``tests/test_oracle_golden.py``).  Upstream ships no tests / golden vectors of its own.
+Parity pin: every function below is checked against the committed fixtures in ``tests/golden/*.npz``
+(``tests/test_oracle_golden.py``), which ``tests/golden/make_golden.py`` produced by running the reference's own,
+unmodified code in the build container (``make_golden.py --check`` regenerates and compares them).  Upstream ships
+no tests / golden vectors of its own.
 
 Each function cites the reference ``file:line`` it restates (paths relative to ``/root/reference``).
 All arithmetic is float32 torch on CPU, op order kept close to the reference so the timings taken from this

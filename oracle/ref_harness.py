@@ -1,8 +1,11 @@
 """Builds the reference's own (unmodified) model / controller / env objects without MuJoCo.
 
-TEST INFRASTRUCTURE ONLY (see ref_shims.py).  Only usable where ``/root/reference`` is mounted, i.e. in
-the build container: used by ``tests/golden/make_golden.py`` (fixture generation) and
-``oracle/validate_against_reference.py``.  Never imported by product code, never needed on the GPU box.
+TEST / BASELINE INFRASTRUCTURE ONLY (see ref_shims.py).  Never imported by product code.  The reference package is taken
+from ``/root/reference`` where that is mounted (the build container: ``tests/golden/make_golden.py`` generates the fixtures
+there) and otherwise from ``oracle/_ref/reference_mbrl.zip`` -- an archive of the reference's own, unmodified ``mbrl/*.py``
+that ``oracle/build_ref.py`` (called by ``__graft_entry__.build()``) packs in the build container; it is git-ignored, travels
+to the GPU box with the snapshot and is imported through ``zipimport``.  ``bench.py --impl reference`` times the reference's
+``TorchMpcICem`` / ``TorchCuriosityMpcICem`` + ``GNNForwardEnsembleModel`` / ``ParallelNNDeterministicEnsemble`` from it.
 
 Environment objects are created with ``object.__new__`` and given exactly the attributes the hot path
 reads (fpp_construction_env.py:32-125, playground_env_wgoals.py:24-72); every *method* that runs
@@ -17,11 +20,14 @@ import warnings
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("CEEUS_REFERENCE_ROOT", "/root/reference")
+REF_ZIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_mbrl.zip")
+REFERENCE_ROOT = os.environ.get("CEEUS_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/mbrl") else REF_ZIP)
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "mbrl"))
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "mbrl")) or (
+        REFERENCE_ROOT.endswith(".zip") and os.path.isfile(REFERENCE_ROOT))
 
 
 _ready = False
@@ -32,7 +38,7 @@ def _prepare():
     if _ready:
         return
     if not reference_available():
-        raise RuntimeError("reference tree not mounted at %s" % REFERENCE_ROOT)
+        raise RuntimeError("reference package not found (neither a tree nor oracle/_ref/reference_mbrl.zip): %s" % REFERENCE_ROOT)
     here = os.path.dirname(os.path.abspath(__file__))
     if here not in sys.path:
         sys.path.insert(0, here)
@@ -170,6 +176,23 @@ def make_mlp_model(env, hidden_dim=256, num_layers=3, n=5, running_stats=False, 
         target_is_delta=True,
         normalize_w_running_stats=running_stats,
     )
+
+
+def load_into_reference(model, weights, normalizers, running_stats):
+    """Seeded weights / normalisers -> a reference model object, through its own load_state_dict and normaliser attributes."""
+    model.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()})
+    if hasattr(model, "input_normalizer_agent"):
+        pairs = {"in_agent": model.input_normalizer_agent, "in_dyn": model.input_normalizer_obj_dyn,
+                 "in_stat": model.input_normalizer_obj_stat, "in_action": model.action_normalizer,
+                 "out_agent": model.output_agent_normalizer, "out_dyn": model.output_obj_normalizer}
+    else:
+        pairs = {"in": model.input_normalizer, "out": model.output_normalizer}
+    for k, nz in pairs.items():
+        m, s = normalizers[k]
+        if running_stats:
+            nz.mean_tensor, nz.std_tensor = torch.from_numpy(m.copy()), torch.from_numpy(s.copy())
+        else:
+            nz.mean, nz.std = torch.from_numpy(m.copy()).view(1, -1), torch.from_numpy(s.copy()).view(1, -1)
 
 
 def make_controller(env, model, *, curiosity, horizon, num_traj, cost_along_trajectory="sum", sampler=None,

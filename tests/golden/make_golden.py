@@ -28,29 +28,6 @@ import ref_harness as rh  # noqa: E402
 from cases import CASES, SeededNoise, build_inputs, cost_trajectories, rollout_actions  # noqa: E402
 
 
-def load_into_reference_gnn(model, weights, normalizers, running_stats):
-    model.model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
-    pairs = {"in_agent": model.input_normalizer_agent, "in_dyn": model.input_normalizer_obj_dyn,
-             "in_stat": model.input_normalizer_obj_stat, "in_action": model.action_normalizer,
-             "out_agent": model.output_agent_normalizer, "out_dyn": model.output_obj_normalizer}
-    for k, nz in pairs.items():
-        m, s = normalizers[k]
-        if running_stats:
-            nz.mean_tensor, nz.std_tensor = torch.from_numpy(m.copy()), torch.from_numpy(s.copy())
-        else:
-            nz.mean, nz.std = torch.from_numpy(m.copy()).view(1, -1), torch.from_numpy(s.copy()).view(1, -1)
-
-
-def load_into_reference_mlp(model, weights, normalizers, running_stats):
-    model.model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
-    for k, nz in {"in": model.input_normalizer, "out": model.output_normalizer}.items():
-        m, s = normalizers[k]
-        if running_stats:
-            nz.mean_tensor, nz.std_tensor = torch.from_numpy(m.copy()), torch.from_numpy(s.copy())
-        else:
-            nz.mean, nz.std = torch.from_numpy(m.copy()).view(1, -1), torch.from_numpy(s.copy()).view(1, -1)
-
-
 def build_reference(c, spec, weights, norms, goal):
     if c["env"] == "construction":
         env = rh.make_construction_env(c["n_obj"], case=c.get("case", "Singletower"), sparse=c.get("sparse", False),
@@ -64,10 +41,10 @@ def build_reference(c, spec, weights, norms, goal):
                                       dtype="float32")
     if c["model"] == "gnn":
         model = rh.make_gnn_model(env, hidden_dim=c["hidden"], num_layers=c["layers"], running_stats=c["running"])
-        load_into_reference_gnn(model, weights, norms, c["running"])
+        rh.load_into_reference(model, weights, norms, c["running"])
     else:
         model = rh.make_mlp_model(env, hidden_dim=c["hidden"], num_layers=c["layers"], running_stats=c["running"])
-        load_into_reference_mlp(model, weights, norms, c["running"])
+        rh.load_into_reference(model, weights, norms, c["running"])
     return env, model
 
 
