@@ -4,9 +4,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libceeus_b200.so")
+LIB_PATH = os.environ.get("CEEUS_LIB") or os.path.join(HERE, "libceeus_b200.so")  # CEEUS_LIB: development builds (A/B runs)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE = 0, -1, -2, -3
 MODEL_GNN, MODEL_MLP = 0, 1
 ACT = {"none": 0, None: 0, "relu": 1, "silu": 2, "swish": 2, "tanh": 3}
@@ -30,7 +30,8 @@ class CeeusConfig(C.Structure):
         ("threshold", C.c_float), ("buffer_threshold", C.c_float),
         ("coord_weights", C.c_float * 3), ("buffer_xyz", C.c_float * 3), ("cost_thres", C.c_float * 3),
         ("gripper_init", C.c_float * 3),
-        ("world_size", C.c_int32), ("rank", C.c_int32), ("seed", C.c_uint64)]
+        ("world_size", C.c_int32), ("rank", C.c_int32), ("cost_in_rollout_tail", C.c_int32), ("reserved0", C.c_int32),
+        ("seed", C.c_uint64)]
 
 
 _FP = C.POINTER(C.c_float)
@@ -73,13 +74,6 @@ SIGNATURES = {
     "ceeus_profile_rollouts": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int]),
     "ceeus_tc_status": (C.c_int, [C.c_void_p]),
     "ceeus_tc_tiling": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
-    "ceeus_selftest_epilogue": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "ceeus_tc_debug_flag": (C.c_int, [C.c_void_p, C.c_longlong]),
-    "ceeus_tc_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
-    "ceeus_selftest_tmem": (C.c_int, [C.c_void_p]),
-    "ceeus_selftest_tmem_contention": (C.c_int, [C.c_int, C.c_void_p]),
-    "ceeus_selftest_umma": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                      C.POINTER(C.c_int)]),
 }
 
 _lib = None
@@ -101,6 +95,28 @@ def load():
             raise RuntimeError("libceeus_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib
+
+
+# Diagnostics outside the product ABI (csrc/debug_tools.h): libceeus_b200_probe.so, test infrastructure
+PROBE_PATH = os.path.join(HERE, "libceeus_b200_probe.so")
+PROBE_SIGNATURES = {
+    "ceeus_selftest_tmem": (C.c_int, [C.c_void_p]),
+    "ceeus_selftest_tmem_contention": (C.c_int, [C.c_int, C.c_void_p]),
+    "ceeus_selftest_umma": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_int)]),
+}
+_probe = None
+
+
+def load_probe():
+    global _probe
+    if _probe is None:
+        lib = C.CDLL(PROBE_PATH)
+        for name, (res, args) in PROBE_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _probe = lib
+    return _probe
 
 
 def check(rc, handle=None):

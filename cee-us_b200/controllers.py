@@ -76,6 +76,7 @@ class B200MpcICem:
                               sampler=self.action_sampler_params, cost_along_trajectory=self.cost_along_trajectory,
                               curiosity=self._curiosity, num_envs=self.backend_params.get("num_envs", 1),
                               world_size=world, rank=rank, seed=self.backend_params.get("seed", 0),
+                              cost_in_rollout_tail=self.backend_params.get("cost_in_rollout_tail", False),
                               **self._extra_engine_kwargs, **kw)
         e = self._engine
         self.num_elites = e.k
@@ -193,6 +194,7 @@ class B200MpcICem:
     def _distributed_step(self, obs, noise):
         e = self._engine
         e.obs_dev_.copy_(torch.from_numpy(np.ascontiguousarray(obs.reshape(e.nE, e.O))), non_blocking=True)
+        e._last_obs_host = None
         return self.plan_on_device(noise).cpu().numpy()
 
     def reset_horizon(self, horizon):  # mpc_torch_curiosity.py:82-95

@@ -8,6 +8,10 @@
 #include <vector>
 
 #include "common.cuh"
+#include "cost_device.cuh"
+#ifdef CEEUS_DEBUG_TOOLS
+#include "debug_tools.h"
+#endif
 #include "kernels.cuh"
 
 using namespace ceeus;
@@ -45,6 +49,15 @@ struct CeeusHandle_t {
   float* d_tc_scratch = nullptr; // logical fp32 stage matrices (pack-time only)
   bool tc_all_fold = false;      // every member's LayerNorm affine could be folded into the weights (read back after packing)
   int* d_tc_err = nullptr;
+  // planner scratch of the fused cost tail: predicted dims of every (trajectory, step, member) + per-trajectory arrival counters
+  float* d_pred = nullptr;
+  int* d_done = nullptr;
+  long long pred_stride = 0;
+  int pred_Op = 0;
+  bool fuse_costs = true;   // CEEUS_NO_FUSE=1: separate cost_kernel on fully materialised trajectories (A/B measurements)
+  bool cost_tail = false;   // reduce the costs in the tail of the rollout kernel instead of in a separate launch (cost_in_rollout_tail)
+  const float* last_plan_obs = nullptr;  // start observations of the last planner rollout (read by the compact cost kernel)
+  bool l2_discard = true;   // CEEUS_NO_DISCARD=1: keep the consumed prediction blocks in L2 (write-back on eviction)
   long long* d_tc_dbg = nullptr;  // optional timeline of one warpgroup (ceeus_tc_debug_timeline)
   CeeusBuffers bufs{};
   bool bound = false, weights_set = false, norms_set = false;
@@ -251,6 +264,13 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
     cd.cost_thres[i] = c.cost_thres[i]; cd.gripper_init[i] = c.gripper_init[i];
   }
 
+  h->fuse_costs = std::getenv("CEEUS_NO_FUSE") == nullptr;
+  h->cost_tail = c.cost_in_rollout_tail != 0;
+  if (const char* ev = std::getenv("CEEUS_COST_TAIL")) h->cost_tail = std::atoi(ev) != 0;
+  h->l2_discard = std::getenv("CEEUS_NO_DISCARD") == nullptr;
+  h->pred_Op = md.kind == CEEUS_MODEL_GNN ? md.A + md.N * md.D : md.sd;
+  // trajectory-major blocks of whole 128-byte lines for the GNN kernels, step-major rows for the dense-MLP kernels (cost_device.cuh)
+  h->pred_stride = md.kind == CEEUS_MODEL_GNN ? round_up(c.horizon * md.E * h->pred_Op, 32) : 0;
   h->F = c.horizon / 2 + 1;
   auto alloc = [&](float** p, size_t n) { return cudaMalloc(p, (n ? n : 1) * sizeof(float)); };
   cudaError_t e = cudaSuccess;
@@ -331,6 +351,7 @@ void ceeus_destroy(CeeusHandle h) {
   cudaFree(h->d_step_ctr);
   cudaFree(h->d_weights); cudaFree(h->d_norm); cudaFree(h->d_low); cudaFree(h->d_high);
   cudaFree(h->d_goal); cudaFree(h->d_obs); cudaFree(h->d_irdft);
+  cudaFree(h->d_pred); cudaFree(h->d_done);
   cudaFree(h->d_wimg); cudaFree(h->d_wpar); cudaFree(h->d_kmap); cudaFree(h->d_tc_scratch); cudaFree(h->d_tc_err); cudaFree(h->d_tc_dbg);
   if (h->h_obs) cudaFreeHost(h->h_obs);
   if (h->h_action) cudaFreeHost(h->h_action);
@@ -399,9 +420,12 @@ int ceeus_set_goal(CeeusHandle h, const float* goal_host) {
 
 int ceeus_bind_buffers(CeeusHandle h, const CeeusBuffers* b) {
   if (!h || !b) return fail(h, CEEUS_ERR_INVALID, "bind_buffers: null argument");
-  if (!b->mean || !b->std || !b->actions || !b->traj || !b->costs_per_model || !b->costs || !b->elite_actions ||
+  if (!b->mean || !b->std || !b->actions || !b->costs_per_model || !b->costs || !b->elite_actions ||
       !b->elite_costs || !b->elite_cpm || !b->elite_idx || !b->cand || !b->action_out)
-    return fail(h, CEEUS_ERR_INVALID, "bind_buffers: every buffer must be non-null");
+    return fail(h, CEEUS_ERR_INVALID, "bind_buffers: every buffer except traj must be non-null");
+  if (!b->traj && (!h->fuse_costs || h->cd.env_kind == CEEUS_ENV_EXTERNAL))
+    return fail(h, CEEUS_ERR_INVALID, "bind_buffers: traj is required when the task cost is evaluated by the caller "
+                                      "(CEEUS_ENV_EXTERNAL) or the fused cost tail is disabled");
   h->bufs = *b;
   h->bound = true;
   drop_graphs(h);  // captured launches hold the old pointers
@@ -412,13 +436,51 @@ int ceeus_cand_record_len(CeeusHandle h) {
   return h ? 2 + h->cfg.ensemble_size + h->cfg.horizon * h->cfg.action_dim : CEEUS_ERR_INVALID;
 }
 
+static void fill_pred_layout(CeeusHandle h, costdev::FusedCost& fc) {
+  const long long n_plan = (long long)h->cfg.num_envs * h->cfg.num_traj;
+  fc.pred = h->d_pred; fc.Op = h->pred_Op; fc.pstride = h->pred_stride;
+  fc.Op_magic = (unsigned)((1ull << 32) / (unsigned)h->pred_Op) + 1u;
+  if (h->pred_stride) { fc.ps = h->pred_stride; fc.hs = (long long)h->md.E * h->pred_Op; fc.es = h->pred_Op; }
+  else { fc.ps = h->pred_Op; fc.hs = (long long)h->md.E * n_plan * h->pred_Op; fc.es = n_plan * h->pred_Op; }
+  fc.cpm = h->bufs.costs_per_model; fc.costs = h->bufs.costs;
+  fc.dims = costdev::CostDims{h->cfg.horizon, h->md.E, h->md.O, h->md.N, h->md.A, h->md.D, h->md.S, h->md.G, h->md.sd, h->pred_Op};
+  fc.cd = h->cd;
+}
+
+static int ensure_plan_scratch(CeeusHandle h) {
+  if (h->d_pred) return CEEUS_OK;
+  if (h->capturing) return fail(h, CEEUS_ERR_STATE, "planner scratch must be allocated before graph capture");
+  const size_t n_plan = (size_t)h->cfg.num_envs * h->cfg.num_traj;
+  const size_t per_traj = h->pred_stride ? (size_t)h->pred_stride : (size_t)h->cfg.horizon * h->md.E * h->pred_Op;
+  CU_CHECK(h, cudaMalloc(&h->d_pred, n_plan * per_traj * sizeof(float)));
+  CU_CHECK(h, cudaMalloc(&h->d_done, n_plan * sizeof(int)));
+  CU_CHECK(h, cudaMemset(h->d_done, 0, n_plan * sizeof(int)));
+  return CEEUS_OK;
+}
+
+// fused != 0: planner launch -- predictions go to the handle's compact scratch and every trajectory's cost is reduced in the tail of
+// the rollout kernel by the warp that completes its last ensemble member (cost_device.cuh); traj_dev is not written.
 static int do_rollout(CeeusHandle h, const float* start_obs_dev, int traj_per_start, const float* actions_dev, int n,
-                      int traj_per_goal, float* traj_dev, cudaStream_t st) {
+                      int traj_per_goal, float* traj_dev, cudaStream_t st, bool fused = false) {
   if (!h->weights_set || !h->norms_set) return fail(h, CEEUS_ERR_STATE, "rollout before set_weights / set_normalizers");
   RolloutArgs ra{};
   ra.weights = h->d_weights; ra.norm = h->d_norm; ra.start_obs = start_obs_dev; ra.goal = h->d_goal;
   ra.actions = actions_dev; ra.traj = traj_dev; ra.n = n; ra.H = h->cfg.horizon;
   ra.traj_per_start = traj_per_start; ra.traj_per_goal = traj_per_goal;
+  costdev::FusedCost fc{};
+  if (fused) {
+    const int n_plan = h->cfg.num_envs * h->cfg.num_traj;
+    if (n != n_plan) return fail(h, CEEUS_ERR_INVALID, "fused rollout: n must be num_envs * num_traj");
+    if (int rc = ensure_plan_scratch(h)) return rc;
+    fill_pred_layout(h, fc);
+    fc.done = h->cost_tail ? h->d_done : nullptr;  // null: the costs are reduced by launch_costs_compact after the rollout
+    h->last_plan_obs = start_obs_dev;
+    static const int tail_dbg = std::getenv("CEEUS_TAIL_DEBUG") ? std::atoi(std::getenv("CEEUS_TAIL_DEBUG")) : 0;
+    fc.dbg_mode = tail_dbg;
+    fc.discard = h->l2_discard ? 1 : 0;
+  } else if (!traj_dev) {
+    return fail(h, CEEUS_ERR_INVALID, "rollout: no trajectory buffer");
+  }
   const bool prof = h->prof_on && !h->capturing && 2 * h->prof_n + 2 <= (int)h->prof_ev.size();
   if (prof) CU_CHECK(h, cudaEventRecord(h->prof_ev[2 * h->prof_n], st));
   struct ProfStop {  // the closing event is recorded on every exit path
@@ -426,12 +488,17 @@ static int do_rollout(CeeusHandle h, const float* start_obs_dev, int traj_per_st
     ~ProfStop() { if (on) { cudaEventRecord(h->prof_ev[2 * h->prof_n + 1], st); h->prof_n += 1; } }
   } prof_stop{h, st, prof};
   if (h->cfg.precision == CEEUS_PREC_TC && h->md.kind == CEEUS_MODEL_MLP)
-    LAUNCH(h, launch_rollout_mlp_tc(h->md, ra, h->tcm, h->d_wimg, h->d_tc_err, st));
+    LAUNCH(h, launch_rollout_mlp_tc(h->md, ra, h->tcm, h->d_wimg, h->d_tc_err, fc, st));
   else if (h->cfg.precision == CEEUS_PREC_TC)
-    LAUNCH(h, launch_rollout_gnn_tc(h->md, ra, h->tc, h->d_wimg, h->d_wpar, h->d_tc_err, h->d_tc_dbg, h->tc_all_fold, st));
-  else if (h->md.kind == CEEUS_MODEL_GNN) LAUNCH(h, launch_rollout_gnn_simt(h->md, ra, h->num_sms, st));
-  else LAUNCH(h, launch_rollout_mlp_simt(h->md, ra, st));
+    LAUNCH(h, launch_rollout_gnn_tc(h->md, ra, h->tc, h->d_wimg, h->d_wpar, h->d_tc_err, h->d_tc_dbg, h->tc_all_fold, fc, st));
+  else if (h->md.kind == CEEUS_MODEL_GNN) LAUNCH(h, launch_rollout_gnn_simt(h->md, ra, h->num_sms, fc, st));
+  else LAUNCH(h, launch_rollout_mlp_simt(h->md, ra, fc, st));
   return CEEUS_OK;
+}
+
+static bool plan_fuses_costs(CeeusHandle h) {
+  const bool need_env = !h->cd.curiosity || h->cd.extrinsic;
+  return h->fuse_costs && !(need_env && h->cd.env_kind == CEEUS_ENV_EXTERNAL);
 }
 
 int ceeus_rollout(CeeusHandle h, const float* start_obs_dev, int n_start, const float* actions_dev, int n, float* traj_dev,
@@ -531,8 +598,8 @@ int ceeus_plan_iter_rollout(CeeusHandle h, int iter, const float* obs_dev, const
     f.seed = c.seed; f.stream_id = (uint32_t)c.opt_iterations; f.step_ctr = h->d_step_ctr; f.streams_per_step = streams_per_step;
     if (f.write_mean_row || f.shift_elites) LAUNCH(h, launch_fixup(f, st));
   }
-  // 3. predict_n_steps
-  return do_rollout(h, obs_dev, c.num_traj, h->bufs.actions, n, c.num_traj, h->bufs.traj, st);
+  // 3. predict_n_steps (+ trajectory costs in the kernel's tail unless the caller evaluates the task cost)
+  return do_rollout(h, obs_dev, c.num_traj, h->bufs.actions, n, c.num_traj, h->bufs.traj, st, plan_fuses_costs(h));
 }
 
 int ceeus_plan_iter_costs(CeeusHandle h, const float* env_cost_dev, void* stream) {
@@ -541,8 +608,16 @@ int ceeus_plan_iter_costs(CeeusHandle h, const float* env_cost_dev, void* stream
   const CeeusConfig& c = h->cfg;
   cudaStream_t st = S(stream);
   const int n = c.num_envs * c.num_traj;
-  // 4. trajectory costs
-  if (int rc = do_costs(h, h->bufs.traj, n, h->bufs.costs_per_model, h->bufs.costs, st, env_cost_dev, true)) return rc;
+  // 4. trajectory costs.  Built-in costs are reduced from the compact prediction scratch: in the tail of the rollout kernel
+  // (cost_in_rollout_tail) or by one warp per trajectory here; a task cost evaluated by the caller needs the full trajectories.
+  if (!plan_fuses_costs(h)) {
+    if (int rc = do_costs(h, h->bufs.traj, n, h->bufs.costs_per_model, h->bufs.costs, st, env_cost_dev, true)) return rc;
+  } else if (!h->cost_tail) {
+    costdev::FusedCost fc{};
+    fill_pred_layout(h, fc);
+    if (!h->last_plan_obs) return fail(h, CEEUS_ERR_STATE, "plan_iter_costs before plan_iter_rollout");
+    LAUNCH(h, launch_costs_compact(fc, h->last_plan_obs, h->d_goal, c.num_traj, c.num_traj, n, st));
+  }
   // 5. this rank's elite candidates
   TopkArgs t{};
   t.costs = h->bufs.costs; t.cpm = h->bufs.costs_per_model; t.actions = h->bufs.actions; t.cand = h->bufs.cand;
@@ -617,6 +692,8 @@ int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, co
     // Device RNG path: the whole step (H2D obs, ~30 kernels, D2H action) is one CUDA graph launch.  Nothing in the sequence
     // depends on host state except "are there elites to shift" (two graphs); the Philox stream base is a device counter.
     const int v = h->has_elites ? 1 : 0;
+    if (plan_fuses_costs(h))
+      if (int rc = ensure_plan_scratch(h)) return rc;
     if (!h->graph_exec[v]) {
       cudaGraph_t g = nullptr;
       const int64_t l0 = h->launches;
@@ -668,6 +745,7 @@ int ceeus_profile_rollouts(CeeusHandle h, int enable, float* ms_out_host, int ma
   return n;
 }
 
+#ifdef CEEUS_DEBUG_TOOLS
 int ceeus_tc_debug_timeline(CeeusHandle h, int enable, long long* out_host, int n_pairs) {
   if (!h || h->cfg.precision != CEEUS_PREC_TC) return CEEUS_ERR_INVALID;
   drop_graphs(h);  // captured launches hold the kernel variant and the d_tc_dbg pointer
@@ -703,6 +781,8 @@ int ceeus_tc_debug_flag(CeeusHandle h, long long flag) {
   if (!h || !h->d_tc_dbg) return CEEUS_ERR_INVALID;
   return cudaMemcpy(h->d_tc_dbg + 499, &flag, sizeof(flag), cudaMemcpyHostToDevice) == cudaSuccess ? CEEUS_OK : CEEUS_ERR_CUDA;
 }
+
+#endif  // CEEUS_DEBUG_TOOLS
 
 int ceeus_tc_tiling(CeeusHandle h, int n, int32_t* rounds_out, int32_t* uneven_out) {
   if (!h || n < 1 || !rounds_out || !uneven_out) return fail(h, CEEUS_ERR_INVALID, "tc_tiling: bad argument");

@@ -3,6 +3,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "cost_device.cuh"
 #include "kernels.cuh"
 
 namespace ceeus {
@@ -160,171 +161,47 @@ __global__ void fixup_kernel(const FixupArgs a) {
   }
 }
 
-__device__ __forceinline__ float warp_allsum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-__device__ __forceinline__ float norm3(const float* a, const float* b) {
-  const float x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
-  return sqrtf(x * x + y * y + z * z);
-}
-
-// env.cost_fn on one predicted observation row.
-// construction: fpp_construction_env.py:404-511; playground: playground_env_wgoals.py:108-157
-__device__ float env_cost_row(const float* __restrict__ row, const CostArgs& a, const CostDesc& cd, int kstar) {
-  if (cd.env_kind == CEEUS_ENV_PLAYGROUND) {
-    float s = 0.f;
-    for (int i = 0; i < a.N; ++i)
-      for (int c = 0; c < 2; ++c) {
-        const float d = fmaxf(fabsf(row[a.A + a.D * i + c] - row[a.sd + 2 * i + c]), 0.23f);
-        s += d * d;
-      }
-    return sqrtf(s);
-  }
-  if (cd.cost_case == CEEUS_CASE_FLIP || cd.cost_case == CEEUS_CASE_SLIDE) {
-    // per-coordinate distances (:297-355): achieved goal = euler angles (Flip, dims 3..5 of a block) or positions (Slide)
-    const int ao = cd.cost_case == CEEUS_CASE_FLIP ? 3 : 0;
-    float n_sparse = 0.f, dense_exp = 0.f;
-    for (int i = 0; i < a.N; ++i) {
-      bool any = false;
-      float es = 0.f;
-      for (int c = 0; c < 3; ++c) {
-        const float v = fmaxf(fabsf(row[a.A + a.D * i + ao + c] - row[a.sd + 3 * i + c]), cd.buffer_xyz[c]) * cd.coord_weights[c];
-        any = any || v > cd.cost_thres[c];
-        es += 1.f - expf(-0.5f * v);
-      }
-      n_sparse += any ? 1.f : 0.f;
-      dense_exp += es * (1.f / 3.f);
-    }
-    float g = 0.f;
-    if (cd.shaped && cd.cost_case == CEEUS_CASE_FLIP) g = norm3(row, cd.gripper_init);  // :457-458
-    if (cd.sparse) return n_sparse + g * 0.001f;
-    return dense_exp * 1e-3f + n_sparse + g * 0.01f;
-  }
-  int unsolved = 0;
-  float dense = 0.f;
-  for (int i = 0; i < a.N; ++i) {
-    const float d = norm3(row + a.A + a.D * i, row + a.sd + 3 * i);
-    unsolved += d > cd.threshold ? 1 : 0;
-    dense += fmaxf(d, cd.buffer_threshold);
-  }
-  float g = 0.f;
-  if (cd.shaped) {
-    const float* target = kstar < a.N ? row + a.A + a.D * kstar : row + a.sd + 3 * a.N;  // block k* or the gripper goal
-    g = norm3(row, target);
-    if (!(a.N - unsolved <= kstar)) g = 0.f;
-  }
-  if (cd.sparse) return (float)unsolved + (g > cd.threshold ? 0.5f : 0.f);
-  if (cd.cost_case == CEEUS_CASE_TOWER) return (float)unsolved + g * 0.01f;
-  return dense + g * 0.01f;
-}
-
-// trajectory_cost_fn (mpc_torch.py:116-137, mpc_torch_curiosity.py:45-80) + ensemble mean / std (:327-332).
-// One warp per trajectory: lanes stride over the observation dims for the disagreement term, lane e evaluates the
-// task cost of member e.
-// EM: compile-time bound of the member loops (the reference's ensemble size 5 gets its own instantiation: no dead registers)
+// trajectory_cost_fn + ensemble mean / std on caller-supplied FULL trajectories [H+1,E,n,O] (ceeus_costs, externally evaluated
+// task costs): one warp per trajectory, the arithmetic is cost_device.cuh's (shared with the fused tail of the rollout kernels).
 template <int EM>
 __global__ void __launch_bounds__(256) cost_kernel(const CostArgs a, const CostDesc cd) {
   const int lane = threadIdx.x & 31;
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (p >= a.n) return;
-  const size_t hs = (size_t)a.E * a.n * a.O;  // stride of one horizon slot
-  const size_t es = (size_t)a.n * a.O;
-  const float* base = a.traj + (size_t)p * a.O;
-  const bool need_env = !cd.curiosity || cd.extrinsic;
+  costdev::CostDims dm{a.H, a.E, a.O, a.N, a.A, a.D, a.S, a.G, a.sd, a.Ostd};
+  costdev::TrajView v;
+  v.hs = (long long)a.E * a.n * a.O;  // stride of one horizon slot
+  v.es = (long long)a.n * a.O;
+  v.row0 = a.traj + v.hs + (size_t)p * a.O;  // traj[1]: next_observations of step 0
+  v.goal = v.row0 + a.sd; v.ghs = v.hs; v.ges = v.es;
+  v.start = a.traj + (size_t)p * a.O;
+  float cpm = 0.f;
+  const float c = costdev::trajectory_cost_warp<EM>(dm, cd, v, a.env_cost_ext ? a.env_cost_ext + (size_t)p * a.E * a.H : nullptr, lane, &cpm);
+  if (lane < a.E) a.cpm[(size_t)p * a.E + lane] = cpm;
+  if (lane == 0) a.costs[p] = c;
+}
 
-  int kstar = 0;
-  if (need_env && a.env_cost_ext == nullptr && cd.env_kind == CEEUS_ENV_CONSTRUCTION && cd.shaped && cd.cost_case != CEEUS_CASE_FLIP &&
-      cd.cost_case != CEEUS_CASE_SLIDE) {  // get_next_block_id, :365-383 (start obs)
-    int unsolved = 0;
-    for (int i = 0; i < a.N; ++i) unsolved += norm3(base + a.A + a.D * i, base + a.sd + 3 * i) > cd.threshold ? 1 : 0;
-    kstar = a.N - unsolved;
-  }
-  float acc = cd.cost_along == CEEUS_COST_BEST ? CUDART_INF_F : 0.f;
-  // HB horizon steps at a time: all HB x E loads of a 32-feature column block are issued before any is used, so a warp
-  // keeps ~20 sectors in flight instead of one dependent load chain (HBM-bound kernel: 4 x H x E x n x O bytes read once)
-  constexpr int HB = 4;
-  const float inv_em1 = 1.f / (float)(a.E - 1);
-  for (int h0 = 0; h0 < a.H; h0 += HB) {
-    float bonus[HB];
-#pragma unroll
-    for (int hb = 0; hb < HB; ++hb) bonus[hb] = 0.f;
-    if (cd.curiosity) {
-      // two 32-feature column blocks per pass: 2 x HB x E independent loads in flight per lane
-      // (dims >= Ostd are known to be identical across the members -- see CostArgs::Ostd -- their std is exactly 0)
-      for (int d = lane; d < a.Ostd; d += 64) {
-        float x[2][HB][EM];
-        const bool second = d + 32 < a.Ostd;
-#pragma unroll
-        for (int hb = 0; hb < HB; ++hb)
-#pragma unroll
-          for (int e = 0; e < EM; ++e)
-            if (e < a.E && h0 + hb < a.H) {
-              const float* src = base + (size_t)(h0 + hb + 1) * hs + e * es + d;
-              x[0][hb][e] = __ldg(src);
-              x[1][hb][e] = second ? __ldg(src + 32) : 0.f;
-            }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c == 1 && !second) continue;
-#pragma unroll
-          for (int hb = 0; hb < HB; ++hb) {
-            if (h0 + hb < a.H) {
-              // Welford, as torch.std does (exactly 0 for dims identical across members, e.g. the goal)
-              float mean = 0.f, m2 = 0.f;
-#pragma unroll
-              for (int e = 0; e < EM; ++e)
-                if (e < a.E) {
-                  // 1/(e+1) as a compile-time constant multiply: <= 1 ulp from torch's division, and still exactly 0 for
-                  // identical members; the IEEE divisions made this kernel instruction-bound (126 us for 105 MB)
-                  const float dl = x[c][hb][e] - mean;
-                  mean = fmaf(dl, 1.f / (float)(e + 1), mean);
-                  m2 = fmaf(dl, x[c][hb][e] - mean, m2);
-                }
-              bonus[hb] += sqrtf(m2 * inv_em1);
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int hb = 0; hb < HB; ++hb) {
-      const int h = h0 + hb;
-      if (h < a.H) {
-        const float* nx = base + (size_t)(h + 1) * hs;
-        const float bs = cd.curiosity ? warp_allsum(bonus[hb]) : 0.f;
-        float c = 0.f;
-        if (lane < a.E) {
-          float envc = 0.f;
-          if (need_env)
-            envc = a.env_cost_ext != nullptr ? __ldg(a.env_cost_ext + ((size_t)p * a.E + lane) * a.H + h)
-                                             : env_cost_row(nx + lane * es, a, cd, kstar);
-          c = cd.curiosity ? (cd.extrinsic ? __fadd_rn(-bs, __fmul_rn(cd.extrinsic_scale, envc)) : -bs) : envc;
-        }
-        if (cd.cost_along == CEEUS_COST_BEST) {
-          if (h >= 1) acc = fminf(acc, c);  // amin over h >= 1 (mpc_torch.py:131)
-        } else {
-          acc += c;
-        }
-      }
-    }
-  }
-  if (lane < a.E) a.cpm[(size_t)p * a.E + lane] = acc;
-  float s = 0.f;
-  for (int e = 0; e < a.E; ++e) s += __shfl_sync(0xffffffffu, acc, e);
-  const float mean = s / (float)a.E;
-  float out = mean;
-  if (cd.use_std) {
-    float v = 0.f;
-    for (int e = 0; e < a.E; ++e) {
-      const float d = __shfl_sync(0xffffffffu, acc, e) - mean;
-      v = fmaf(d, d, v);
-    }
-    out = mean + sqrtf(v / (float)(a.E - 1));
-  }
-  if (lane == 0) a.costs[p] = out;
+// The same reduction on the planner's COMPACT scratch (cost_device.cuh: FusedCost; predicted dims only): one warp per
+// trajectory, 64 warps per SM -- the high-occupancy alternative to the in-kernel tail of the rollout kernels.
+template <int EM>
+__global__ void __launch_bounds__(256) cost_compact_kernel(const costdev::FusedCost f, const float* __restrict__ start_obs,
+                                                           const float* __restrict__ goal, int traj_per_start, int traj_per_goal,
+                                                           int n) {
+  extern __shared__ float envscratch[];  // [warps][E * H] task costs of all (member, step) pairs (0 bytes for pure curiosity)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int p = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (p >= n) return;
+  const bool need_env = !f.cd.curiosity || f.cd.extrinsic;
+  costdev::TrajView v;
+  v.row0 = f.pred + (long long)p * f.ps;
+  v.hs = f.hs; v.es = f.es;
+  v.goal = goal + (size_t)(p / traj_per_goal) * f.dims.G; v.ghs = 0; v.ges = 0;
+  v.start = start_obs + (size_t)(p / traj_per_start) * f.dims.O;
+  float cpm = 0.f;
+  const float c = costdev::trajectory_cost_warp<EM, 4>(f.dims, f.cd, v, nullptr, lane, &cpm,
+                                                       need_env ? envscratch + warp * f.dims.E * f.dims.H : nullptr);
+  if (lane < f.dims.E) f.cpm[(size_t)p * f.dims.E + lane] = cpm;
+  if (lane == 0) f.costs[p] = c;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -541,8 +418,6 @@ size_t sample_smem_bytes(int H, int colored) {
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st) {
   const long long npairs = (long long)a.n * a.U;
   if (npairs == 0) return cudaSuccess;
-  const int nz = a.colored ? 2 * a.F : a.H;
-  const int nzp = (nz + 3) & ~3;
   const size_t smem = sample_smem_bytes(a.H, a.colored);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -563,6 +438,18 @@ cudaError_t launch_costs(const CostArgs& a, const CostDesc& cd, cudaStream_t st)
   const int wpb = 8;
   if (a.E <= 5) cost_kernel<5><<<(a.n + wpb - 1) / wpb, wpb * 32, 0, st>>>(a, cd);
   else cost_kernel<kMaxEnsemble><<<(a.n + wpb - 1) / wpb, wpb * 32, 0, st>>>(a, cd);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_costs_compact(const costdev::FusedCost& f, const float* start_obs, const float* goal, int traj_per_start,
+                                 int traj_per_goal, int n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const int wpb = 8;
+  const bool need_env = !f.cd.curiosity || f.cd.extrinsic;
+  const size_t smem = need_env ? (size_t)wpb * f.dims.E * f.dims.H * sizeof(float) : 0;
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  if (f.dims.E <= 5) cost_compact_kernel<5><<<(n + wpb - 1) / wpb, wpb * 32, smem, st>>>(f, start_obs, goal, traj_per_start, traj_per_goal, n);
+  else cost_compact_kernel<kMaxEnsemble><<<(n + wpb - 1) / wpb, wpb * 32, smem, st>>>(f, start_obs, goal, traj_per_start, traj_per_goal, n);
   return cudaGetLastError();
 }
 

@@ -4,6 +4,8 @@
 
 namespace ceeus {
 
+namespace costdev { struct FusedCost; }  // cost_device.cuh: compact prediction scratch + arrival counters of a planner launch
+
 struct RolloutArgs {
   const float* weights;    // packed [E][member_stride]
   const float* norm;       // normaliser buffer (NormDesc offsets)
@@ -25,8 +27,8 @@ struct GnnTiling {
 };
 
 GnnTiling make_gnn_tiling(const ModelDesc& md);
-cudaError_t launch_rollout_gnn_simt(const ModelDesc& md, const RolloutArgs& ra, int num_sms, cudaStream_t st);
-cudaError_t launch_rollout_mlp_simt(const ModelDesc& md, const RolloutArgs& ra, cudaStream_t st);
+cudaError_t launch_rollout_gnn_simt(const ModelDesc& md, const RolloutArgs& ra, int num_sms, const costdev::FusedCost& fc, cudaStream_t st);
+cudaError_t launch_rollout_mlp_simt(const ModelDesc& md, const RolloutArgs& ra, const costdev::FusedCost& fc, cudaStream_t st);
 
 // ---- tensor-core rollout (rollout_tc.cu) ----
 // Stage matrices of one model step, in issue order per edge pass / node tile / global tile.
@@ -81,7 +83,8 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
 cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, const int* kmap_dev, float* scratch,
                            uint8_t* wimg, float* wpar, cudaStream_t st);
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
-                                  const float* wpar, int* err_flag, long long* dbg, bool all_fold, cudaStream_t st);
+                                  const float* wpar, int* err_flag, long long* dbg, bool all_fold, const costdev::FusedCost& fc,
+                                  cudaStream_t st);
 
 // ---- tensor-core rollout of the dense-MLP ensemble (rollout_mlp_tc.cu) ----
 struct TcMlpMat { int K, N, nloc, off; };
@@ -95,7 +98,7 @@ struct TcMlpLayout {
 bool make_mlp_tc_layout(const ModelDesc& md, int num_sms, TcMlpLayout* out);
 cudaError_t launch_mlp_tc_pack(const float* w32, const ModelDesc& md, const TcMlpLayout& tl, uint8_t* wimg, cudaStream_t st);
 cudaError_t launch_rollout_mlp_tc(const ModelDesc& md, const RolloutArgs& ra, const TcMlpLayout& tl, const uint8_t* wimg, int* err_flag,
-                                  cudaStream_t st);
+                                  const costdev::FusedCost& fc, cudaStream_t st);
 
 cudaError_t launch_epi_bench(int nwg, int with_bias, int with_mma, long long* out_dev);  // profiling aid (ceeus_selftest_epilogue)
 
@@ -150,6 +153,9 @@ struct CostArgs {
              // std is exactly 0 either way
 };
 cudaError_t launch_costs(const CostArgs& a, const CostDesc& cd, cudaStream_t st);
+// the same reduction on the planner's compact prediction scratch (cost_device.cuh: FusedCost), one warp per trajectory
+cudaError_t launch_costs_compact(const costdev::FusedCost& f, const float* start_obs, const float* goal, int traj_per_start,
+                                 int traj_per_goal, int n, cudaStream_t st);
 
 struct TopkArgs {
   const float* costs;    // [nE,P]

@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "cost_device.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
 #include "tc_rollout_common.cuh"
@@ -41,8 +42,9 @@ __device__ __forceinline__ float mlp_act(float x, int act) {
 template <int HD, bool SILU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
     rollout_mlp_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcMlpLayout tl, const uint8_t* __restrict__ wimg,
-                          int* __restrict__ err) {
+                          int* __restrict__ err, const costdev::FusedCost fc) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const bool fused = fc.pred != nullptr;  // planner launch: predictions -> compact scratch, costs reduced in the tail
   constexpr int W = HD / 2;  // accumulator columns per thread in a hidden layer
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -150,7 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
     for (int idx = tid; idx < Gc * O; idx += kMlpThreads) {
       const int b = idx / O, c = idx % O;
       const float v = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
-      ra.traj[((size_t)e * ra.n + p0 + b) * O + c] = v;
+      if (!fused) ra.traj[((size_t)e * ra.n + p0 + b) * O + c] = v;
       if (c < sd) s_state[b * sd + c] = v;
     }
     cta_sync();
@@ -161,7 +163,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
     }
     if (tid < 128 && live) snrm[tid * SNS + in] = __float2half_rn(1.f);
     // the goal part of every predicted observation (env.obs_postproc) is constant along the horizon: written here, once
-    for (int idx = tid; idx < Gc * md.G; idx += kMlpThreads) {
+    for (int idx = tid; idx < (fused ? 0 : Gc * md.G); idx += kMlpThreads) {
       const int b = idx / md.G, c = idx % md.G;
       const float gv = __ldg(ra.goal + (size_t)((p0 + b) / ra.traj_per_goal) * md.G + c);
       for (int hh = 1; hh <= ra.H; ++hh) ra.traj[(((size_t)hh * md.E + e) * ra.n + p0 + b) * O + sd + c] = gv;
@@ -189,7 +191,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
       }
       signal_a(cx, 0, lane);
       mma_layer(0);
-      float* outp = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
+      // row `row` of this step's predictions: full trajectories [H+1,E,n,O] or the trajectory's block of the planner scratch
+      float* outr = fused ? fc.pred + (size_t)(p0 + row) * fc.ps + (size_t)h * fc.hs + (size_t)e * fc.es
+                          : ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0 + row) * O;
 
 #pragma unroll 1
       for (int m = 0; m <= L; ++m) {
@@ -234,8 +238,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
                     const float na = st[c0 + j] + fmaf(ta.x, __uint_as_float(v[j]), ta.y);
                     const float nb = st[c0 + j + 1] + fmaf(tb.x, __uint_as_float(v[j + 1]), tb.y);
                     st[c0 + j] = na; st[c0 + j + 1] = nb;
-                    if (d0 + j < sd) outp[(size_t)row * O + d0 + j] = na;
-                    if (d0 + j + 1 < sd) outp[(size_t)row * O + d0 + j + 1] = nb;
+                    if (d0 + j < sd) outr[d0 + j] = na;
+                    if (d0 + j + 1 < sd) outr[d0 + j + 1] = nb;
                     pk[j / 2] = pack_half2((na - ta.z) * ta.w, (nb - tb.z) * tb.w);
                   }
                   __half* dst = snrm + row * SNS + d0;
@@ -261,6 +265,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
       }
       cta_sync();  // snrm of the next step is complete
     }
+  }
+  // ---- fused cost tail (planner launches), after the round loop so that nothing of the step loop is live here ----
+  // This member's rollouts of the CTA's tiles are complete: warp w arrives for the trajectories w, w + 8, ... of every tile and
+  // reduces those whose last ensemble member this was (disagreement + task cost + ensemble mean / std, cost_device.cuh), while the
+  // predictions are still in L2.
+  if (fused && fc.done != nullptr && fc.dbg_mode != 2) {
+    __threadfence();
+    cta_sync();
+    float* envbuf = (128 * sd) / 8 >= md.E * ra.H ? s_state + warp * ((128 * sd) / 8) : nullptr;  // the state tile is free now
+    // phase 0: arrive for the warp's trajectories; phase 1: reduce the ones assigned to this member (p % E == e) once every member
+    // has arrived (all CTAs of this persistent grid are resident, so the wait cannot deadlock)
+    for (int phase = 0; phase < 2; ++phase)
+      for (int rd = 0; rd < rounds; ++rd) {
+        const int w_lo = min(ra.n, worker * per_worker), w_hi = min(ra.n, w_lo + per_worker);
+        const int p0 = w_lo + rd * T;
+        const int Gc = max(0, min(T, w_hi - p0));
+        for (int b = warp; b < Gc; b += kMlpThreads / 32) {
+          const int p = p0 + b;
+          if (phase == 0) {
+            if (lane == 0) costdev::fused_arrive_nowait(fc, p);
+          } else if (p % md.E == e) {
+            costdev::fused_wait(fc, p, lane);
+            const float* srow = ra.start_obs + (size_t)(p / ra.traj_per_start) * O;
+            const float* grow = ra.goal + (size_t)(p / ra.traj_per_goal) * md.G;
+            if (md.E <= 5) costdev::fused_reduce<5, 8>(fc, p, lane, srow, grow, envbuf);
+            else costdev::fused_reduce<kMaxEnsemble, 4>(fc, p, lane, srow, grow, envbuf);
+          }
+        }
+      }
   }
   tc_fence_before();
   __syncthreads();
@@ -297,10 +330,10 @@ __global__ void mlp_tc_pack_kernel(const float* __restrict__ w32, const ModelDes
 
 template <int HD, bool SILU>
 cudaError_t launch_mlp_t(const ModelDesc& md, const RolloutArgs& ra, const TcMlpLayout& tl, const uint8_t* wimg, int* err_flag,
-                         cudaStream_t st) {
+                         const costdev::FusedCost& fc, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(rollout_mlp_tc_kernel<HD, SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
   if (e != cudaSuccess) return e;
-  rollout_mlp_tc_kernel<HD, SILU><<<dim3(2 * tl.pairs), kMlpThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, err_flag);
+  rollout_mlp_tc_kernel<HD, SILU><<<dim3(2 * tl.pairs), kMlpThreads, tl.smem_bytes, st>>>(md, ra, tl, wimg, err_flag, fc);
   return cudaGetLastError();
 }
 
@@ -348,10 +381,10 @@ cudaError_t launch_mlp_tc_pack(const float* w32, const ModelDesc& md, const TcMl
 }
 
 cudaError_t launch_rollout_mlp_tc(const ModelDesc& md, const RolloutArgs& ra, const TcMlpLayout& tl, const uint8_t* wimg, int* err_flag,
-                                  cudaStream_t st) {
+                                  const costdev::FusedCost& fc, cudaStream_t st) {
   const bool silu = md.act == CEEUS_ACT_SILU;
-  if (md.Hd == 256) return silu ? launch_mlp_t<256, true>(md, ra, tl, wimg, err_flag, st) : launch_mlp_t<256, false>(md, ra, tl, wimg, err_flag, st);
-  return silu ? launch_mlp_t<128, true>(md, ra, tl, wimg, err_flag, st) : launch_mlp_t<128, false>(md, ra, tl, wimg, err_flag, st);
+  if (md.Hd == 256) return silu ? launch_mlp_t<256, true>(md, ra, tl, wimg, err_flag, fc, st) : launch_mlp_t<256, false>(md, ra, tl, wimg, err_flag, fc, st);
+  return silu ? launch_mlp_t<128, true>(md, ra, tl, wimg, err_flag, fc, st) : launch_mlp_t<128, false>(md, ra, tl, wimg, err_flag, fc, st);
 }
 
 }  // namespace ceeus

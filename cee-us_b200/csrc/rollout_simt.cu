@@ -10,6 +10,7 @@
 // bias + LayerNorm + activation are fused into the GEMM epilogue.  The only HBM traffic is the action read and
 // one coalesced store of the predicted observation per step.
 #include "common.cuh"
+#include "cost_device.cuh"
 #include "kernels.cuh"
 
 namespace ceeus {
@@ -206,6 +207,25 @@ __device__ __forceinline__ void zero_cols(float* X, int XS, int c0, int c1) {
   for (int idx = threadIdx.x; idx < kTileRows * w; idx += kSimtThreads) X[(idx / w) * XS + c0 + idx % w] = 0.f;
 }
 
+// Tail of a planner launch: this member's rollout of the CTA's trajectories is complete; warp w arrives for the trajectories
+// w, w + 8, ... and reduces those whose last ensemble member this was (cost_device.cuh).
+__device__ __forceinline__ void simt_fused_tail(const costdev::FusedCost& fc, const RolloutArgs& ra, const ModelDesc& md, int p0, int Gc,
+                                                float* scratch, int scratch_floats) {
+  __threadfence();
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_warp = scratch_floats / (kSimtThreads / 32);
+  float* envbuf = per_warp >= md.E * ra.H ? scratch + warp * per_warp : nullptr;  // a slice of the (now idle) GEMM input tile
+  for (int b = warp; b < Gc; b += kSimtThreads / 32) {
+    const int p = p0 + b;
+    const float* srow = ra.start_obs + (size_t)(p / ra.traj_per_start) * md.O;
+    const float* grow = ra.goal + (size_t)(p / ra.traj_per_goal) * md.G;
+    if (md.E <= 5) costdev::fused_cost_arrive<5>(fc, p, lane, srow, grow, envbuf);
+    else costdev::fused_cost_arrive<kMaxEnsemble>(fc, p, lane, srow, grow, envbuf);
+  }
+  __syncthreads();  // the tile is reused by the next group
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
@@ -214,7 +234,8 @@ __device__ __forceinline__ void zero_cols(float* X, int XS, int c0, int c1) {
 // ------------------------------------------------------------------------------------------------------------
 template <int NCH>
 __global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_simt_kernel(const ModelDesc md, const RolloutArgs ra,
-                                                                            const GnnTiling tl) {
+                                                                            const GnnTiling tl, const costdev::FusedCost fc) {
+  const bool fused = fc.pred != nullptr;  // planner launch: predictions -> compact scratch, costs reduced in the tail
   constexpr int HD = 16 * NCH;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
@@ -251,7 +272,7 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_simt_kernel(const
       if (b < Gc) v = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
       sraw[idx] = v;
     }
-    for (int idx = tid; idx < Gc * O; idx += kSimtThreads) {
+    for (int idx = tid; idx < (fused ? 0 : Gc * O); idx += kSimtThreads) {
       const int b = idx / O, c = idx % O;
       ra.traj[((size_t)e * ra.n + p0 + b) * O + c] = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
     }
@@ -390,7 +411,13 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_simt_kernel(const
         sraw[idx] = v;
       }
       __syncthreads();
-      {
+      if (fused) {
+        // planner: only the predicted dims (agent + dynamic object features), into each trajectory's block [H][E][Op]
+        for (int idx = tid; idx < Gc * fc.Op; idx += kSimtThreads) {
+          const int b = idx / fc.Op, c = idx % fc.Op;
+          fc.pred[(size_t)(p0 + b) * fc.ps + (size_t)h * fc.hs + (size_t)e * fc.es + c] = sraw[b * sd + c];
+        }
+      } else {
         float* out = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
         for (int idx = tid; idx < Gc * O; idx += kSimtThreads) {
           const int b = idx / O, c = idx % O;
@@ -399,6 +426,7 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_simt_kernel(const
       }
       // (next iteration starts with reads of sraw only; writes to snrm are ordered by the sync above)
     }
+    if (fused && fc.done != nullptr) simt_fused_tail(fc, ra, md, p0, Gc, Xe, kTileRows * XSe);
   }
 }
 
@@ -408,7 +436,8 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_simt_kernel(const
 // ------------------------------------------------------------------------------------------------------------
 template <int NCH>
 __global__ void __launch_bounds__(kSimtThreads, 1) rollout_mlp_simt_kernel(const ModelDesc md, const RolloutArgs ra,
-                                                                            const int XS) {
+                                                                            const int XS, const costdev::FusedCost fc) {
+  const bool fused = fc.pred != nullptr;
   constexpr int HD = 16 * NCH;
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
@@ -431,7 +460,7 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_mlp_simt_kernel(const
       const int b = idx / sd, c = idx % sd;
       sraw[idx] = b < Gc ? __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c) : 0.f;
     }
-    for (int idx = tid; idx < Gc * O; idx += kSimtThreads) {
+    for (int idx = tid; idx < (fused ? 0 : Gc * O); idx += kSimtThreads) {
       const int b = idx / O, c = idx % O;
       ra.traj[((size_t)e * ra.n + p0 + b) * O + c] = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
     }
@@ -469,12 +498,20 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_mlp_simt_kernel(const
         sraw[idx] += fmaf(dl[idx], __ldg(nrm + md.nrm.out_all + sd + c), __ldg(nrm + md.nrm.out_all + c));
       }
       __syncthreads();
-      float* out = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
-      for (int idx = tid; idx < Gc * O; idx += kSimtThreads) {
-        const int b = idx / O, c = idx % O;
-        out[idx] = c < sd ? sraw[b * sd + c] : __ldg(ra.goal + (size_t)((p0 + b) / ra.traj_per_goal) * md.G + (c - sd));
+      if (fused) {
+        for (int idx = tid; idx < Gc * sd; idx += kSimtThreads) {
+          const int b = idx / sd, c = idx % sd;
+          fc.pred[(size_t)(p0 + b) * fc.ps + (size_t)h * fc.hs + (size_t)e * fc.es + c] = sraw[idx];
+        }
+      } else {
+        float* out = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
+        for (int idx = tid; idx < Gc * O; idx += kSimtThreads) {
+          const int b = idx / O, c = idx % O;
+          out[idx] = c < sd ? sraw[b * sd + c] : __ldg(ra.goal + (size_t)((p0 + b) / ra.traj_per_goal) * md.G + (c - sd));
+        }
       }
     }
+    if (fused && fc.done != nullptr) simt_fused_tail(fc, ra, md, p0, Gc, X, kTileRows * XS);
   }
 }
 
@@ -509,29 +546,30 @@ GnnTiling make_gnn_tiling(const ModelDesc& md) {
 
 template <int NCH>
 static cudaError_t launch_gnn(const ModelDesc& md, const RolloutArgs& ra, const GnnTiling& tl, int num_sms,
-                              cudaStream_t st) {
+                              const costdev::FusedCost& fc, cudaStream_t st) {
   auto kern = rollout_gnn_simt_kernel<NCH>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_bytes);
   if (err != cudaSuccess) return err;
   const int groups = (ra.n + tl.G - 1) / tl.G;
   dim3 grid(groups, md.E);
   (void)num_sms;
-  kern<<<grid, kSimtThreads, tl.smem_bytes, st>>>(md, ra, tl);
+  kern<<<grid, kSimtThreads, tl.smem_bytes, st>>>(md, ra, tl, fc);
   return cudaGetLastError();
 }
 
-cudaError_t launch_rollout_gnn_simt(const ModelDesc& md, const RolloutArgs& ra, int num_sms, cudaStream_t st) {
+cudaError_t launch_rollout_gnn_simt(const ModelDesc& md, const RolloutArgs& ra, int num_sms, const costdev::FusedCost& fc,
+                                    cudaStream_t st) {
   const GnnTiling tl = make_gnn_tiling(md);
   if (tl.G < 1 || tl.TPT < 1) return cudaErrorInvalidValue;
   switch (md.Hd) {
-    case 64: return launch_gnn<4>(md, ra, tl, num_sms, st);
-    case 128: return launch_gnn<8>(md, ra, tl, num_sms, st);
+    case 64: return launch_gnn<4>(md, ra, tl, num_sms, fc, st);
+    case 128: return launch_gnn<8>(md, ra, tl, num_sms, fc, st);
     default: return cudaErrorInvalidValue;
   }
 }
 
 template <int NCH>
-static cudaError_t launch_mlp(const ModelDesc& md, const RolloutArgs& ra, cudaStream_t st) {
+static cudaError_t launch_mlp(const ModelDesc& md, const RolloutArgs& ra, const costdev::FusedCost& fc, cudaStream_t st) {
   auto kern = rollout_mlp_simt_kernel<NCH>;
   const int Hd = md.Hd;
   const int k0 = md.mlp[0].layer[0].Kpad;
@@ -540,15 +578,15 @@ static cudaError_t launch_mlp(const ModelDesc& md, const RolloutArgs& ra, cudaSt
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (err != cudaSuccess) return err;
   dim3 grid((ra.n + kTileRows - 1) / kTileRows, md.E);
-  kern<<<grid, kSimtThreads, bytes, st>>>(md, ra, XS);
+  kern<<<grid, kSimtThreads, bytes, st>>>(md, ra, XS, fc);
   return cudaGetLastError();
 }
 
-cudaError_t launch_rollout_mlp_simt(const ModelDesc& md, const RolloutArgs& ra, cudaStream_t st) {
+cudaError_t launch_rollout_mlp_simt(const ModelDesc& md, const RolloutArgs& ra, const costdev::FusedCost& fc, cudaStream_t st) {
   switch (md.Hd) {
-    case 64: return launch_mlp<4>(md, ra, st);
-    case 128: return launch_mlp<8>(md, ra, st);
-    case 256: return launch_mlp<16>(md, ra, st);
+    case 64: return launch_mlp<4>(md, ra, fc, st);
+    case 128: return launch_mlp<8>(md, ra, fc, st);
+    case 256: return launch_mlp<16>(md, ra, fc, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -30,6 +30,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "cost_device.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
 #include "tc_rollout_common.cuh"
@@ -171,8 +172,10 @@ __device__ __forceinline__ void tc_issue_stage(volatile int* abort_flag, int* er
 template <int HD, bool RELU, bool DBG, bool FOLD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::value, 1)
     rollout_gnn_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcLayout tl, const uint8_t* __restrict__ wimg,
-                          const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg) {
+                          const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg,
+                          const costdev::FusedCost fc) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const bool fused = fc.pred != nullptr;  // planner launch: predictions -> compact scratch, costs reduced in the tail
   constexpr int CH = HD / 8;  // 16-byte chunks per hidden row
   constexpr int NS = TcSlots<HD>::value;
   constexpr int kTcThreads = 128 * NS;
@@ -355,11 +358,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       wg_sync(s);
       // ---- group init: start observation -> registers, snrm, traj[0]; the trailing observation part for every step ----
       for (int idx = row; idx < (tl.Tmax * SNs) / 8; idx += 128) reinterpret_cast<uint4*>(snrm)[idx] = make_uint4(0u, 0u, 0u, 0u);
-      for (int idx = row; idx < Gc * O; idx += 128) {
-        const int bb = idx / O, c = idx % O;
-        const float v = __ldg(ra.start_obs + (size_t)((p0 + bb) / ra.traj_per_start) * O + c);
-        ra.traj[((size_t)e * ra.n + p0 + bb) * O + c] = v;
-      }
+      if (!fused)
+        for (int idx = row; idx < Gc * O; idx += 128) {
+          const int bb = idx / O, c = idx % O;
+          const float v = __ldg(ra.start_obs + (size_t)((p0 + bb) / ra.traj_per_start) * O + c);
+          ra.traj[((size_t)e * ra.n + p0 + bb) * O + c] = v;
+        }
       for (int idx = row; idx < Gc * tail; idx += 128) {
         const int bb = idx / tail, c = idx % tail;
         s_tail[idx] = c < N * S ? __ldg(ra.start_obs + (size_t)((p0 + bb) / ra.traj_per_start) * O + A + N * D + c)
@@ -417,8 +421,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       };
       // state after model step hh -> traj[hh + 1]: the warp's trajectories are contiguous in global memory, so the staged rows
       // go out as one coalesced copy (issued while an MMA stage runs, off the dependency chain)
-      const int n_out = max(0, min(tpw, Gc - qf * tpw)) * O;
+      const int n_traj_w = max(0, min(tpw, Gc - qf * tpw));  // live trajectories of this warp
+      const int n_out = n_traj_w * O;
       auto flush_outputs = [&](int hh) {
+#ifndef EXP_OLD_FLUSH
+        if (fused) {
+          // planner: only the predicted dims, into the trajectory's own block [H][E][Op] of the compact scratch
+          float* og = fc.pred + (size_t)(p0 + qf * tpw) * fc.ps + (size_t)hh * fc.hs + (size_t)e * fc.es;
+          const int n_pred = n_traj_w * fc.Op;
+#pragma unroll 4
+          for (int i = lane; i < n_pred; i += 32) {
+            const int tb = (int)__umulhi((unsigned)i, fc.Op_magic), c = i - tb * fc.Op;
+            og[(size_t)tb * fc.ps + c] = s_obs[tb * O + c];
+          }
+          return;
+        }
+#endif
         float* og = ra.traj + (((size_t)(hh + 1) * md.E + e) * ra.n + p0 + qf * tpw) * O;
 #pragma unroll 4
         for (int i = lane; i < n_out; i += 32) og[i] = s_obs[i];
@@ -645,6 +663,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       }
       flush_outputs(ra.H - 1);
     }
+    // ---- fused cost tail (planner launches) ----
+    // This member's rollouts of the warp's trajectories (all rounds) are complete in global memory.  For every one of them the
+    // warp bumps the trajectory's arrival counter; the warp that brings it to E reduces the trajectory (disagreement + task cost
+    // + ensemble mean / std, cost_device.cuh) while the predictions are still in L2.  Placed AFTER the round loop on purpose:
+    // nothing of the 255-register step loop is live here (inside the loop it cost 600 bytes of spills and 1.8x the time).
+    if (fused && fc.done != nullptr && fc.dbg_mode != 2) {
+      __threadfence();
+      __syncwarp();
+      float* envbuf = tpw * O >= md.E * ra.H ? s_obs : nullptr;  // the warp's observation staging is free now
+      // phase 0: arrive for every trajectory of this warp; phase 1: reduce the ones assigned to this member (p % E == e) once all
+      // members have arrived (every CTA of this persistent grid is resident, so the wait cannot deadlock)
+      for (int phase = 0; phase < 2; ++phase)
+        for (int rd = 0; rd < rounds; ++rd) {
+          int w_lo, w_hi, Tw;
+          if (uneven) {
+            const int u_off = lp * NS * 7 + (rank == 0 ? 3 * s : 3 * NS + 4 * s);
+            Tw = (rank == 0 ? 3 : 4) * q_un;
+            w_lo = min(ra.n, u_off * q_un * rounds);
+            w_hi = min(ra.n, w_lo + Tw * rounds);
+          } else {
+            Tw = T;
+            w_lo = min(ra.n, worker * per_worker);
+            w_hi = min(ra.n, w_lo + per_worker);
+          }
+          const int p0 = w_lo + rd * Tw;
+          const int Gc = max(0, min(Tw, w_hi - p0));
+          const int n_traj_w = max(0, min(tpw, Gc - qf * tpw));
+          if (phase == 0) {  // lane tb arrives for trajectory tb (the stores were fenced above)
+            if (lane < n_traj_w) costdev::fused_arrive_nowait(fc, p0 + qf * tpw + lane);
+            continue;
+          }
+          constexpr int FB = HD == 128 ? 8 : 4;  // loads in flight per lane and member: what the register budget allows
+          for (int tb = 0; tb < n_traj_w; ++tb) {
+            const int p = p0 + qf * tpw + tb;
+            if (p % md.E != e) continue;
+            costdev::fused_wait(fc, p, lane);
+            const float* srow = ra.start_obs + (size_t)(p / ra.traj_per_start) * O;
+            const float* grow = ra.goal + (size_t)(p / ra.traj_per_goal) * md.G;
+            if (md.E <= 5) costdev::fused_reduce<5, FB>(fc, p, lane, srow, grow, envbuf);
+            else costdev::fused_reduce<kMaxEnsemble, 4>(fc, p, lane, srow, grow, envbuf);
+          }
+        }
+    }
   }
   // ---- teardown ----
   tc_fence_before();
@@ -654,6 +715,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
 }
 
 
+#ifdef CEEUS_DEBUG_TOOLS
 // ---- epilogue micro-benchmark: the hidden-layer epilogue alone (no barriers), 1..3 warps per scheduler; optionally one
 // extra warp keeps the tensor core busy with back-to-back MMAs into other TMEM columns (with_mma) ----
 template <int NWG>
@@ -713,6 +775,8 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) epi_bench_kernel(long long*
   __syncthreads();
   if (warp == 0) tmem_dealloc<1>(tmem_slot, 512);
 }
+
+#endif  // CEEUS_DEBUG_TOOLS
 
 // ---- weight packing ------------------------------------------------------------------------------------------
 __device__ __forceinline__ const LayerDesc& mat_layer(const ModelDesc& md, int m) {
@@ -870,6 +934,7 @@ __global__ void tc_image_kernel(const float* __restrict__ w32, const ModelDesc m
 
 }  // namespace
 
+#ifdef CEEUS_DEBUG_TOOLS
 cudaError_t launch_epi_bench(int nwg, int with_bias, int with_mma, long long* out_dev) {
   const int smem = 65536;
   switch (nwg) {
@@ -888,6 +953,8 @@ cudaError_t launch_epi_bench(int nwg, int with_bias, int with_mma, long long* ou
   }
   return cudaGetLastError();
 }
+
+#endif  // CEEUS_DEBUG_TOOLS
 
 bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_host) {
   TcLayout t{};
@@ -1003,23 +1070,31 @@ cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout
 
 template <int HD, bool RELU>
 static cudaError_t launch_tc_n(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
-                               const float* wpar, int* err_flag, long long* dbg, bool all_fold, cudaStream_t st) {
+                               const float* wpar, int* err_flag, long long* dbg, bool all_fold, const costdev::FusedCost& fc,
+                               cudaStream_t st) {
   auto kern = rollout_gnn_tc_kernel<HD, RELU, false, false>;
+  if (RELU && all_fold) kern = rollout_gnn_tc_kernel<HD, RELU, false, RELU>;
+#ifdef CEEUS_DEBUG_TOOLS  // the timeline-probe instantiations exist only in the debug build
   if (dbg != nullptr) kern = (RELU && all_fold) ? rollout_gnn_tc_kernel<HD, RELU, true, RELU> : rollout_gnn_tc_kernel<HD, RELU, true, false>;
-  else if (RELU && all_fold) kern = rollout_gnn_tc_kernel<HD, RELU, false, RELU>;
+#endif
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
   if (e != cudaSuccess) return e;
-  kern<<<dim3(2 * tl.pairs), 128 * TcSlots<HD>::value, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg);
+  kern<<<dim3(2 * tl.pairs), 128 * TcSlots<HD>::value, tl.smem_bytes, st>>>(md, ra, tl, wimg, wpar, err_flag, dbg, fc);
   return cudaGetLastError();
 }
 
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
-                                  const float* wpar, int* err_flag, long long* dbg, bool all_fold, cudaStream_t st) {
+                                  const float* wpar, int* err_flag, long long* dbg, bool all_fold, const costdev::FusedCost& fc,
+                                  cudaStream_t st) {
   const bool relu = md.act == CEEUS_ACT_RELU;
-  if (md.Hd == 128) return relu ? launch_tc_n<128, true>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st)
-                                : launch_tc_n<128, false>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st);
-  return relu ? launch_tc_n<64, true>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st)
-              : launch_tc_n<64, false>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, st);
+#ifdef CEEUS_TC_FAST_COMPILE  // development aid (register / spill checks): only the ReLU instantiations
+  if (md.Hd == 128) return launch_tc_n<128, true>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, fc, st);
+  return launch_tc_n<64, true>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, fc, st);
+#endif
+  if (md.Hd == 128) return relu ? launch_tc_n<128, true>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, fc, st)
+                                : launch_tc_n<128, false>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, fc, st);
+  return relu ? launch_tc_n<64, true>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, fc, st)
+              : launch_tc_n<64, false>(md, ra, tl, wimg, wpar, err_flag, dbg, all_fold, fc, st);
 }
 
 }  // namespace ceeus

@@ -6,6 +6,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "debug_tools.h"
 #include "tc_common.cuh"
 
 namespace ceeus {

@@ -3,6 +3,7 @@
 PyTorch is plumbing here (device memory, streams, torch.distributed); all arithmetic happens in the CUDA library.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -40,7 +41,7 @@ class Engine:
     def __init__(self, *, env, model_kind, ensemble_size, hidden_dim, num_layers, act_fn, layer_norm, aggr_fn="mean",
                  horizon, num_traj, sampler=None, cost_along_trajectory="sum", curiosity=True, extrinsic_reward=False,
                  extrinsic_reward_scale=1.0, num_envs=1, world_size=1, rank=0, precision="fp32", seed=0,
-                 device=None):
+                 device=None, cost_in_rollout_tail=False):
         if not torch.cuda.is_available():
             raise RuntimeError("ceeus_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -95,6 +96,7 @@ class Engine:
         for name in ("coord_weights", "buffer_xyz", "cost_thres", "gripper_init"):
             getattr(cfg, name)[:] = [float(v) for v in d[name]]
         cfg.world_size, cfg.rank, cfg.seed = world_size, rank, seed
+        cfg.cost_in_rollout_tail = int(bool(cost_in_rollout_tail))
         self.cfg = cfg
         self.model_kind, self.num_layers, self.layer_norm = model_kind, num_layers, bool(layer_norm)
         self.handle = C.c_void_p()
@@ -109,7 +111,12 @@ class Engine:
         self.mean_ = torch.zeros(nE, H, U, **f32)
         self.std_ = torch.ones(nE, H, U, **f32)
         self.actions_ = torch.zeros(nE * P, H, U, **f32)
-        self.traj_ = torch.zeros(H + 1, E, nE * P, O, **f32)
+        # full trajectories [H+1,E,nE*P,O] are materialised only on request (predict_n_steps, elite_samples, externally
+        # evaluated task costs): the planner's own rollouts stay in the library's compact scratch and are reduced to costs in
+        # the tail of the rollout kernel
+        self._traj = None
+        self._last_obs_host = None
+        self._needs_traj = self.external_cost or bool(os.environ.get("CEEUS_NO_FUSE"))
         self.costs_per_model_ = torch.zeros(nE, P, E, **f32)
         self.costs_ = torch.zeros(nE, P, **f32)
         self.elite_actions_ = torch.zeros(nE, k, H, U, **f32)
@@ -119,19 +126,39 @@ class Engine:
         self.cand_ = torch.zeros(nE, k, self.rec, **f32)
         self.action_out_ = torch.zeros(nE, U, **f32)
         self.obs_dev_ = torch.zeros(nE, O, **f32)
-        b = _lib.CeeusBuffers()
-        for name, t in (("mean", self.mean_), ("std", self.std_), ("actions", self.actions_), ("traj", self.traj_),
-                        ("costs_per_model", self.costs_per_model_), ("costs", self.costs_),
-                        ("elite_actions", self.elite_actions_), ("elite_costs", self.elite_costs_),
-                        ("elite_cpm", self.elite_cpm_), ("elite_idx", self.elite_idx_), ("cand", self.cand_),
-                        ("action_out", self.action_out_)):
-            setattr(b, name, t.data_ptr())
-        self._bufs = b
-        _lib.check(self.lib.ceeus_bind_buffers(self.handle, C.byref(b)), self.handle)
+        self._bind()
         lo, hi = np.ascontiguousarray(d["action_low"]), np.ascontiguousarray(d["action_high"])
         _lib.check(self.lib.ceeus_set_action_bounds(self.handle, lo.ctypes.data_as(C.c_void_p),
                                                     hi.ctypes.data_as(C.c_void_p)), self.handle)
         self.weights_version = None
+
+    def _bind(self):
+        if self._needs_traj and self._traj is None:
+            self._traj = torch.zeros(self.H + 1, self.E, self.nE * self.P, self.O, device=self.device, dtype=torch.float32)
+        b = _lib.CeeusBuffers()
+        for name, t in (("mean", self.mean_), ("std", self.std_), ("actions", self.actions_), ("traj", self._traj),
+                        ("costs_per_model", self.costs_per_model_), ("costs", self.costs_),
+                        ("elite_actions", self.elite_actions_), ("elite_costs", self.elite_costs_),
+                        ("elite_cpm", self.elite_cpm_), ("elite_idx", self.elite_idx_), ("cand", self.cand_),
+                        ("action_out", self.action_out_)):
+            setattr(b, name, t.data_ptr() if t is not None else None)
+        self._bufs = b
+        _lib.check(self.lib.ceeus_bind_buffers(self.handle, C.byref(b)), self.handle)
+
+    @property
+    def traj_(self):
+        """The full-trajectory buffer [H+1,E,nE*P,O] (allocated on first use; rollout() without `out` writes here)."""
+        if self._traj is None:
+            self._needs_traj = True
+            self._bind()
+        return self._traj
+
+    def materialise(self):
+        """Full trajectories of the planner's CURRENT population (actions_) from the current observation(s) obs_dev_ -- what
+        the reference keeps in all_observations_ / all_next_observations_ after simulate_trajectories (mpc_torch.py:139-157)."""
+        if self._last_obs_host is not None:  # plan_step() keeps the observation in the library's own staging buffer
+            self.obs_dev_.copy_(torch.from_numpy(self._last_obs_host))
+        return self.rollout(self.obs_dev_, self.actions_)
 
     def close(self):
         if getattr(self, "handle", None):
@@ -218,6 +245,7 @@ class Engine:
     def plan_step(self, obs, noise=None):
         """obs: host float32 [nE,O] (or [O]); returns host float32 [nE,U].  One H2D + one D2H inside."""
         obs = np.ascontiguousarray(np.asarray(obs, np.float32).reshape(self.nE, self.O))
+        self._last_obs_host = obs
         out = np.empty((self.nE, self.U), np.float32)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ceeus_plan_step(self.handle, obs.ctypes.data_as(C.c_void_p),

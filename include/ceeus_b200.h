@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define CEEUS_ABI_VERSION 2
+#define CEEUS_ABI_VERSION 3
 
 enum {
   CEEUS_OK = 0,
@@ -123,6 +123,12 @@ typedef struct CeeusConfig {
   /* ---- multi GPU: trajectories are sharded, rank r owns global indices [r*P, (r+1)*P) of every env ---- */
   int32_t world_size;
   int32_t rank;
+  /* ---- where the planner's trajectory costs are reduced (built-in costs; predictions live in a compact scratch either way) ----
+   * 0: by a separate one-warp-per-trajectory launch after the rollout (64 warps per SM hide the L2 / HBM latency);
+   * 1: in the tail of the rollout kernel itself, by the warps of member p % E once all E members of trajectory p have arrived
+   *    (no extra launch; measured slower on B200 at the BASELINE sizes) */
+  int32_t cost_in_rollout_tail;
+  int32_t reserved0;
   uint64_t seed;         /* Philox key of the on-device noise sampler */
 } CeeusConfig;
 
@@ -222,29 +228,8 @@ int ceeus_tc_status(CeeusHandle h);
  * split that keeps the MMA-issuing warp empty (GNN kernel only).  The parity tests assert with it that every tiling branch
  * of the kernels is compared with the oracle. */
 int ceeus_tc_tiling(CeeusHandle h, int n, int32_t* rounds_out /* [E] */, int32_t* uneven_out /* [E] */);
-/* CEEUS_PREC_TC profiling aid: enable=1 makes thread 0 of CTA 0 record (tag, clock64) pairs at every pipeline stage of
- * the next rollouts; out_host (nullable) receives the first n_pairs pairs.  enable=0 releases the buffer. */
-int ceeus_tc_debug_timeline(CeeusHandle h, int enable, long long* out_host, int n_pairs);
-/* Diagnostic: cycles per hidden-layer epilogue (128 columns, LayerNorm + ReLU, TMEM -> TMEM) of one warp when
- * `warps_per_scheduler` (1..3) warps run it concurrently on every SM sub-partition; with_mma = 1 keeps the tensor core busy
- * with back-to-back MMAs from another warp.  cycles_host[0] = cycles per epilogue, [1] = MMAs issued meanwhile. */
-int ceeus_selftest_epilogue(int warps_per_scheduler, int with_bias, int with_mma, long long* cycles_host);
-/* CEEUS_PREC_TC profiling aid (needs ceeus_tc_debug_timeline enabled): flag 1 = slot 1 of every CTA idles. */
-int ceeus_tc_debug_flag(CeeusHandle h, long long flag);
 /* 1 once elites from a previous MPC step exist (controls whether shift noise is consumed) */
 int ceeus_has_elites(CeeusHandle h);
-
-/* Diagnostic: one D[128*cta_group, N] = A[.,K] * Bt[N,K]^T tile (fp16 in, fp32 out) through exactly the tcgen05 / TMEM /
- * mbarrier building blocks of the CEEUS_PREC_TC rollout kernel (cta_group 1 = single CTA, 2 = CTA pair).  Synchronous.
- * status_host: 0 ok, >0 a bounded barrier wait expired, <0 CUDA error.  No reference counterpart (test hook). */
-int ceeus_selftest_umma(int cta_group, const void* a_dev, const void* bt_dev, float* d_dev, int K, int N, int variant,
-                        int* status_host);
-
-/* Diagnostic: cycle counts of TMEM <-> register transfers (tcgen05.ld / tcgen05.st 32x32b.x32) for 1 / 4 / 8 active warps;
- * out_host receives 32 values (see tmem_bench_kernel in csrc/tc_probe.cu).  No reference counterpart (profiling aid). */
-int ceeus_selftest_tmem(long long* out_host);
-/* Diagnostic: latency of one tcgen05.ld / tcgen05.st issued while `nmma` tcgen05.mma are in flight (out_host[0..3]). */
-int ceeus_selftest_tmem_contention(int nmma, long long* out_host);
 
 #ifdef __cplusplus
 }

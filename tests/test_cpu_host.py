@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert declared == set(ceeus_b200._lib.SIGNATURES), declared ^ set(ceeus_b200._lib.SIGNATURES)
     for name in declared:
         assert hasattr(built_lib, name), name
-    assert built_lib.ceeus_abi_version() == ceeus_b200._lib.ABI_VERSION == 2
+    assert built_lib.ceeus_abi_version() == ceeus_b200._lib.ABI_VERSION == 3
 
 
 def test_ctypes_structs_match_c_layout(built_lib):

@@ -252,3 +252,47 @@ def test_mpc_matches_oracle_larger_population():
         np.testing.assert_allclose(a, want, rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(ctrl.mean_.cpu().numpy(), oc.mean_.numpy(), rtol=1e-5, atol=2e-6)
         np.testing.assert_allclose(ctrl.std_.cpu().numpy(), oc.std_.numpy(), rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("tail", [False, True])
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("name,num_envs", [("mpc_gnn_c2_curious", 1), ("mpc_gnn_c6_stack_extr", 1), ("mpc_gnn_c2_task", 1),
+                                           ("mpc_gnn_pg4_curious", 3), ("mpc_mlp_c4_curious", 1),
+                                           ("mpc_gnn_c3_task_coststd", 2)])
+def test_planner_costs_from_compact_scratch_equal_cost_kernel_on_materialised_trajectories(name, num_envs, precision, tail):
+    """The planner never materialises trajectories: the rollout kernel writes only the predicted dims into the library's compact
+    scratch and the costs are reduced from there -- by a one-warp-per-trajectory launch (default) or, with
+    ``cost_in_rollout_tail``, in the tail of the rollout kernel itself (no cost launch at all).  Same arithmetic as ceeus_costs on
+    the fully materialised trajectories of the same population, up to the summation order over the (step, feature) terms."""
+    import ceeus_b200
+
+    c = dict(CASES[name])
+    spec, weights, norms, obs, goal = build_inputs(c)
+    rs = np.random.RandomState(3)
+    obss = np.stack([obs + np.concatenate([0.05 * rs.standard_normal(spec.state_dim), np.zeros(spec.goal_dim)]).astype(np.float32)
+                     for _ in range(num_envs)])
+    goals = np.stack([goal + np.float32(0.01 * i) for i in range(num_envs)])
+    obss[:, spec.state_dim:] = goals
+    env = product_env(c, goal)
+    env.goal = goals if num_envs > 1 else goal
+    model = product_model(c, env, weights, norms, precision=precision)
+    ctrl = product_controller(c, env, model, precision=precision, num_envs=num_envs, seed=5, cost_in_rollout_tail=tail)
+    ctrl.beginning_of_rollout(observation=obss if num_envs > 1 else obss[0], state=None, mode="train")
+    e = ctrl.engine
+    assert not e.external_cost and e._traj is None  # no full-trajectory buffer exists on the planning path
+    e.obs_dev_.copy_(torch.from_numpy(obss))
+    e.set_goal(env.goal)
+    model.push_to(e)
+    l0 = e.kernel_launches()
+    e.plan_iter_local(0)  # sample (device RNG) + rollout with the fused cost tail + top-k
+    launched = e.kernel_launches() - l0
+    fused_cpm, fused_costs = e.costs_per_model_.clone(), e.costs_.clone()
+    traj = e.materialise()  # same population, same start observations -> full [H+1,E,n,O] trajectories
+    cpm, costs = e.costs(traj)
+    assert torch.isfinite(costs).all()
+    assert rel_err(fused_costs.reshape(-1).cpu().numpy(), costs.cpu().numpy()) < 2e-6
+    assert rel_err(fused_cpm.reshape(-1, e.E).cpu().numpy(), cpm.cpu().numpy()) < 2e-6
+    assert launched == (3 if tail else 4), launched  # sample, rollout (+ costs in its tail | + compact cost launch), top-k
+    # arrival counters are self-resetting: a second launch over the same scratch gives the same answer
+    e.plan_iter_local(0)
+    assert torch.equal(e.costs_, fused_costs) and torch.equal(e.costs_per_model_, fused_cpm)  # and the tail is deterministic

@@ -100,7 +100,7 @@ def test_full_size_properties_config2():
     a = ctrl.get_action(obs, None)
     e = ctrl.engine
     assert a.shape == (4,) and np.all(np.abs(a) <= 1.0) and np.all(np.isfinite(a))
-    traj = e.traj_
+    traj = e.materialise()  # the planner itself keeps no trajectories (costs are reduced inside the rollout kernel)
     assert torch.isfinite(traj).all()
     # traj[0] is the start observation for every member / trajectory; every predicted obs carries env.goal
     assert torch.equal(traj[0], torch.from_numpy(obs).to(DEV).expand_as(traj[0]))

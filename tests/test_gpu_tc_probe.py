@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 def run_probe(cg, K, N, variant=0, seed=0):
     import ceeus_b200
 
-    lib = ceeus_b200._lib.load()
+    lib = ceeus_b200._lib.load_probe()
     g = torch.Generator(device="cpu").manual_seed(seed)
     M = 128 * cg
     A = (torch.randn(M, K, generator=g) * 0.5).half().cuda()
