@@ -41,7 +41,7 @@ class CeeusBuffers(C.Structure):
     _fields_ = [("mean", C.c_void_p), ("std", C.c_void_p), ("actions", C.c_void_p), ("traj", C.c_void_p),
                 ("costs_per_model", C.c_void_p), ("costs", C.c_void_p), ("elite_actions", C.c_void_p),
                 ("elite_costs", C.c_void_p), ("elite_cpm", C.c_void_p), ("elite_idx", C.c_void_p),
-                ("cand", C.c_void_p), ("action_out", C.c_void_p)]
+                ("cand", C.c_void_p), ("action_out", C.c_void_p), ("obs", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/ceeus_b200.h declares (tests check the export table)
@@ -69,6 +69,9 @@ SIGNATURES = {
     "ceeus_plan_iter_update": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "ceeus_plan_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ceeus_plan_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ceeus_plan_step_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ceeus_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "ceeus_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ceeus_kernel_launches": (C.c_int64, [C.c_void_p]),
     "ceeus_has_elites": (C.c_int, [C.c_void_p]),
     "ceeus_profile_rollouts": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int]),

@@ -79,6 +79,8 @@ class B200MpcICem:
                               cost_in_rollout_tail=self.backend_params.get("cost_in_rollout_tail", False),
                               **self._extra_engine_kwargs, **kw)
         e = self._engine
+        if world > 1 and self.backend_params.get("c_comm", True) and not e.external_cost:
+            e.comm_init()  # library-side NCCL communicator: the N-rank step is one CUDA-graph launch, like the 1-GPU step
         self.num_elites = e.k
         self.opt_iter = int(e.sampler["opt_iterations"])
         self.mean_, self.std_ = e.mean_[0], e.std_[0]          # [H,U] views of the bound buffers
@@ -149,7 +151,7 @@ class B200MpcICem:
         obs = np.asarray(obs, np.float32)
         single = obs.ndim == 1
         self._last_obs = obs.copy()
-        if e.world_size == 1 and not e.external_cost:
+        if (e.world_size == 1 or e.comm_ready) and not e.external_cost:
             action = e.plan_step(obs, noise)
         else:
             action = self._distributed_step(obs, noise)
@@ -165,6 +167,9 @@ class B200MpcICem:
         and by callers that keep their environments on the GPU)."""
         e = self._engine
         self.forward_model.push_to(e)
+        if (e.world_size == 1 or e.comm_ready) and not e.external_cost:
+            self._iterated = True
+            return e.plan_step_resident(noise)
         per_iter = e.nE * e.P * e.U * e.H
         per_shift = e.nE * e.n_kept * e.U * e.H
         off = 0

@@ -1,5 +1,7 @@
 // C ABI of libceeus_b200.so (see include/ceeus_b200.h): handle, weight hand-off, and the launch sequence of one
 // iCEM planning step.  No CPU fallback: every entry point either enqueues CUDA work or returns an error.
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +20,43 @@ using namespace ceeus;
 
 namespace {
 std::string g_create_error;
+
+// ---- NCCL, bound at run time ---------------------------------------------------------------------------------------------
+// The library is dlopen'ed (the copy torch has already loaded into the process, if any) so that libceeus_b200.so has no link-time
+// dependency on it; only the five entry points below are used.  Prototypes as in nccl.h (stable across NCCL 2.x).
+struct NcclApi {
+  using Comm = void*;
+  struct UniqueId { char internal[128]; };
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int /* ncclDataType_t */, Comm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(Comm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+constexpr int kNcclFloat32 = 7;
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* lib = nullptr;
+  if (const char* path = std::getenv("CEEUS_NCCL_LIB")) lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // the copy already in the process (torch)
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { api.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return api; }
+  auto sym = [&](const char* n) { return dlsym(lib, n); };
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+  if (!api.ok) api.why = "libnccl.so.2 lacks an expected symbol";
+  return api;
+}
 
 struct TensorSpec {
   int rows, cols;  // per member
@@ -60,6 +99,10 @@ struct CeeusHandle_t {
   bool l2_discard = true;   // CEEUS_NO_DISCARD=1: keep the consumed prediction blocks in L2 (write-back on eviction)
   long long* d_tc_dbg = nullptr;  // optional timeline of one warpgroup (ceeus_tc_debug_timeline)
   CeeusBuffers bufs{};
+  // multi-GPU: NCCL communicator over the ranks that share the trajectories of one planning problem (ceeus_comm_init) and the
+  // gathered candidate records of all ranks [world,nE,k,rec]
+  void* comm = nullptr;
+  float* d_cand_all = nullptr;
   bool bound = false, weights_set = false, norms_set = false;
   bool has_elites = false;
   unsigned long long* d_step_ctr = nullptr;  // MPC steps planned so far (base of the Philox stream ids), lives on the device
@@ -67,8 +110,9 @@ struct CeeusHandle_t {
   // ceeus_plan_step as a CUDA graph: [0] first step after begin_rollout (no elites to shift), [1] steady state
   cudaStream_t gstream = nullptr;
   cudaEvent_t gevent = nullptr;
-  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
-  int64_t graph_launches[2] = {0, 0};
+  // [has elites][0: host observation in / host action out, 1: observation resident in bufs.obs, action left in bufs.action_out]
+  cudaGraphExec_t graph_exec[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  int64_t graph_launches[2][2] = {{0, 0}, {0, 0}};
   bool capturing = false;
   // optional CUDA-event pairs around every rollout launch of the eager path (ceeus_profile_rollouts): in-step kernel time
   std::vector<cudaEvent_t> prof_ev;
@@ -336,15 +380,18 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
 
 static void drop_graphs(CeeusHandle h) {
   for (int i = 0; i < 2; ++i)
-    if (h->graph_exec[i]) {
-      cudaGraphExecDestroy(h->graph_exec[i]);
-      h->graph_exec[i] = nullptr;
-    }
+    for (int j = 0; j < 2; ++j)
+      if (h->graph_exec[i][j]) {
+        cudaGraphExecDestroy(h->graph_exec[i][j]);
+        h->graph_exec[i][j] = nullptr;
+      }
 }
 
 void ceeus_destroy(CeeusHandle h) {
   if (!h) return;
   drop_graphs(h);
+  if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+  cudaFree(h->d_cand_all);
   if (h->gstream) cudaStreamDestroy(h->gstream);
   if (h->gevent) cudaEventDestroy(h->gevent);
   for (auto e : h->prof_ev) if (e) cudaEventDestroy(e);
@@ -652,11 +699,17 @@ int ceeus_plan_finish(CeeusHandle h, void* stream) {
 }
 
 // The launch sequence of one MPC step on `stream` (shared by the eager path and the graph capture).
-static int enqueue_plan_step(CeeusHandle h, const float* noise_dev_or_null, void* stream) {
+// resident: the observation is already in bufs.obs and the action stays in bufs.action_out (no host copies).
+static int enqueue_plan_step(CeeusHandle h, const float* noise_dev_or_null, void* stream, bool resident) {
   const CeeusConfig& c = h->cfg;
   cudaStream_t st = S(stream);
-  const size_t ob = (size_t)c.num_envs * h->md.O * sizeof(float);
-  CU_CHECK(h, cudaMemcpyAsync(h->d_obs, h->h_obs, ob, cudaMemcpyHostToDevice, st));
+  const float* obs_dev = h->d_obs;
+  if (resident) {
+    obs_dev = h->bufs.obs;
+  } else {
+    const size_t ob = (size_t)c.num_envs * h->md.O * sizeof(float);
+    CU_CHECK(h, cudaMemcpyAsync(h->d_obs, h->h_obs, ob, cudaMemcpyHostToDevice, st));
+  }
   const size_t per_iter = (size_t)c.num_envs * c.num_traj * h->md.U * c.horizon;
   const size_t per_shift = (size_t)c.num_envs * c.num_kept * h->md.U * c.horizon;
   const float* np = noise_dev_or_null;
@@ -670,59 +723,128 @@ static int enqueue_plan_step(CeeusHandle h, const float* noise_dev_or_null, void
         np += per_shift;
       }
     }
-    if (int rc = ceeus_plan_iter_local(h, i, h->d_obs, ni, ns, stream)) return rc;
-    if (int rc = ceeus_plan_iter_update(h, i, h->bufs.cand, stream)) return rc;
+    if (int rc = ceeus_plan_iter_local(h, i, obs_dev, ni, ns, stream)) return rc;
+    const float* cand_all = h->bufs.cand;
+    if (c.world_size > 1) {
+      // the ranks' k best candidates -> every rank (a few KB, latency bound); captured into the step's CUDA graph like any kernel
+      const size_t cnt = (size_t)c.num_envs * c.num_elites * ceeus_cand_record_len(h);
+      const int nr = nccl().AllGather(h->bufs.cand, h->d_cand_all, cnt, kNcclFloat32, h->comm, st);
+      if (nr != 0) return fail(h, CEEUS_ERR_CUDA, std::string("ncclAllGather: ") + nccl().GetErrorString(nr));
+      h->launches += 1;
+      cand_all = h->d_cand_all;
+    }
+    if (int rc = ceeus_plan_iter_update(h, i, cand_all, stream)) return rc;
   }
   if (int rc = ceeus_plan_finish(h, stream)) return rc;
-  const size_t ab = (size_t)c.num_envs * h->md.U * sizeof(float);
-  CU_CHECK(h, cudaMemcpyAsync(h->h_action, h->bufs.action_out, ab, cudaMemcpyDeviceToHost, st));
+  if (!resident) {
+    const size_t ab = (size_t)c.num_envs * h->md.U * sizeof(float);
+    CU_CHECK(h, cudaMemcpyAsync(h->h_action, h->bufs.action_out, ab, cudaMemcpyDeviceToHost, st));
+  }
   if (h->d_tc_err) CU_CHECK(h, cudaMemcpyAsync(h->h_tc_err, h->d_tc_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  return CEEUS_OK;
+}
+
+// One MPC step as ONE CUDA-graph launch on the handle's own stream (device RNG).  Nothing in the sequence depends on host state
+// except "are there elites to shift" (two graphs per variant); the Philox stream base is a device counter.
+static int launch_plan_graph(CeeusHandle h, cudaStream_t caller, bool resident, bool sync) {
+  const int v = h->has_elites ? 1 : 0, r = resident ? 1 : 0;
+  if (plan_fuses_costs(h))
+    if (int rc = ensure_plan_scratch(h)) return rc;
+  if (!h->graph_exec[v][r]) {
+    cudaGraph_t g = nullptr;
+    const int64_t l0 = h->launches;
+    h->capturing = true;
+    CU_CHECK(h, cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed));
+    const int rc = enqueue_plan_step(h, nullptr, h->gstream, resident);
+    const cudaError_t ce = cudaStreamEndCapture(h->gstream, &g);
+    h->capturing = false;
+    h->graph_launches[v][r] = h->launches - l0;
+    h->launches = l0;
+    if (rc != CEEUS_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    CU_CHECK(h, ce);
+    const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec[v][r], g, 0);
+    cudaGraphDestroy(g);
+    CU_CHECK(h, ie);
+  }
+  CU_CHECK(h, cudaEventRecord(h->gevent, caller));  // work already queued on the caller's stream (weight repack, obs copy) comes first
+  CU_CHECK(h, cudaStreamWaitEvent(h->gstream, h->gevent, 0));
+  CU_CHECK(h, cudaGraphLaunch(h->graph_exec[v][r], h->gstream));
+  h->launches += h->graph_launches[v][r];
+  h->has_elites = true;
+  if (sync) {
+    CU_CHECK(h, cudaStreamSynchronize(h->gstream));
+  } else {  // the caller's stream continues after the step
+    CU_CHECK(h, cudaEventRecord(h->gevent, h->gstream));
+    CU_CHECK(h, cudaStreamWaitEvent(caller, h->gevent, 0));
+  }
+  return CEEUS_OK;
+}
+
+static int plan_step_checks(CeeusHandle h) {
+  if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
+  if (h->cfg.world_size != 1 && !h->comm)
+    return fail(h, CEEUS_ERR_STATE, "world_size > 1: call ceeus_comm_init first (or drive plan_iter_local / plan_iter_update "
+                                    "yourself with an all-gather of the candidate records in between)");
+  const bool need_env = !h->cd.curiosity || h->cd.extrinsic;
+  if (need_env && h->cd.env_kind == CEEUS_ENV_EXTERNAL)
+    return fail(h, CEEUS_ERR_STATE, "this environment's task cost is evaluated by the caller: use ceeus_plan_iter_rollout / _costs");
   return CEEUS_OK;
 }
 
 int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, const float* noise_dev_or_null, void* stream) {
   if (!h || !obs_host || !action_host) return fail(h, CEEUS_ERR_INVALID, "plan_step: null argument");
-  if (h->cfg.world_size != 1) return fail(h, CEEUS_ERR_INVALID, "plan_step is single-GPU; use plan_iter_local/update with an all-gather");
-  if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
+  if (int rc = plan_step_checks(h)) return rc;
   const CeeusConfig& c = h->cfg;
   cudaStream_t st = S(stream);
   std::memcpy(h->h_obs, obs_host, (size_t)c.num_envs * h->md.O * sizeof(float));
   static const bool no_graph = std::getenv("CEEUS_NO_GRAPH") != nullptr;
   if (noise_dev_or_null == nullptr && !no_graph) {
-    // Device RNG path: the whole step (H2D obs, ~30 kernels, D2H action) is one CUDA graph launch.  Nothing in the sequence
-    // depends on host state except "are there elites to shift" (two graphs); the Philox stream base is a device counter.
-    const int v = h->has_elites ? 1 : 0;
-    if (plan_fuses_costs(h))
-      if (int rc = ensure_plan_scratch(h)) return rc;
-    if (!h->graph_exec[v]) {
-      cudaGraph_t g = nullptr;
-      const int64_t l0 = h->launches;
-      h->capturing = true;
-      CU_CHECK(h, cudaStreamBeginCapture(h->gstream, cudaStreamCaptureModeRelaxed));
-      const int rc = enqueue_plan_step(h, nullptr, h->gstream);
-      const cudaError_t ce = cudaStreamEndCapture(h->gstream, &g);
-      h->capturing = false;
-      h->graph_launches[v] = h->launches - l0;
-      h->launches = l0;
-      if (rc != CEEUS_OK) { if (g) cudaGraphDestroy(g); return rc; }
-      CU_CHECK(h, ce);
-      const cudaError_t ie = cudaGraphInstantiate(&h->graph_exec[v], g, 0);
-      cudaGraphDestroy(g);
-      CU_CHECK(h, ie);
-    }
-    CU_CHECK(h, cudaEventRecord(h->gevent, st));  // work already queued on the caller's stream (weight repack, ...) comes first
-    CU_CHECK(h, cudaStreamWaitEvent(h->gstream, h->gevent, 0));
-    CU_CHECK(h, cudaGraphLaunch(h->graph_exec[v], h->gstream));
-    h->launches += h->graph_launches[v];
-    h->has_elites = true;
-    CU_CHECK(h, cudaStreamSynchronize(h->gstream));
+    if (int rc = launch_plan_graph(h, st, false, true)) return rc;
   } else {
-    if (int rc = enqueue_plan_step(h, noise_dev_or_null, stream)) return rc;
+    if (int rc = enqueue_plan_step(h, noise_dev_or_null, stream, false)) return rc;
+    if (!h->capturing) h->has_elites = true;
     CU_CHECK(h, cudaStreamSynchronize(st));
   }
   if (h->d_tc_err && *h->h_tc_err != 0)
     return fail(h, CEEUS_ERR_CUDA, "tensor-core rollout kernel reported protocol error " + std::to_string(*h->h_tc_err));
   std::memcpy(action_host, h->h_action, (size_t)c.num_envs * h->md.U * sizeof(float));
+  return CEEUS_OK;
+}
+
+int ceeus_plan_step_resident(CeeusHandle h, const float* noise_dev_or_null, void* stream) {
+  if (!h) return CEEUS_ERR_INVALID;
+  if (int rc = plan_step_checks(h)) return rc;
+  if (!h->bufs.obs) return fail(h, CEEUS_ERR_STATE, "plan_step_resident: no observation buffer bound (CeeusBuffers.obs)");
+  static const bool no_graph = std::getenv("CEEUS_NO_GRAPH") != nullptr;
+  // (with ceeus_profile_rollouts on, the step is enqueued kernel by kernel so that the event pairs around the rollouts exist)
+  if (noise_dev_or_null == nullptr && !no_graph && !h->prof_on) return launch_plan_graph(h, S(stream), true, false);
+  if (int rc = enqueue_plan_step(h, noise_dev_or_null, stream, true)) return rc;
+  h->has_elites = true;
+  return CEEUS_OK;
+}
+
+int ceeus_comm_unique_id(uint8_t* id_out) {
+  if (!id_out) return fail(nullptr, CEEUS_ERR_INVALID, "comm_unique_id: null argument");
+  if (!nccl().ok) return fail(nullptr, CEEUS_ERR_CUDA, nccl().why);
+  NcclApi::UniqueId id;
+  const int nr = nccl().GetUniqueId(&id);
+  if (nr != 0) return fail(nullptr, CEEUS_ERR_CUDA, std::string("ncclGetUniqueId: ") + nccl().GetErrorString(nr));
+  std::memcpy(id_out, id.internal, sizeof(id.internal));
+  return CEEUS_OK;
+}
+
+int ceeus_comm_init(CeeusHandle h, const uint8_t* unique_id) {
+  if (!h || !unique_id) return fail(h, CEEUS_ERR_INVALID, "comm_init: null argument");
+  if (h->cfg.world_size < 2) return fail(h, CEEUS_ERR_INVALID, "comm_init: the handle was created with world_size 1");
+  if (!nccl().ok) return fail(h, CEEUS_ERR_CUDA, nccl().why);
+  if (h->comm) return CEEUS_OK;
+  NcclApi::UniqueId id;
+  std::memcpy(id.internal, unique_id, sizeof(id.internal));
+  const int nr = nccl().CommInitRank(&h->comm, h->cfg.world_size, id, h->cfg.rank);
+  if (nr != 0) { h->comm = nullptr; return fail(h, CEEUS_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl().GetErrorString(nr)); }
+  const size_t cnt = (size_t)h->cfg.world_size * h->cfg.num_envs * h->cfg.num_elites * ceeus_cand_record_len(h);
+  CU_CHECK(h, cudaMalloc(&h->d_cand_all, cnt * sizeof(float)));
+  drop_graphs(h);
   return CEEUS_OK;
 }
 

@@ -115,6 +115,7 @@ class Engine:
         # evaluated task costs): the planner's own rollouts stay in the library's compact scratch and are reduced to costs in
         # the tail of the rollout kernel
         self._traj = None
+        self.comm_ready = False
         self._last_obs_host = None
         self._needs_traj = self.external_cost or bool(os.environ.get("CEEUS_NO_FUSE"))
         self.costs_per_model_ = torch.zeros(nE, P, E, **f32)
@@ -140,7 +141,7 @@ class Engine:
                         ("costs_per_model", self.costs_per_model_), ("costs", self.costs_),
                         ("elite_actions", self.elite_actions_), ("elite_costs", self.elite_costs_),
                         ("elite_cpm", self.elite_cpm_), ("elite_idx", self.elite_idx_), ("cand", self.cand_),
-                        ("action_out", self.action_out_)):
+                        ("action_out", self.action_out_), ("obs", self.obs_dev_)):
             setattr(b, name, t.data_ptr() if t is not None else None)
         self._bufs = b
         _lib.check(self.lib.ceeus_bind_buffers(self.handle, C.byref(b)), self.handle)
@@ -251,6 +252,31 @@ class Engine:
             _lib.check(self.lib.ceeus_plan_step(self.handle, obs.ctypes.data_as(C.c_void_p),
                                                 out.ctypes.data_as(C.c_void_p), _ptr(noise), _stream()), self.handle)
         return out
+
+    def plan_step_resident(self, noise=None):
+        """One MPC step with the observation already in ``obs_dev_`` and the action left in ``action_out_``: one CUDA-graph
+        launch (device RNG), no host copy, no host synchronisation."""
+        self._last_obs_host = None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ceeus_plan_step_resident(self.handle, _ptr(noise), _stream()), self.handle)
+        return self.action_out_
+
+    def comm_init(self, group=None):
+        """Collective over the ranks of ``group``: creates the NCCL communicator of the library (the id travels through
+        torch.distributed).  Afterwards plan_step / plan_step_resident are one graph launch at any world size."""
+        import torch.distributed as dist
+
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_uint8 * 128)()
+            _lib.check(self.lib.ceeus_comm_unique_id(buf), None)
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        ident = ident.to(self.device) if dist.get_backend(group) == "nccl" else ident
+        dist.broadcast(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = (C.c_uint8 * 128)(*ident.cpu().tolist())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ceeus_comm_init(self.handle, raw), self.handle)
+        self.comm_ready = True
 
     def plan_iter_local(self, it, noise=None, shift_noise=None):
         with torch.cuda.device(self.device):

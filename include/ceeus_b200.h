@@ -139,7 +139,9 @@ typedef struct CeeusBuffers {
   float* mean;            /* [nE,H,U]            TorchMpcICem.mean_ */
   float* std;             /* [nE,H,U]            TorchMpcICem.std_ */
   float* actions;         /* [nE*P,H,U]          action_sequences of the current iteration (this rank) */
-  float* traj;            /* [H+1,E,nE*P,O]      traj[:-1] = observations, traj[1:] = next_observations */
+  float* traj;            /* [H+1,E,nE*P,O]      traj[:-1] = observations, traj[1:] = next_observations; may be NULL unless the
+                                                 task cost is evaluated by the caller (CEEUS_ENV_EXTERNAL): the planner itself
+                                                 keeps only the predicted dims in a compact scratch of its own */
   float* costs_per_model; /* [nE,P,E]            costs_per_model_ (this rank's fresh samples) */
   float* costs;           /* [nE,P]              costs_ (this rank's fresh samples) */
   float* elite_actions;   /* [nE,k,H,U]          elite_samples["actions"][:,0] */
@@ -148,6 +150,7 @@ typedef struct CeeusBuffers {
   int32_t* elite_idx;     /* [nE,k]              index into the global population of the last iteration */
   float* cand;            /* [nE,k,rec]          this rank's top-k candidate records, rec = ceeus_cand_record_len() */
   float* action_out;      /* [nE,U]              executed action */
+  float* obs;             /* [nE,O]              optional: observation(s) resident on the device (ceeus_plan_step_resident) */
 } CeeusBuffers;
 
 typedef struct CeeusHandle_t* CeeusHandle;
@@ -216,6 +219,21 @@ int ceeus_plan_finish(CeeusHandle h, void* stream);
 int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, const float* noise_dev_or_null,
                     void* stream);
 /* counters for bench.py: kernels launched by this handle since creation */
+/* The same MPC step with the observation(s) already on the device (CeeusBuffers.obs) and the action left in
+ * CeeusBuffers.action_out: no host copy, no host synchronisation; `stream` continues after the step (callers that keep their
+ * environments on the GPU, and the device-timed leg of bench.py). */
+int ceeus_plan_step_resident(CeeusHandle h, const float* noise_dev_or_null, void* stream);
+
+/* ---- multi GPU (one process per GPU) ----
+ * The trajectories of one planning problem are sharded over world_size ranks; per iCEM iteration the ranks exchange their k best
+ * candidate records with one ncclAllGather that is part of the step's CUDA graph, so ceeus_plan_step stays ONE graph launch at any
+ * number of GPUs.  Rank 0 obtains an id with ceeus_comm_unique_id and hands it to the other ranks by any means (the Python layer
+ * broadcasts it through torch.distributed); every rank then calls ceeus_comm_init (collective).  NCCL is bound at run time
+ * (dlopen of libnccl.so.2, preferably the copy already loaded into the process; CEEUS_NCCL_LIB overrides the path).
+ * Reference precedent for sharding trajectories over workers: ParallelGroundTruthModel.predict_n_steps, mbrl/models/gt_par_model.py:91-128. */
+int ceeus_comm_unique_id(uint8_t* id_out /* [128] */);
+int ceeus_comm_init(CeeusHandle h, const uint8_t* unique_id /* [128] */);
+
 int64_t ceeus_kernel_launches(CeeusHandle h);
 /* Measurement aid: with enable != 0 every rollout launch of the eager path (ceeus_rollout, ceeus_plan_iter_*) is bracketed by
  * a CUDA-event pair on its launch stream (up to 256 launches between two reads).  Each call first copies the durations (ms) of
