@@ -40,11 +40,11 @@ CONFIGS = {
                 sampler={})),
     "c3": ("construction N=6 (30 edges) GNN ensemble, stack task cost + disagreement, best, P=2048/GPU, H=30 (BASELINE configs[2])",
            dict(env="construction", n_obj=6, model="gnn", hidden=128, layers=2, P=2048, H=30, curiosity=True,
-                extrinsic=True, cost="best", sampler=dict(init_std=0.5, use_mean_actions=False))),
+                extrinsic=True, cost="best", sampler=dict(init_std=0.5, use_mean_actions=False), strong_total_traj=16384)),
     "c4": ("playground N=4 GNN ensemble Hd=64, 8 envs x 1024 traj per GPU, H=30 (BASELINE configs[3])",
            dict(env="playground", n_obj=4, model="gnn", hidden=64, layers=2, P=1024, H=30, curiosity=True, cost="sum",
-                num_envs=8, sampler=dict(keep_previous_elites=False, shift_elites_over_time=False,
-                                         fraction_elites_reused=0.1))),
+                num_envs=8, strong_total_envs=64,
+                sampler=dict(keep_previous_elites=False, shift_elites_over_time=False, fraction_elites_reused=0.1))),
     "c5": ("construction N=4 dense-MLP ensemble 62-256x3-58 SiLU, P=8192/GPU, H=30 (BASELINE configs[4])",
            dict(env="construction", n_obj=4, model="mlp", hidden=256, layers=3, P=8192, H=30, curiosity=True, cost="sum",
                 sampler={})),
@@ -208,6 +208,25 @@ def _cpu_measure(c, w, steps, warm, budget_s):
 
 
 # ---- GPU arm ------------------------------------------------------------------------------------------------------
+def shard(c, world, scaling):
+    """-> (case dict for one rank, trajectories are sharded?).  weak: every GPU keeps the config's per-GPU population.
+    strong: BASELINE.json's TOTAL population (c3: 16384 trajectories; c4: 64 environments x 1024; others: N=1 size) is split over
+    the GPUs -- trajectories of ONE planning problem are sharded with a candidate all-gather per iteration, whole environments
+    are sharded without any collective (each rank plans its own)."""
+    c = dict(c)
+    if scaling == "strong":
+        if c.get("num_envs", 1) > 1:
+            total_envs = c.get("strong_total_envs", c["num_envs"])
+            assert total_envs % world == 0
+            c["num_envs"] = total_envs // world
+            return c, False
+        total = c.get("strong_total_traj", c["P"])
+        assert total % world == 0
+        c["P"] = total // world
+        return c, world > 1
+    return c, world > 1 and c.get("num_envs", 1) == 1
+
+
 def make_controller(c, w, world, precision, seed=1234):
     import ceeus_b200
 
@@ -226,19 +245,23 @@ def make_controller(c, w, world, precision, seed=1234):
     model.set_normalizers(w["norms"])
     kw = dict(env=env, forward_model=model, horizon=c["H"], num_simulated_trajectories=c["P"] * world,
               action_sampler_params=sampler_of(c), cost_along_trajectory=c.get("cost", "sum"), logging=False,
-              backend_params=dict(precision=precision, seed=seed, num_envs=nenv))
+              backend_params=dict(precision=precision, seed=seed, num_envs=nenv, distributed=world > 1))
     if c.get("curiosity", True):
         return ceeus_b200.B200CuriosityMpcICem(extrinsic_reward=c.get("extrinsic", False), **kw)
     return ceeus_b200.B200MpcICem(**kw)
 
 
-def gpu_measure(name, steps, warmup, precision, world, rank, dev, flush, dist):
+def gpu_measure(name, steps, warmup, precision, world, rank, dev, flush, dist, scaling="weak"):
     """-> dict with the device-timed value, the end-to-end value through get_action (host obs in, host action out) and the
     roofline of the rollout kernel timed inside the steps.  All times are CUDA-event times, max over ranks."""
     desc, c = CONFIGS[name]
+    c, traj_sharded = shard(c, world, scaling)
     w = build_workload(c)
     nenv = c.get("num_envs", 1)
-    ctrl = make_controller(c, w, world, precision)
+    if not traj_sharded and world > 1:
+        w["obs"] = w["obs"].copy()
+        w["obs"][:2] += np.float32(0.01 * rank)  # env-sharded ranks plan different problems
+    ctrl = make_controller(c, w, world if traj_sharded else 1, precision, seed=1234 + (0 if traj_sharded else rank))
     eng = ctrl.engine
     obs_b = w["obs"] if nenv == 1 else np.tile(w["obs"], (nenv, 1))
     ctrl.beginning_of_rollout(observation=obs_b, state=None, mode="train")
@@ -282,7 +305,7 @@ def gpu_measure(name, steps, warmup, precision, world, rank, dev, flush, dist):
         ctrl.get_action(obs_b, None)
     e2e_ms = max_over_ranks(timed(lambda: ctrl.get_action(obs_b, None), steps))
     agree = None
-    if world > 1:  # every rank must have planned the same action and the same refitted distribution
+    if world > 1 and traj_sharded:  # every rank must have planned the same action and the same refitted distribution
         d = 0.0
         for t in (eng.action_out_, eng.mean_, eng.std_):
             ref = t.clone()
@@ -311,7 +334,9 @@ def gpu_measure(name, steps, warmup, precision, world, rank, dev, flush, dist):
         "dtype": "f32" if not tc_mode else "f16 operands, f32 accumulate",
         "config": {"workload": desc, "global_traj": c["P"] * nenv * world, "traj_per_gpu": c["P"] * nenv, "horizon": c["H"],
                    "ensemble": E, "icem_iters": ITERS, "num_envs": nenv, "precision": precision,
-                   "parallelism": f"traj-sharded x{world}",
+                   "parallelism": (f"traj-sharded x{world} (one candidate all-gather per iteration inside the step's CUDA graph)"
+                                   if traj_sharded else f"env-sharded x{world} (no collective)") if world > 1 else "single GPU",
+                   "scaling": scaling,
                    "l2": "256 MiB buffer written between timed steps (outside the timed interval)"},
         "e2e": {"value": msteps_gpu * world / (e2e_ms / steps / 1e3), "unit": "model-steps/s", "ms_per_step": e2e_ms / steps,
                 "h2d_bytes_per_step": int(obs_b.size * 4), "d2h_bytes_per_step": int(nenv * eng.U * 4)},
@@ -342,6 +367,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-per-config", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=0.0, help="wall-clock budget of a CPU leg (0 = default)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: BASELINE.json's total population (c3: 16384 trajectories, c4: 64 environments) split over the GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.precision == "auto":
@@ -387,7 +414,8 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    main_out, c, w = gpu_measure(args.config, args.steps, args.warmup, args.precision, world, rank, dev, flush, dist)
+    main_out, c, w = gpu_measure(args.config, args.steps, args.warmup, args.precision, world, rank, dev, flush, dist,
+                                 args.scaling)
     per = {}
     if world == 1 and not args.no_per_config:
         for name in sorted(CONFIGS):
@@ -406,6 +434,7 @@ def main():
         return
     out = dict(base)
     out.update(main_out)
+    out["scaling"] = args.scaling
     out["clocks"] = clocks
     if not args.no_cpu_baseline:
         r = cpu_measure(c, w, 3, 1, args.cpu_budget_s or 25.0)

@@ -178,6 +178,25 @@ class _B200Ensemble:
         idx = torch.arange(E, device=nxt.device)
         return nxt[idx, idx], None, None
 
+    def rollout_field_names(self):
+        return "observations", "next_observations", "actions", "rewards"  # abstract_models.py:29-30
+
+    @torch.no_grad()
+    def rollout_generator(self, start_states, start_observations, horizon, policy, mode=None):
+        """Like the reference's (gnn_ensemble.py:876-901, mlp_ensemble.py:502-528; not a generator there either): fills
+        ``all_observations_ / all_next_observations_ / all_actions_`` ([H,E,P,*]) -- here as views of one CUDA rollout."""
+        buf, _ = self.predict_n_steps(start_observations=torch.as_tensor(start_observations), start_states=start_states,
+                                      policy=policy, horizon=horizon)
+        self.all_observations_ = buf.as_array("observations").permute(2, 1, 0, 3)
+        self.all_next_observations_ = buf.as_array("next_observations").permute(2, 1, 0, 3)
+        self.all_actions_ = buf.as_array("actions").permute(2, 1, 0, 3)
+
+    def get_state(self):
+        return None  # base_types.py:105-109
+
+    def set_state(self, state):
+        pass
+
     def train(self, *a, **k):
         raise NotImplementedError("model training stays with the reference implementation (SURVEY.md section 2 #18); "
                                   "train there and call sync_from(reference_model)")

@@ -1,4 +1,5 @@
-"""Recipe for ``oracle/_ref/``: packs the reference's OWN, unmodified Python package (``/root/reference/mbrl/**/*.py``) into
+"""Recipe for ``oracle/_ref/``: packs the reference's OWN, unmodified Python package (``/root/reference/mbrl/**/*.py``, plus
+the settings yamls under ``experiments/``) into
 ``oracle/_ref/reference_mbrl.zip`` so that ``bench.py --impl reference`` can time the reference itself on the GPU box, where
 ``/root/reference`` does not exist (the archive is git-ignored -- no reference source enters the history -- but not
 gpurun-ignored, so it travels with the snapshot like the built ``.so``).  Imported through ``zipimport`` behind the stub
@@ -20,6 +21,9 @@ def build(reference_root="/root/reference"):
     files = []
     for root, _, names in os.walk(src):
         files += [os.path.join(root, n) for n in names if n.endswith(".py")]
+    # the settings files the boundary tests build the drop-ins from (yaml field names are the reference's API)
+    for root, _, names in os.walk(os.path.join(reference_root, "experiments")):
+        files += [os.path.join(root, n) for n in names if n.endswith(".yaml")]
     files.sort()
     newest = max(os.path.getmtime(f) for f in files)
     if os.path.exists(OUT) and os.path.getmtime(OUT) >= newest:

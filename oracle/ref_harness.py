@@ -30,6 +30,25 @@ def reference_available():
         REFERENCE_ROOT.endswith(".zip") and os.path.isfile(REFERENCE_ROOT))
 
 
+def read_reference_text(relpath):
+    """Text of a file of the reference checkout (path relative to its root), from the tree or from the archive."""
+    if os.path.isdir(REFERENCE_ROOT):
+        return open(os.path.join(REFERENCE_ROOT, relpath)).read()
+    import zipfile
+
+    with zipfile.ZipFile(REFERENCE_ROOT) as z:
+        return z.read(relpath).decode()
+
+
+def reference_has(relpath):
+    if os.path.isdir(REFERENCE_ROOT):
+        return os.path.exists(os.path.join(REFERENCE_ROOT, relpath))
+    import zipfile
+
+    with zipfile.ZipFile(REFERENCE_ROOT) as z:
+        return relpath in z.namelist()
+
+
 _ready = False
 
 
