@@ -30,7 +30,9 @@ class CeeusConfig(C.Structure):
         ("threshold", C.c_float), ("buffer_threshold", C.c_float),
         ("coord_weights", C.c_float * 3), ("buffer_xyz", C.c_float * 3), ("cost_thres", C.c_float * 3),
         ("gripper_init", C.c_float * 3),
-        ("world_size", C.c_int32), ("rank", C.c_int32), ("cost_in_rollout_tail", C.c_int32), ("reserved0", C.c_int32),
+        ("world_size", C.c_int32), ("rank", C.c_int32), ("cost_in_rollout_tail", C.c_int32),
+        ("gnn_variant", C.c_int32), ("edge_global", C.c_int32), ("num_message_passing", C.c_int32),
+        ("embedding_dim", C.c_int32), ("reserved0", C.c_int32),
         ("seed", C.c_uint64)]
 
 

@@ -212,7 +212,11 @@ int validate(const CeeusConfig& c, std::string& why) {
   if (c.hidden_dim != 64 && c.hidden_dim != 128 && c.hidden_dim != 256) return bad("hidden_dim must be 64, 128 or 256");
   if (c.model_kind == CEEUS_MODEL_GNN) {
     if (c.hidden_dim == 256) return bad("GNN hidden_dim must be 64 or 128");
-    if (c.n_obj < 2) return bad("GNN needs n_obj >= 2 (gnn_modules.py:190-241: row undefined for one node)");
+    if (c.n_obj < 2 && c.gnn_variant == 0) return bad("GNN needs n_obj >= 2 (gnn_modules.py:190-241: row undefined for one node)");
+    if (c.gnn_variant != 0 && c.gnn_variant != 1) return bad("gnn_variant");
+    if (c.gnn_variant == 1 && (c.embedding_dim < 1 || c.embedding_dim > 64 || c.n_obj < 1))
+      return bad("homogeneous GNN: embedding_dim must be in [1,64]");
+    if (c.gnn_variant == 1 && (c.n_obj + 1) * c.n_obj > kTileRows) return bad("homogeneous GNN: (N+1) N edges must be <= 64");
     // the fp32 path tiles whole trajectories' edges into 64 rows; the tensor-core path (node-major rows) takes N <= 32
     if (c.precision == CEEUS_PREC_FP32 && c.n_obj * (c.n_obj - 1) > kTileRows) return bad("n_obj too large for fp32 mode: N(N-1) must be <= 64");
     if (c.dyn_dim > 64 || c.agent_dim > 64) return bad("dyn_dim / agent_dim must be <= 64");
@@ -274,9 +278,26 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
   const bool ln = c.layer_norm != 0;
   if (c.model_kind == CEEUS_MODEL_GNN) {
     const int na = c.dyn_dim + c.stat_dim;
-    add_mlp(h, md.mlp[0], 2 * na + c.agent_dim + c.action_dim, c.hidden_dim, c.hidden_dim, c.num_layers, ln, off);
-    add_mlp(h, md.mlp[1], na + c.agent_dim + c.action_dim + c.hidden_dim, c.dyn_dim, c.hidden_dim, c.num_layers, ln, off);
-    add_mlp(h, md.mlp[2], c.agent_dim + c.action_dim + c.hidden_dim, c.agent_dim, c.hidden_dim, c.num_layers, ln, off);
+    md.variant = c.gnn_variant; md.edge_global = c.edge_global; md.n_mp = c.num_message_passing > 0 ? c.num_message_passing : 1;
+    md.emb = c.embedding_dim;
+    if (c.gnn_variant == 0) {
+      // weight order = edge_mlp, node_mlp, global_mlp (, edge_mlp_global)
+      add_mlp(h, md.mlp[0], 2 * na + c.agent_dim + c.action_dim, c.hidden_dim, c.hidden_dim, c.num_layers, ln, off);
+      add_mlp(h, md.mlp[1], na + c.agent_dim + c.action_dim + c.hidden_dim, c.dyn_dim, c.hidden_dim, c.num_layers, ln, off);
+      add_mlp(h, md.mlp[2], c.agent_dim + c.action_dim + c.hidden_dim * (c.edge_global ? 2 : 1), c.agent_dim, c.hidden_dim,
+              c.num_layers, ln, off);
+      if (c.edge_global) add_mlp(h, md.mlp[3], na + c.agent_dim + c.action_dim, c.hidden_dim, c.hidden_dim, c.num_layers, ln, off);
+    } else {
+      // weight order = edge_mlp, node_mlp, embed_agent, embed_obj, output_head_agent, output_head_objdyn (the heads are single
+      // linear layers: num_layers 0, no LayerNorm, gnn_modules.py:351-381)
+      const int F = c.embedding_dim;
+      add_mlp(h, md.mlp[0], 2 * F + c.action_dim, c.hidden_dim, c.hidden_dim, c.num_layers, ln, off);
+      add_mlp(h, md.mlp[1], F + c.action_dim + c.hidden_dim, F, c.hidden_dim, c.num_layers, ln, off);
+      add_mlp(h, md.mlp[2], c.agent_dim, F, c.hidden_dim, 0, false, off);
+      add_mlp(h, md.mlp[3], na, F, c.hidden_dim, 0, false, off);
+      add_mlp(h, md.mlp[4], F, c.agent_dim, c.hidden_dim, 0, false, off);
+      add_mlp(h, md.mlp[5], F, c.dyn_dim, c.hidden_dim, 0, false, off);
+    }
     int o = 0;
     md.nrm.in_agent = o; o += 2 * md.A;
     md.nrm.in_dyn = o; o += 2 * md.D;
@@ -286,6 +307,10 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
     md.nrm.out_dyn = o; o += 2 * md.D;
     h->norm_floats = o;
     const GnnTiling tl = make_gnn_tiling(md);
+    if ((c.gnn_variant != 0 || c.edge_global) && c.precision != CEEUS_PREC_FP32) {
+      delete h;
+      return fail(nullptr, CEEUS_ERR_INVALID, "the homogeneous GNN and ignore_agent_object=false run on the CEEUS_PREC_FP32 path only");
+    }
     if (c.precision == CEEUS_PREC_FP32 && (tl.G < 1 || tl.smem_bytes > 227 * 1024)) {
       delete h;
       return fail(nullptr, CEEUS_ERR_INVALID, "GNN tiling does not fit shared memory");

@@ -39,7 +39,13 @@ struct ModelDesc {
   int sd;  // state dim = A + N (D+S)
   int O;   // obs dim = sd + G
   long long member_stride;  // floats per member in the packed weight buffer
-  MlpDesc mlp[3];           // GNN: edge, node, global; MLP: [0]
+  // GNN, agent as global node: edge, node, global (, edge_mlp_global); homogeneous GNN: edge, node, embed_agent, embed_obj,
+  // output_head_agent, output_head_objdyn; dense MLP: [0]
+  MlpDesc mlp[6];
+  int variant;              // CeeusConfig::gnn_variant
+  int edge_global;          // ignore_agent_object: false
+  int n_mp;                 // message-passing rounds (homogeneous variant)
+  int emb;                  // embedding_dim (homogeneous variant)
   NormDesc nrm;
 };
 

@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_simt_kernel(const
   float* snrm = sraw + G * sd;                 // G * (sd+U) normalised [agent | nodes (dyn,stat) | action]
   float* dn = snrm + G * (sd + U);             // 64 * D     node deltas (normalised)
   float* dg = dn + kTileRows * D;              // G * A      agent deltas (normalised)
+  float* aggN = dg + G * A;                    // G * HD     ignore_agent_object=false: per-trajectory aggregate of edge_mlp_global
 
   const float inv_node = md.aggr_mean ? 1.f / fmaxf((float)(N - 1), 1.f) : 1.f;
   const float inv_glob = md.aggr_mean ? 1.f / fmaxf((float)NE, 1.f) : 1.f;
@@ -374,16 +375,51 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_simt_kernel(const
         gemm_tile<4>(wm + ld.w_off, ld.Kpad, Xn, XSn, Wbuf, acc);
         out_epilogue<4>(acc, wm, ld, dn, D, G * N);
       }
-      // ---- global stage: tile [agent | action | agg_all]  (gnn_modules.py:250-254) ----
+      // ---- ignore_agent_object=false: edge_mlp_global on every node's [node_i | agent | action], aggregated per trajectory over
+      // its N nodes (gnn_modules.py:98-106, 225-238) ----
+      if (md.edge_global) {
+        const int w = NA + A + U;
+        const int kp = md.mlp[3].layer[0].Kpad;
+        for (int idx = tid; idx < kTileRows * kp; idx += kSimtThreads) {
+          const int r = idx / kp, c = idx % kp;
+          const int b = r / N, i = r % N;
+          float v = 0.f;
+          if (r < G * N && c < w) {
+            if (c < NA) v = snrm[b * snw + A + i * NA + c];
+            else if (c < NA + A) v = snrm[b * snw + (c - NA)];
+            else v = snrm[b * snw + sd + (c - NA - A)];
+          }
+          Xe[r * XSe + c] = v;
+        }
+        __syncthreads();
+        mlp_hidden<NCH>(md.mlp[3], wm, md.act, ln, Xe, XSe, Wbuf);
+        {
+          float acc[4][NCH];
+          const LayerDesc& ld = md.mlp[3].layer[md.mlp[3].n_layers - 1];
+          gemm_tile<NCH>(wm + ld.w_off, ld.Kpad, Xe, XSe, Wbuf, acc);
+          hidden_epilogue<NCH>(acc, wm, ld, false, CEEUS_ACT_NONE, Xe, XSe);
+        }
+        const float inv_n = md.aggr_mean ? 1.f / (float)N : 1.f;
+        for (int idx = tid; idx < G * HD; idx += kSimtThreads) {
+          const int b = idx / HD, c = idx % HD;
+          float s = 0.f;
+          for (int i = 0; i < N; ++i) s += Xe[(b * N + i) * XSe + c];
+          aggN[idx] = s * inv_n;
+        }
+        __syncthreads();
+      }
+      // ---- global stage: tile [agent | action | (agg of edge_mlp_global) | agg_all]  (gnn_modules.py:244-254) ----
       {
         const int kp = md.mlp[2].layer[0].Kpad;
+        const int o2 = md.edge_global ? HD : 0;
         for (int idx = tid; idx < kTileRows * kp; idx += kSimtThreads) {
           const int r = idx / kp, c = idx % kp;
           float v = 0.f;
           if (r < G) {
             if (c < A) v = snrm[r * snw + c];
             else if (c < A + U) v = snrm[r * snw + sd + (c - A)];
-            else if (c < A + U + HD) v = aggG[r * HD + (c - A - U)];
+            else if (c < A + U + o2) v = aggN[r * HD + (c - A - U)];
+            else if (c < A + U + o2 + HD) v = aggG[r * HD + (c - A - U - o2)];
           }
           Xe[r * XSe + c] = v;
         }
@@ -425,6 +461,228 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_simt_kernel(const
         }
       }
       // (next iteration starts with reads of sraw only; writes to snrm are ordered by the sync above)
+    }
+    if (fused && fc.done != nullptr) simt_fused_tail(fc, ra, md, p0, Gc, Xe, kTileRows * XSe);
+  }
+}
+
+
+// output layer with an arbitrary destination: f(row, col, value) for the first ld.N columns of the first `rows` rows
+template <int NC, typename F>
+__device__ __forceinline__ void out_epilogue_map(float (&acc)[4][NC], const float* __restrict__ wm, const LayerDesc& ld, int rows, F f) {
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty * 4 + i;
+    if (r < rows) {
+#pragma unroll
+      for (int j = 0; j < NC / 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int col = j * 64 + tx * 4 + c;
+          if (col < ld.N) f(r, col, acc[i][j * 4 + c] + __ldg(wm + ld.b_off + col));
+        }
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Homogeneous GNN rollout (HomogeneousGraphNeuralNetworkEnsemble, gnn_modules.py:281-545; yaml gnn_ensemble_homogeneous.yaml,
+// agent_as_global_node: false): the agent is node 0 of a fully connected graph of M = N + 1 nodes.  Per model step:
+//   features  f_0 = embed_agent(agent), f_{1+i} = embed_obj([dyn_i, stat_i])                      (:351-381, :506-523)
+//   n_mp x {  m_ij = edge_mlp([f_i, f_j, action]);  f_i <- node_mlp([f_i, action, aggr_{j != i} m_ij])  }   (:449-497, :525-526)
+//   d_agent = output_head_agent(f_0), d_dyn_i = output_head_objdyn(f_{1+i})                          (:528-545)
+// grid = (groups, E); a group is G trajectories with G*M <= 64 node rows; edge tiles hold TPT whole trajectories.
+// ------------------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_homog_simt_kernel(const ModelDesc md, const RolloutArgs ra,
+                                                                                  const GnnTiling tl, const costdev::FusedCost fc) {
+  const bool fused = fc.pred != nullptr;
+  constexpr int HD = 16 * NCH;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int e = blockIdx.y;
+  const int N = md.N, A = md.A, D = md.D, S = md.S, U = md.U, sd = md.sd, O = md.O, FD = md.emb;
+  const int NA = D + S, M = N + 1, ME = M * (M - 1);
+  const int G = tl.G, TPT = tl.TPT, XSe = tl.XSe, XSn = tl.XSn;
+  const float* __restrict__ wm = ra.weights + (size_t)e * md.member_stride;
+  const float* __restrict__ nrm = ra.norm;
+
+  float* Wbuf = smem;                          // 2 * kKChunk * HD
+  float* Xe = Wbuf + 2 * kKChunk * HD;         // 64 * XSe   edge tile; also the input tile of the embeddings / output heads
+  float* Xn = Xe + kTileRows * XSe;            // 64 * XSn   node-MLP tile [f_i | action | agg_i]
+  float* Fm = Xn + kTileRows * XSn;            // 64 * FD    node features, row b * M + node
+  float* sraw = Fm + kTileRows * FD;           // G * sd
+  float* snrm = sraw + G * sd;                 // G * (sd+U)
+  float* dn = snrm + G * (sd + U);             // 64 * D
+  float* dg = dn + kTileRows * D;              // G * A
+  const float inv_node = md.aggr_mean ? 1.f / (float)(M - 1) : 1.f;
+  const bool ln = md.layer_norm != 0;
+  const int snw = sd + U;
+
+  for (int grp = blockIdx.x; grp * G < ra.n; grp += gridDim.x) {
+    const int p0 = grp * G;
+    const int Gc = min(G, ra.n - p0);
+    __syncthreads();
+    for (int idx = tid; idx < G * sd; idx += kSimtThreads) {
+      const int b = idx / sd, c = idx % sd;
+      sraw[idx] = b < Gc ? __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c) : 0.f;
+    }
+    for (int idx = tid; idx < (fused ? 0 : Gc * O); idx += kSimtThreads) {
+      const int b = idx / O, c = idx % O;
+      ra.traj[((size_t)e * ra.n + p0 + b) * O + c] = __ldg(ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O + c);
+    }
+    __syncthreads();
+
+    for (int h = 0; h < ra.H; ++h) {
+      // ---- normalise state + action (gnn_ensemble.py:190-243) ----
+      for (int idx = tid; idx < G * snw; idx += kSimtThreads) {
+        const int b = idx / snw, c = idx % snw;
+        float v;
+        if (c < A) {
+          v = (sraw[b * sd + c] - __ldg(nrm + md.nrm.in_agent + c)) / __ldg(nrm + md.nrm.in_agent + A + c);
+        } else if (c < sd) {
+          const int q = c - A, i = q / NA, f = q % NA;
+          if (f < D)
+            v = (sraw[b * sd + A + i * D + f] - __ldg(nrm + md.nrm.in_dyn + f)) / __ldg(nrm + md.nrm.in_dyn + D + f);
+          else
+            v = (sraw[b * sd + A + N * D + i * S + (f - D)] - __ldg(nrm + md.nrm.in_stat + (f - D))) /
+                __ldg(nrm + md.nrm.in_stat + S + (f - D));
+        } else {
+          const int u = c - sd;
+          const float a = b < Gc ? __ldg(ra.actions + ((size_t)(p0 + b) * ra.H + h) * U + u) : 0.f;
+          v = (a - __ldg(nrm + md.nrm.in_action + u)) / __ldg(nrm + md.nrm.in_action + U + u);
+        }
+        snrm[idx] = v;
+      }
+      __syncthreads();
+      // ---- embeddings: f_0 = embed_agent(agent), f_{1+i} = embed_obj(node_i) ----
+      {
+        const LayerDesc& la = md.mlp[2].layer[0];
+        for (int idx = tid; idx < kTileRows * la.Kpad; idx += kSimtThreads) {
+          const int r = idx / la.Kpad, c = idx % la.Kpad;
+          Xe[r * XSe + c] = (r < G && c < A) ? snrm[r * snw + c] : 0.f;
+        }
+        __syncthreads();
+        float acc[4][4];
+        gemm_tile<4>(wm + la.w_off, la.Kpad, Xe, XSe, Wbuf, acc);
+        out_epilogue<4>(acc, wm, la, Fm, M * FD, G);  // row b -> feature row b * M
+        const LayerDesc& lo = md.mlp[3].layer[0];
+        for (int idx = tid; idx < kTileRows * lo.Kpad; idx += kSimtThreads) {
+          const int r = idx / lo.Kpad, c = idx % lo.Kpad;
+          Xe[r * XSe + c] = (r < G * N && c < NA) ? snrm[(r / N) * snw + A + (r % N) * NA + c] : 0.f;
+        }
+        __syncthreads();
+        gemm_tile<4>(wm + lo.w_off, lo.Kpad, Xe, XSe, Wbuf, acc);
+        out_epilogue_map<4>(acc, wm, lo, G * N, [&](int r, int col, float v) { Fm[((r / N) * M + 1 + r % N) * FD + col] = v; });
+      }
+      // ---- message passing ----
+      for (int mp = 0; mp < md.n_mp; ++mp) {
+        // static part of the node tile: [f_i | action]; K padding zeroed
+        {
+          const int w = FD + U;
+          const int kp = md.mlp[1].layer[0].Kpad;
+          for (int idx = tid; idx < kTileRows * w; idx += kSimtThreads) {
+            const int r = idx / w, c = idx % w;
+            float v = 0.f;
+            if (r < G * M) v = c < FD ? Fm[r * FD + c] : snrm[(r / M) * snw + sd + (c - FD)];
+            Xn[r * XSn + c] = v;
+          }
+          for (int idx = tid; idx < kTileRows * (kp - w - HD); idx += kSimtThreads)
+            Xn[(idx / (kp - w - HD)) * XSn + w + HD + idx % (kp - w - HD)] = 0.f;
+        }
+        for (int b0 = 0; b0 < G; b0 += TPT) {
+          const int e_in = 2 * FD + U;
+          const int kp = md.mlp[0].layer[0].Kpad;
+          for (int idx = tid; idx < kTileRows * kp; idx += kSimtThreads) {
+            const int r = idx / kp, c = idx % kp;
+            const int bb = r / ME, q = r % ME, b = b0 + bb;
+            float v = 0.f;
+            if (bb < TPT && b < G && c < e_in) {
+              const int i = q / (M - 1), jj = q % (M - 1);
+              const int j = jj + (jj >= i ? 1 : 0);  // (i asc, j asc, j != i); row = source node i (gnn_modules.py:424-447)
+              if (c < FD) v = Fm[(b * M + i) * FD + c];
+              else if (c < 2 * FD) v = Fm[(b * M + j) * FD + (c - FD)];
+              else v = snrm[b * snw + sd + (c - 2 * FD)];
+            }
+            Xe[r * XSe + c] = v;
+          }
+          __syncthreads();
+          mlp_hidden<NCH>(md.mlp[0], wm, md.act, ln, Xe, XSe, Wbuf);
+          {
+            float acc[4][NCH];
+            const LayerDesc& ld = md.mlp[0].layer[md.mlp[0].n_layers - 1];
+            gemm_tile<NCH>(wm + ld.w_off, ld.Kpad, Xe, XSe, Wbuf, acc);
+            hidden_epilogue<NCH>(acc, wm, ld, false, CEEUS_ACT_NONE, Xe, XSe);
+          }
+          const int nb = min(TPT, G - b0);
+          for (int idx = tid; idx < nb * M * HD; idx += kSimtThreads) {
+            const int c = idx % HD, t = idx / HD;
+            const int bb = t / M, i = t % M;
+            const float* src = Xe + (bb * ME + i * (M - 1)) * XSe + c;
+            float s = 0.f;
+            for (int jj = 0; jj < M - 1; ++jj) s += src[jj * XSe];
+            Xn[((b0 + bb) * M + i) * XSn + FD + U + c] = s * inv_node;
+          }
+          __syncthreads();
+        }
+        mlp_hidden<NCH>(md.mlp[1], wm, md.act, ln, Xn, XSn, Wbuf);
+        {
+          float acc[4][4];
+          const LayerDesc& ld = md.mlp[1].layer[md.mlp[1].n_layers - 1];
+          gemm_tile<4>(wm + ld.w_off, ld.Kpad, Xn, XSn, Wbuf, acc);
+          out_epilogue<4>(acc, wm, ld, Fm, FD, G * M);  // the new node features
+        }
+      }
+      // ---- output heads ----
+      {
+        const LayerDesc& la = md.mlp[4].layer[0];
+        for (int idx = tid; idx < kTileRows * la.Kpad; idx += kSimtThreads) {
+          const int r = idx / la.Kpad, c = idx % la.Kpad;
+          Xe[r * XSe + c] = (r < G && c < FD) ? Fm[(r * M) * FD + c] : 0.f;
+        }
+        __syncthreads();
+        float acc[4][4];
+        gemm_tile<4>(wm + la.w_off, la.Kpad, Xe, XSe, Wbuf, acc);
+        out_epilogue<4>(acc, wm, la, dg, A, G);
+        const LayerDesc& lo = md.mlp[5].layer[0];
+        for (int idx = tid; idx < kTileRows * lo.Kpad; idx += kSimtThreads) {
+          const int r = idx / lo.Kpad, c = idx % lo.Kpad;
+          Xe[r * XSe + c] = (r < G * N && c < FD) ? Fm[((r / N) * M + 1 + r % N) * FD + c] : 0.f;
+        }
+        __syncthreads();
+        gemm_tile<4>(wm + lo.w_off, lo.Kpad, Xe, XSe, Wbuf, acc);
+        out_epilogue<4>(acc, wm, lo, dn, D, G * N);
+      }
+      // ---- de-normalise, residual update (gnn_ensemble.py:302-334, 935-939), emit ----
+      for (int idx = tid; idx < G * sd; idx += kSimtThreads) {
+        const int b = idx / sd, c = idx % sd;
+        float v;
+        if (c < A) {
+          v = fmaf(__ldg(nrm + md.nrm.out_agent + A + c), dg[b * A + c], __ldg(nrm + md.nrm.out_agent + c)) + sraw[idx];
+        } else if (c < A + N * D) {
+          const int q = c - A, i = q / D, f = q % D;
+          v = fmaf(__ldg(nrm + md.nrm.out_dyn + D + f), dn[(b * N + i) * D + f], __ldg(nrm + md.nrm.out_dyn + f)) + sraw[idx];
+        } else {
+          const int q = c - A - N * D, i = q / S, f = q % S;
+          v = fmaf(__ldg(nrm + md.nrm.in_stat + S + f), snrm[b * snw + A + i * NA + D + f], __ldg(nrm + md.nrm.in_stat + f));
+        }
+        sraw[idx] = v;
+      }
+      __syncthreads();
+      if (fused) {
+        for (int idx = tid; idx < Gc * fc.Op; idx += kSimtThreads) {
+          const int b = idx / fc.Op, c = idx % fc.Op;
+          fc.pred[(size_t)(p0 + b) * fc.ps + (size_t)h * fc.hs + (size_t)e * fc.es + c] = sraw[b * sd + c];
+        }
+      } else {
+        float* out = ra.traj + (((size_t)(h + 1) * md.E + e) * ra.n + p0) * O;
+        for (int idx = tid; idx < Gc * O; idx += kSimtThreads) {
+          const int b = idx / O, c = idx % O;
+          out[idx] = c < sd ? sraw[b * sd + c] : __ldg(ra.goal + (size_t)((p0 + b) / ra.traj_per_goal) * md.G + (c - sd));
+        }
+      }
     }
     if (fused && fc.done != nullptr) simt_fused_tail(fc, ra, md, p0, Gc, Xe, kTileRows * XSe);
   }
@@ -524,6 +782,26 @@ static int pick_xs(int kmax) {  // smallest stride >= kmax with stride % 8 == 4:
   return xs;
 }
 
+static GnnTiling make_homog_tiling(const ModelDesc& md) {
+  GnnTiling t{};
+  const int M = md.N + 1, ME = M * (M - 1), Hd = md.Hd;
+  t.TPT = kTileRows / ME;
+  if (t.TPT < 1) return t;
+  const int gmax = kTileRows / M;
+  t.G = (gmax / t.TPT) * t.TPT;
+  if (t.G < t.TPT) t.G = t.TPT <= gmax ? t.TPT : 0;
+  int kmax_e = md.mlp[0].layer[0].Kpad > Hd ? md.mlp[0].layer[0].Kpad : Hd;
+  for (int m = 2; m < 6; ++m)
+    if (md.mlp[m].layer[0].Kpad > kmax_e) kmax_e = md.mlp[m].layer[0].Kpad;
+  t.XSe = pick_xs(kmax_e);
+  const int kn = md.mlp[1].layer[0].Kpad;
+  t.XSn = pick_xs(kn > Hd ? kn : Hd);
+  const size_t fl = (size_t)2 * kKChunk * Hd + (size_t)kTileRows * t.XSe + (size_t)kTileRows * t.XSn + (size_t)kTileRows * md.emb +
+                    (size_t)t.G * md.sd + (size_t)t.G * (md.sd + md.U) + (size_t)kTileRows * md.D + (size_t)t.G * md.A;
+  t.smem_bytes = fl * sizeof(float);
+  return t;
+}
+
 GnnTiling make_gnn_tiling(const ModelDesc& md) {
   GnnTiling t{};
   const int NE = md.N * (md.N - 1);
@@ -533,13 +811,16 @@ GnnTiling make_gnn_tiling(const ModelDesc& md) {
   t.G = (gmax / t.TPT) * t.TPT;
   if (t.G < t.TPT) t.G = t.TPT <= gmax ? t.TPT : 0;
   const int Hd = md.Hd;
+  if (md.variant == 1) return make_homog_tiling(md);
   const int ke = md.mlp[0].layer[0].Kpad, kg = md.mlp[2].layer[0].Kpad, kn = md.mlp[1].layer[0].Kpad;
   int kmax_e = ke > Hd ? ke : Hd;
   if (kg > kmax_e) kmax_e = kg;
+  if (md.edge_global && md.mlp[3].layer[0].Kpad > kmax_e) kmax_e = md.mlp[3].layer[0].Kpad;
   t.XSe = pick_xs(kmax_e);
   t.XSn = pick_xs(kn > Hd ? kn : Hd);
   const size_t fl = (size_t)2 * kKChunk * Hd + (size_t)kTileRows * t.XSe + (size_t)kTileRows * t.XSn + (size_t)t.G * Hd +
-                    (size_t)t.G * md.sd + (size_t)t.G * (md.sd + md.U) + (size_t)kTileRows * md.D + (size_t)t.G * md.A;
+                    (size_t)t.G * md.sd + (size_t)t.G * (md.sd + md.U) + (size_t)kTileRows * md.D + (size_t)t.G * md.A +
+                    (md.edge_global ? (size_t)t.G * Hd : 0);
   t.smem_bytes = fl * sizeof(float);
   return t;
 }
@@ -547,7 +828,7 @@ GnnTiling make_gnn_tiling(const ModelDesc& md) {
 template <int NCH>
 static cudaError_t launch_gnn(const ModelDesc& md, const RolloutArgs& ra, const GnnTiling& tl, int num_sms,
                               const costdev::FusedCost& fc, cudaStream_t st) {
-  auto kern = rollout_gnn_simt_kernel<NCH>;
+  auto kern = md.variant == 1 ? rollout_gnn_homog_simt_kernel<NCH> : rollout_gnn_simt_kernel<NCH>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tl.smem_bytes);
   if (err != cudaSuccess) return err;
   const int groups = (ra.n + tl.G - 1) / tl.G;

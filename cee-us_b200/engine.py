@@ -25,14 +25,21 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def weight_key_order(model_kind, num_layers, layer_norm):
+def weight_key_order(model_kind, num_layers, layer_norm, gnn_variant=0, edge_global=False):
     """state_dict keys in the order ceeus_set_weights expects (include/ceeus_b200.h)."""
-    prefixes = ("edge_mlp.", "node_mlp.", "global_mlp.") if model_kind == "gnn" else ("",)
+    if model_kind != "gnn":
+        mlps = (("", num_layers, layer_norm),)
+    elif gnn_variant == 0:  # GraphNeuralNetworkEnsemble (gnn_modules.py:78-115)
+        mlps = tuple((p, num_layers, layer_norm) for p in ("edge_mlp.", "node_mlp.", "global_mlp.") +
+                     (("edge_mlp_global.",) if edge_global else ()))
+    else:                   # HomogeneousGraphNeuralNetworkEnsemble (:351-405): embeddings / heads are single linear layers
+        mlps = (("edge_mlp.", num_layers, layer_norm), ("node_mlp.", num_layers, layer_norm), ("embed_agent.", 0, False),
+                ("embed_obj.", 0, False), ("output_head_agent.", 0, False), ("output_head_objdyn.", 0, False))
     keys = []
-    for p in prefixes:
-        for l in range(num_layers + 1):
+    for p, nl, lnorm in mlps:
+        for l in range(nl + 1):
             keys += [f"{p}layers.{l}.0.weight", f"{p}layers.{l}.0.bias"]
-            if l < num_layers and layer_norm:
+            if l < nl and lnorm:
                 keys += [f"{p}layers.{l}.1.gamma", f"{p}layers.{l}.1.beta"]
     return keys
 
@@ -41,7 +48,8 @@ class Engine:
     def __init__(self, *, env, model_kind, ensemble_size, hidden_dim, num_layers, act_fn, layer_norm, aggr_fn="mean",
                  horizon, num_traj, sampler=None, cost_along_trajectory="sum", curiosity=True, extrinsic_reward=False,
                  extrinsic_reward_scale=1.0, num_envs=1, world_size=1, rank=0, precision="fp32", seed=0,
-                 device=None, cost_in_rollout_tail=False):
+                 device=None, cost_in_rollout_tail=False, gnn_variant=0, edge_global=False, num_message_passing=1,
+                 embedding_dim=0):
         if not torch.cuda.is_available():
             raise RuntimeError("ceeus_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -97,6 +105,9 @@ class Engine:
             getattr(cfg, name)[:] = [float(v) for v in d[name]]
         cfg.world_size, cfg.rank, cfg.seed = world_size, rank, seed
         cfg.cost_in_rollout_tail = int(bool(cost_in_rollout_tail))
+        cfg.gnn_variant, cfg.edge_global = int(gnn_variant), int(bool(edge_global))
+        cfg.num_message_passing, cfg.embedding_dim = int(num_message_passing), int(embedding_dim or 0)
+        self.gnn_variant, self.edge_global = int(gnn_variant), bool(edge_global)
         self.cfg = cfg
         self.model_kind, self.num_layers, self.layer_norm = model_kind, num_layers, bool(layer_norm)
         self.handle = C.c_void_p()
@@ -174,7 +185,7 @@ class Engine:
 
     # ---- hand-off -------------------------------------------------------------------------------------------
     def set_weights(self, state_dict):
-        keys = weight_key_order(self.model_kind, self.num_layers, self.layer_norm)
+        keys = weight_key_order(self.model_kind, self.num_layers, self.layer_norm, self.gnn_variant, self.edge_global)
         n = self.lib.ceeus_num_weight_tensors(self.handle)
         if n != len(keys):
             raise RuntimeError(f"library expects {n} tensors, state_dict layout gives {len(keys)}")

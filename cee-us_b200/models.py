@@ -31,9 +31,9 @@ class _B200Ensemble:
                  backend_params=None, **kwargs):
         if not target_is_delta:
             raise NotImplementedError("target_is_delta=False is not used by any shipped setting and is unsupported")
-        if not agent_as_global_node:
-            raise NotImplementedError("HomogeneousGraphNeuralNetworkEnsemble is not implemented (SURVEY.md 8f rank 1)")
         self.env = env
+        # agent_as_global_node: false (or no agent features) -> HomogeneousGraphNeuralNetworkEnsemble (gnn_ensemble.py:62-66, 116-132)
+        self.agent_as_global_node = bool(agent_as_global_node)
         self.train_params = dict(train_params or {})
         self.target_is_delta = target_is_delta
         self.use_input_normalization = use_input_normalization
@@ -126,7 +126,10 @@ class _B200Ensemble:
         return dict(env=self.env, model_kind=self.model_kind, ensemble_size=self.ensemble_size,
                     hidden_dim=self.hidden_dim, num_layers=self.num_layers, act_fn=self.act_fn,
                     layer_norm=self.layer_norm, aggr_fn=getattr(self, "aggr_fn", "mean"),
-                    precision=self.backend_params.get("precision", "fp32"))
+                    precision=self.backend_params.get("precision", "fp32"), **self._variant_kwargs())
+
+    def _variant_kwargs(self):
+        return {}
 
     def push_to(self, engine):
         """(Re)uploads weights, normalisers if ``engine`` holds an older version."""
@@ -213,10 +216,24 @@ class B200GNNEnsemble(_B200Ensemble):
                             embedding_dim=None, embedding=False):
         if output_act_fn not in ("none", None):
             raise NotImplementedError("output_act_fn other than 'none'")
-        if not ignore_agent_object or num_message_passing != 1:
-            raise NotImplementedError("ignore_agent_object=False / num_message_passing>1 (SURVEY.md 8f rank 1)")
         self.ensemble_size, self.hidden_dim, self.act_fn, self.num_layers = n, hidden_dim, act_fn, num_layers
         self.layer_norm, self.aggr_fn = layer_norm, aggr_fn
+        self.ignore_agent_object, self.num_message_passing = bool(ignore_agent_object), int(num_message_passing)
+        if self.agent_as_global_node:
+            # like the reference: embedding settings are dropped, and num_message_passing is NOT handed to
+            # GraphNeuralNetworkEnsemble (gnn_ensemble.py:100-114), i.e. the global-node variant always does one round
+            self.embedding_dim, self.embedding = None, False
+        else:
+            if self.env.agent_dim <= 0:
+                raise NotImplementedError("homogeneous GNN without agent features (embedding optional) is not built")
+            if not embedding_dim:
+                raise ValueError("agent_as_global_node=False needs model_params.embedding_dim")
+            self.embedding_dim, self.embedding = int(embedding_dim), True  # forced on whenever agent_dim > 0 (gnn_modules.py:322-323)
+
+    def _variant_kwargs(self):
+        if self.agent_as_global_node:
+            return dict(gnn_variant=0, edge_global=not self.ignore_agent_object)
+        return dict(gnn_variant=1, num_message_passing=self.num_message_passing, embedding_dim=self.embedding_dim)
 
     def _norm_dims(self):
         e = self.env

@@ -128,6 +128,17 @@ typedef struct CeeusConfig {
    * 1: in the tail of the rollout kernel itself, by the warps of member p % E once all E members of trajectory p have arrived
    *    (no extra launch; measured slower on B200 at the BASELINE sizes) */
   int32_t cost_in_rollout_tail;
+  /* ---- GNN variants (yaml model_params / forward_model_params; mbrl/models/gnn_ensemble.py:96-132) ----
+   * gnn_variant 0: GraphNeuralNetworkEnsemble, the agent is the global node (agent_as_global_node: true).
+   *   edge_global = 1: ignore_agent_object: false -> edge_mlp_global on [node, agent, action], aggregated per sample and fed to the
+   *   global MLP as well (gnn_modules.py:98-106, 225-238).
+   * gnn_variant 1: HomogeneousGraphNeuralNetworkEnsemble (agent_as_global_node: false, gnn_modules.py:281-545): agent and objects
+   *   are embedded into embedding_dim features, num_message_passing rounds of edge / node MLPs over the N + 1 nodes, linear output
+   *   heads.  Both variants run on the CEEUS_PREC_FP32 path. */
+  int32_t gnn_variant;
+  int32_t edge_global;
+  int32_t num_message_passing;
+  int32_t embedding_dim;
   int32_t reserved0;
   uint64_t seed;         /* Philox key of the on-device noise sampler */
 } CeeusConfig;

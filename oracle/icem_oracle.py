@@ -85,24 +85,42 @@ def playground_spec(n_obj: int) -> EnvSpec:
 # --------------------------------------------------------------------------------------------------
 
 
-def gnn_weight_shapes(spec: EnvSpec, hidden: int, num_layers: int, E: int) -> Dict[str, Tuple[int, ...]]:
-    """state_dict layout of GraphNeuralNetworkEnsemble (gnn_modules.py:78-115, simple.py:36-57)."""
-    node_attr = spec.dyn_dim + spec.stat_dim
-    ins = {
-        "edge_mlp": (2 * node_attr + spec.agent_dim + spec.action_dim, hidden),
-        "node_mlp": (node_attr + hidden + spec.action_dim + spec.agent_dim, spec.dyn_dim),
-        "global_mlp": (spec.agent_dim + hidden + spec.action_dim, spec.agent_dim),
-    }
-    shapes = {}
-    for name, (din, dout) in ins.items():
-        dims = [din] + [hidden] * num_layers
-        for l in range(num_layers):
-            shapes[f"{name}.layers.{l}.0.weight"] = (E, dims[l], dims[l + 1])
-            shapes[f"{name}.layers.{l}.0.bias"] = (E, dims[l + 1])
+def _mlp_shapes(shapes, name, din, dout, hidden, num_layers, E, layer_norm=True):
+    dims = [din] + [hidden] * num_layers
+    for l in range(num_layers):
+        shapes[f"{name}.layers.{l}.0.weight"] = (E, dims[l], dims[l + 1])
+        shapes[f"{name}.layers.{l}.0.bias"] = (E, dims[l + 1])
+        if layer_norm:
             shapes[f"{name}.layers.{l}.1.gamma"] = (E, dims[l + 1])
             shapes[f"{name}.layers.{l}.1.beta"] = (E, dims[l + 1])
-        shapes[f"{name}.layers.{num_layers}.0.weight"] = (E, hidden, dout)
-        shapes[f"{name}.layers.{num_layers}.0.bias"] = (E, dout)
+    shapes[f"{name}.layers.{num_layers}.0.weight"] = (E, dims[-1], dout)
+    shapes[f"{name}.layers.{num_layers}.0.bias"] = (E, dout)
+
+
+def gnn_weight_shapes(spec: EnvSpec, hidden: int, num_layers: int, E: int, edge_global: bool = False) -> Dict[str, Tuple[int, ...]]:
+    """state_dict layout of GraphNeuralNetworkEnsemble (gnn_modules.py:78-115, simple.py:36-57); edge_global ==
+    ignore_global_v_node=False (:98-106)."""
+    node_attr = spec.dyn_dim + spec.stat_dim
+    shapes = {}
+    _mlp_shapes(shapes, "edge_mlp", 2 * node_attr + spec.agent_dim + spec.action_dim, hidden, hidden, num_layers, E)
+    _mlp_shapes(shapes, "node_mlp", node_attr + hidden + spec.action_dim + spec.agent_dim, spec.dyn_dim, hidden, num_layers, E)
+    _mlp_shapes(shapes, "global_mlp", spec.agent_dim + hidden * (2 if edge_global else 1) + spec.action_dim, spec.agent_dim, hidden,
+                num_layers, E)
+    if edge_global:
+        _mlp_shapes(shapes, "edge_mlp_global", node_attr + spec.agent_dim + spec.action_dim, hidden, hidden, num_layers, E)
+    return shapes
+
+
+def homog_weight_shapes(spec: EnvSpec, hidden: int, num_layers: int, E: int, emb: int) -> Dict[str, Tuple[int, ...]]:
+    """state_dict layout of HomogeneousGraphNeuralNetworkEnsemble (gnn_modules.py:351-405)."""
+    node_attr = spec.dyn_dim + spec.stat_dim
+    shapes = {}
+    _mlp_shapes(shapes, "embed_agent", spec.agent_dim, emb, hidden, 0, E)
+    _mlp_shapes(shapes, "embed_obj", node_attr, emb, hidden, 0, E)
+    _mlp_shapes(shapes, "output_head_agent", emb, spec.agent_dim, hidden, 0, E)
+    _mlp_shapes(shapes, "output_head_objdyn", emb, spec.dyn_dim, hidden, 0, E)
+    _mlp_shapes(shapes, "edge_mlp", 2 * emb + spec.action_dim, hidden, hidden, num_layers, E)
+    _mlp_shapes(shapes, "node_mlp", emb + hidden + spec.action_dim, emb, hidden, num_layers, E)
     return shapes
 
 
@@ -246,6 +264,9 @@ class GNNEnsembleOracle:
     layer_norm: bool = True
     aggr: str = "mean"
     kind: str = "gnn"
+    edge_global: bool = False  # ignore_agent_object: false (gnn_modules.py:98-106, 225-238)
+    homogeneous: bool = False  # agent_as_global_node: false -> HomogeneousGraphNeuralNetworkEnsemble (:281-545)
+    num_message_passing: int = 1
     _w: Dict[str, torch.Tensor] = field(default_factory=dict, repr=False)
     _edge_cache: Dict[int, tuple] = field(default_factory=dict, repr=False)
 
@@ -261,7 +282,7 @@ class GNNEnsembleOracle:
     def _edges(self, B: int):
         # gnn_modules.py:148-170: nonzero() of (ones - eye) -> row-major (i asc, j asc, j != i); row = source i.
         if B not in self._edge_cache:
-            N = self.spec.n_obj
+            N = self.spec.n_obj + (1 if self.homogeneous else 0)
             pairs = [(i, j) for i in range(N) for j in range(N) if i != j]
             base = torch.tensor(pairs, dtype=torch.int64)
             off = (torch.arange(B, dtype=torch.int64) * N).repeat_interleave(len(pairs)).unsqueeze(-1)
@@ -282,8 +303,32 @@ class GNNEnsembleOracle:
             out = out / cnt.clamp(1.0)
         return out
 
+    def _homog_forward(self, agent, dyn, stat, action):
+        """HomogeneousGraphNeuralNetworkEnsemble.forward (gnn_modules.py:499-545)."""
+        E, B, N, _ = dyn.shape
+        M = N + 1
+        w = self._w
+        lin = lambda x, p: torch.bmm(x, w[f"{p}.layers.0.0.weight"]) + w[f"{p}.layers.0.0.bias"].unsqueeze(1)
+        obj = torch.cat([dyn, stat], dim=-1) if self.spec.stat_dim > 0 else dyn
+        f_agent = lin(agent, "embed_agent")                                   # [E,B,F]
+        f_obj = lin(obj.reshape(E, B * N, -1), "embed_obj").view(E, B, N, -1)
+        feat = torch.cat([f_agent.unsqueeze(2), f_obj], dim=2)                # agent = node 0
+        row, col, edge_batch, node_batch = self._edges(B)
+        for _ in range(self.num_message_passing):                             # :449-497
+            node = feat.reshape(E, B * M, -1)
+            edge_in = torch.cat([node[:, row], node[:, col], action[:, edge_batch]], dim=-1)
+            msg = ensemble_mlp(edge_in, w, "edge_mlp.", self.num_layers, self.act, self.layer_norm)
+            agg = self._segment(msg, row, B * M)
+            node_in = torch.cat([node, action[:, node_batch], agg], dim=-1)
+            feat = ensemble_mlp(node_in, w, "node_mlp.", self.num_layers, self.act, self.layer_norm).view(E, B, M, -1)
+        d_agent = lin(feat[:, :, 0].contiguous(), "output_head_agent")
+        d_dyn = lin(feat[:, :, 1:].reshape(E, B * N, -1), "output_head_objdyn").view(E, B, N, -1)
+        return d_agent, d_dyn
+
     def gnn_forward(self, agent, dyn, stat, action):
         """[E,B,A], [E,B,N,D], [E,B,N,S] (S may be 0), [E,B,U] -> (d_agent [E,B,A], d_dyn [E,B,N,D]); normalised."""
+        if self.homogeneous:
+            return self._homog_forward(agent, dyn, stat, action)
         E, B, N, _ = dyn.shape
         node = torch.cat([dyn, stat], dim=-1) if self.spec.stat_dim > 0 else dyn
         node = node.reshape(E, B * N, -1)
@@ -295,7 +340,12 @@ class GNNEnsembleOracle:
         node_in = torch.cat([node, ctx[:, node_batch], agg_node], dim=-1)
         d_dyn = ensemble_mlp(node_in, self._w, "node_mlp.", self.num_layers, self.act, self.layer_norm)
         agg_glob = self._segment(msg, edge_batch, B)
-        glob_in = torch.cat([ctx, agg_glob], dim=-1)
+        glob_in = ctx
+        if self.edge_global:  # :225-238, 244-246
+            ng = ensemble_mlp(torch.cat([node, ctx[:, node_batch]], dim=-1), self._w, "edge_mlp_global.", self.num_layers,
+                              self.act, self.layer_norm)
+            glob_in = torch.cat([ctx, self._segment(ng, node_batch, B)], dim=-1)
+        glob_in = torch.cat([glob_in, agg_glob], dim=-1)
         d_agent = ensemble_mlp(glob_in, self._w, "global_mlp.", self.num_layers, self.act, self.layer_norm)
         return d_agent, d_dyn.view(E, B, N, -1)
 

@@ -163,20 +163,25 @@ _TRAIN_PARAMS = dict(batch_size=125, epochs=25, iterations=0, learning_rate=1e-5
                      optimizer="Adam", bootstrapped=False, train_epochs_only_with_latest_data=False)
 
 
-def make_gnn_model(env, hidden_dim=128, num_layers=2, n=5, running_stats=False, seed=0):
+def make_gnn_model(env, hidden_dim=128, num_layers=2, n=5, running_stats=False, seed=0, ignore_agent_object=True,
+                   agent_as_global_node=True, embedding_dim=None, num_message_passing=1):
     _prepare()
     from mbrl.models.gnn_ensemble import GNNForwardEnsembleModel
 
     torch.manual_seed(seed)
+    mp = dict(n=n, hidden_dim=hidden_dim, num_layers=num_layers, layer_norm=True, num_message_passing=num_message_passing,
+              act_fn="relu", output_act_fn="none", ignore_agent_object=ignore_agent_object)
+    if not agent_as_global_node:
+        mp.update(embedding_dim=embedding_dim, embedding=True)
     return GNNForwardEnsembleModel(
         env=env,
-        model_params=dict(n=n, hidden_dim=hidden_dim, num_layers=num_layers, layer_norm=True,
-                          num_message_passing=1, act_fn="relu", output_act_fn="none"),
+        model_params=mp,
         train_params=dict(_TRAIN_PARAMS),
         use_input_normalization=True,
         use_output_normalization=True,
         target_is_delta=True,
         normalize_w_running_stats=running_stats,
+        agent_as_global_node=agent_as_global_node,
     )
 
 

@@ -55,6 +55,18 @@ CASES = {
     "rollout_gnn_c3_slide": dict(kind="rollout", env="construction", n_obj=3, model="gnn", hidden=128, layers=2, P=12, H=5,
                                  wseed=17, identity_norm=True, running=False, oseed=14, case="Slide", sparse=False,
                                  shaped=False),
+    # the other GNN variants reachable through the same yaml: ignore_agent_object: false (edge_mlp_global),
+    # and the homogeneous GNN of gnn_ensemble_homogeneous.yaml (agent_as_global_node: false) with 1 and 2 message-passing rounds
+    "rollout_gnn_c3_edge_global": dict(kind="rollout", env="construction", n_obj=3, model="gnn", hidden=128, layers=2, P=14, H=5,
+                                       wseed=31, identity_norm=False, running=False, oseed=21, variant="edge_global"),
+    "rollout_gnn_pg4_edge_global": dict(kind="rollout", env="playground", n_obj=4, model="gnn", hidden=64, layers=2, P=12, H=4,
+                                        wseed=32, identity_norm=False, running=True, oseed=22, variant="edge_global"),
+    "rollout_gnn_c2_homog": dict(kind="rollout", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=16, H=5,
+                                 wseed=33, identity_norm=False, running=False, oseed=23, variant="homog", emb=32, n_mp=1),
+    "rollout_gnn_c4_homog_mp2": dict(kind="rollout", env="construction", n_obj=4, model="gnn", hidden=128, layers=2, P=10, H=4,
+                                     wseed=34, identity_norm=False, running=False, oseed=24, variant="homog", emb=32, n_mp=2),
+    "rollout_gnn_pg3_homog": dict(kind="rollout", env="playground", n_obj=3, model="gnn", hidden=64, layers=2, P=12, H=4,
+                                  wseed=35, identity_norm=False, running=True, oseed=25, variant="homog", emb=16, n_mp=1),
     # task costs on synthetic trajectories close to the goal (a random-init model never gets there): every comparison of
     # fpp_construction_env.py:404-511 falls on both sides -- solved / unsolved blocks, the gripper mask, the 0.5 term of the
     # sparse branch, the buffer of PickAndPlace
@@ -111,7 +123,10 @@ def build_inputs(c):
         spec = orc.playground_spec(c["n_obj"])
     E = 5
     if c["model"] == "gnn":
-        shapes = orc.gnn_weight_shapes(spec, c["hidden"], c["layers"], E)
+        if c.get("variant") == "homog":
+            shapes = orc.homog_weight_shapes(spec, c["hidden"], c["layers"], E, c["emb"])
+        else:
+            shapes = orc.gnn_weight_shapes(spec, c["hidden"], c["layers"], E, edge_global=c.get("variant") == "edge_global")
         ndims = orc.gnn_normalizer_dims(spec)
     else:
         shapes = orc.mlp_weight_shapes(spec, c["hidden"], c["layers"], E)

@@ -40,7 +40,10 @@ def build_reference(c, spec, weights, norms, goal):
         env.action_space = spaces.Box(np.asarray(c["abounds"][0], np.float32), np.asarray(c["abounds"][1], np.float32),
                                       dtype="float32")
     if c["model"] == "gnn":
-        model = rh.make_gnn_model(env, hidden_dim=c["hidden"], num_layers=c["layers"], running_stats=c["running"])
+        model = rh.make_gnn_model(env, hidden_dim=c["hidden"], num_layers=c["layers"], running_stats=c["running"],
+                                  ignore_agent_object=c.get("variant") != "edge_global",
+                                  agent_as_global_node=c.get("variant") != "homog", embedding_dim=c.get("emb"),
+                                  num_message_passing=c.get("n_mp", 1))
         rh.load_into_reference(model, weights, norms, c["running"])
     else:
         model = rh.make_mlp_model(env, hidden_dim=c["hidden"], num_layers=c["layers"], running_stats=c["running"])

@@ -36,10 +36,15 @@ def product_model(c, env, weights, norms, precision="fp32"):
     import ceeus_b200
 
     if c["model"] == "gnn":
-        m = ceeus_b200.B200GNNEnsemble(env=env, model_params=dict(n=5, hidden_dim=c["hidden"], num_layers=c["layers"],
-                                                                   layer_norm=True, act_fn="relu"),
-                                       normalize_w_running_stats=c.get("running", False),
-                                       backend_params=dict(precision=precision))
+        mp = dict(n=5, hidden_dim=c["hidden"], num_layers=c["layers"], layer_norm=True, act_fn="relu")
+        kw = {}
+        if c.get("variant") == "edge_global":
+            mp["ignore_agent_object"] = False
+        elif c.get("variant") == "homog":
+            mp.update(embedding_dim=c["emb"], num_message_passing=c.get("n_mp", 1))
+            kw["agent_as_global_node"] = False
+        m = ceeus_b200.B200GNNEnsemble(env=env, model_params=mp, normalize_w_running_stats=c.get("running", False),
+                                       backend_params=dict(precision=precision), **kw)
     else:
         m = ceeus_b200.B200MLPEnsemble(env=env, model_params=dict(n=5, hidden_dim=c["hidden"], num_layers=c["layers"],
                                                                    act_fn="silu", layer_norm=False),
@@ -67,7 +72,12 @@ def product_controller(c, env, model, precision="fp32", **backend):
 
 def oracle_model(c, spec, weights, norms):
     cls = orc.GNNEnsembleOracle if c["model"] == "gnn" else orc.MLPEnsembleOracle
-    return cls(spec=spec, weights=weights, normalizers=norms, hidden=c["hidden"], num_layers=c["layers"])
+    kw = {}
+    if c.get("variant") == "edge_global":
+        kw["edge_global"] = True
+    elif c.get("variant") == "homog":
+        kw.update(homogeneous=True, num_message_passing=c.get("n_mp", 1))
+    return cls(spec=spec, weights=weights, normalizers=norms, hidden=c["hidden"], num_layers=c["layers"], **kw)
 
 
 def oracle_params(c):

@@ -25,7 +25,8 @@ class _Policy:
         self.action_sequences = a
 
 
-GNN_ROLLOUTS = [k for k, c in CASES.items() if c["kind"] == "rollout" and c["model"] == "gnn"]
+# (the homogeneous GNN and ignore_agent_object=false run on the fp32 path only)
+GNN_ROLLOUTS = [k for k, c in CASES.items() if c["kind"] == "rollout" and c["model"] == "gnn" and "variant" not in c]
 
 
 @pytest.mark.parametrize("name", GNN_ROLLOUTS)
@@ -132,6 +133,10 @@ def test_tc_step_is_deterministic_and_unsupported_shapes_are_refused():
     spec5, w5, n5, o5, g5 = build_inputs(c5)
     with pytest.raises(RuntimeError, match="CEEUS_PREC_TC"):
         product_model(c5, product_env(c5, g5), w5, n5, precision="tc")._rollout_engine(8, 4)
+    cv = CASES["rollout_gnn_c2_homog"]
+    specv, wv, nv, ov, gv = build_inputs(cv)
+    with pytest.raises(RuntimeError, match="FP32 path only"):
+        product_model(cv, product_env(cv, gv), wv, nv, precision="tc")._rollout_engine(8, 4)
     with pytest.raises(ValueError, match="precision"):  # there is no tf32 alias: "tc" is fp16 operands / fp32 accumulate
         product_model(c, env, weights, norms, precision="tf32")._rollout_engine(8, 4)
 

@@ -13,8 +13,9 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def make_oracle_model(c, spec, weights, norms):
-    cls = orc.GNNEnsembleOracle if c["model"] == "gnn" else orc.MLPEnsembleOracle
-    return cls(spec=spec, weights=weights, normalizers=norms, hidden=c["hidden"], num_layers=c["layers"])
+    from helpers import oracle_model
+
+    return oracle_model(c, spec, weights, norms)
 
 
 def icem_params(c):
