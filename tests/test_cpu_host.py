@@ -138,10 +138,14 @@ def test_model_dropin_hand_off_surface(built_lib, tmp_path):
     np.testing.assert_array_equal(m2._normalizers["out_dyn"][1], m._normalizers["out_dyn"][1])
     assert m.reset(np.zeros(43, np.float32))["obs"].shape == (43,)
     assert m.got_actual_observation_and_env_state(observation=None) is None
-    with pytest.raises(NotImplementedError):
-        ceeus_b200.B200GNNEnsemble(env=env, model_params=dict(n=5, hidden_dim=128, num_message_passing=2))
-    with pytest.raises(NotImplementedError):
-        m.train(None, None)
+    # like the reference, the global-node variant accepts num_message_passing but always does one round (gnn_ensemble.py:100-114)
+    mv = ceeus_b200.B200GNNEnsemble(env=env, model_params=dict(n=5, hidden_dim=128, num_message_passing=2))
+    assert mv.engine_kwargs()["gnn_variant"] == 0 and "num_message_passing" not in mv.engine_kwargs()
+    mh = ceeus_b200.B200GNNEnsemble(env=env, agent_as_global_node=False,
+                                    model_params=dict(n=5, hidden_dim=128, num_message_passing=2, embedding_dim=32))
+    assert mh.engine_kwargs()["gnn_variant"] == 1 and mh.engine_kwargs()["num_message_passing"] == 2
+    with pytest.raises(ValueError):
+        ceeus_b200.B200GNNEnsemble(env=env, agent_as_global_node=False, model_params=dict(n=5, hidden_dim=128))
 
 
 def _gloo_worker(rank, world, port, q):
