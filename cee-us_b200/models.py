@@ -200,9 +200,28 @@ class _B200Ensemble:
     def set_state(self, state):
         pass
 
-    def train(self, *a, **k):
-        raise NotImplementedError("model training stays with the reference implementation (SURVEY.md section 2 #18); "
-                                  "train there and call sync_from(reference_model)")
+    # -- training (training.py) -----------------------------------------------------------------
+    default_bootstrapped = True   # gnn_ensemble.py:732 (the dense model defaults to False, mlp_ensemble.py:124)
+
+    @property
+    def epsilon(self):
+        return float(self.train_params.get("epsilon", 1e-6))
+
+    def _normalizer_list_by_name(self):
+        return dict(zip(self._norm_groups, self._normalizer_list()))
+
+    def train(self, rollout_buffer, eval_buffer=None, maybe_update_normalizer=True):
+        """Batched training of all members on the CUDA device with the reference's semantics (normaliser update, per-member
+        batches, MSE summed over members, Adam eps=1e-4); the planner's engines pick the new weights up on their next call."""
+        from .training import EnsembleTrainer
+
+        if self._state is None:
+            raise RuntimeError("no weights to train: load_state_dict / load / sync_from first")
+        if getattr(self, "_trainer", None) is None or self._trainer_version != self.weights_version:
+            self._trainer = EnsembleTrainer(self)   # (re)built whenever the weights were replaced from outside
+        stats = self._trainer.train(rollout_buffer, eval_buffer, maybe_update_normalizer)
+        self._trainer_version = self.weights_version
+        return stats
 
 
 class B200GNNEnsemble(_B200Ensemble):
@@ -252,6 +271,26 @@ class B200GNNEnsemble(_B200Ensemble):
     def reset(self, obs):
         return {"obs": torch.as_tensor(np.asarray(obs), dtype=torch.float32)}  # gnn_ensemble.py:810-830
 
+    def update_normalizer(self, batch):
+        """GNNForwardEnsembleModel.update_normalizer (gnn_ensemble.py:428-487): statistics of the agent / object / action
+        inputs and of the delta targets over the given transitions."""
+        from .training import update_normalizer_state
+
+        if not (self.use_input_normalization or self.use_output_normalization):
+            return
+        obs, act, nxt = (np.asarray(batch[k], np.float32) for k in ("observations", "actions", "next_observations"))
+        e = self.env
+        A, D, S, N = e.agent_dim, e.object_dyn_dim, e.object_stat_dim, e.nObj
+        dyn = lambda o: o[:, A:A + N * D].reshape(-1, D)
+        if self.use_input_normalization:
+            update_normalizer_state(self, "in_agent", obs[:, :A])
+            update_normalizer_state(self, "in_dyn", dyn(obs))
+            update_normalizer_state(self, "in_stat", obs[:, A + N * D:A + N * (D + S)].reshape(-1, S))
+            update_normalizer_state(self, "in_action", act)
+        if self.use_output_normalization:
+            update_normalizer_state(self, "out_agent", nxt[:, :A] - obs[:, :A])
+            update_normalizer_state(self, "out_dyn", dyn(nxt) - dyn(obs))
+
     def load(self, path, for_training=True):
         """Reads a checkpoint written by GNNForwardEnsembleModel.save (gnn_ensemble.py:756-808)."""
         sd = torch.load(path, map_location="cpu", weights_only=False)
@@ -290,8 +329,21 @@ class B200MLPEnsemble(_B200Ensemble):
     def _read_reference_normalizers(self, m):
         return {"in": self._nz(m.input_normalizer), "out": self._nz(m.output_normalizer)}
 
+    default_bootstrapped = False
+
     def reset(self, observation):
         return None  # mlp_ensemble.py:640-641
+
+    def update_normalizer(self, batch):
+        """ParallelNNDeterministicEnsemble.update_normalizer (mlp_ensemble.py:172-188)."""
+        from .training import update_normalizer_state
+
+        obs, act, nxt = (np.asarray(batch[k], np.float32) for k in ("observations", "actions", "next_observations"))
+        sd = self.env.observation_space_size_preproc
+        if self.use_input_normalization:
+            update_normalizer_state(self, "in", np.concatenate([obs[:, :sd], act], -1))
+        if self.use_output_normalization:
+            update_normalizer_state(self, "out", nxt[:, :sd] - obs[:, :sd])
 
     def load(self, path, for_training=True):
         sd = torch.load(path, map_location="cpu", weights_only=False)  # mlp_ensemble.py:625-638

@@ -1,0 +1,109 @@
+"""GPU: batched ensemble training (cee-us_b200/training.py) against the reference's own train() run on the CPU of the box: same
+seeded np.random stream -> same per-member batches -> the weights after training must agree (fp32, Adam: 1e-4 relative)."""
+import functools
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_harness as rh  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not rh.reference_available(), reason="reference package not available")]
+
+
+class _Buffer:
+    """The slice of the RolloutBuffer protocol train() uses (rolloutbuffer.py): ["key"], [("k1", "k2", ...)], latest_rollouts."""
+
+    def __init__(self, data, latest=None):
+        self.data, self._latest = data, latest
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple):
+            return tuple(self.data.get(k) for k in key)
+        return self.data[key]
+
+    @property
+    def latest_rollouts(self):
+        return self._latest if self._latest is not None else self
+
+
+def _transitions(rs, env, n):
+    O, U = env.observation_space.shape[0], env.action_space.shape[0]
+    sd = env.observation_space_size_preproc
+    obs = (rs.standard_normal((n, O)) * 0.3 + 0.5).astype(np.float32)
+    nxt = obs.copy()
+    S, N, A, D = env.object_stat_dim, env.nObj, env.agent_dim, env.object_dyn_dim
+    nxt[:, :A + N * D] += (rs.standard_normal((n, A + N * D)) * 0.05).astype(np.float32)  # static features do not change
+    act = rs.uniform(-1, 1, (n, U)).astype(np.float32)
+    return _Buffer(dict(observations=obs, actions=act, next_observations=nxt, rewards=np.zeros((n, 1), np.float32)))
+
+
+@pytest.mark.parametrize("kind,variant,running,bootstrapped", [
+    ("gnn", "global", False, False), ("gnn", "global", True, True), ("gnn", "edge_global", False, False),
+    ("gnn", "homog", False, False), ("mlp", None, False, False), ("mlp", None, True, True)])
+def test_train_matches_reference_train(kind, variant, running, bootstrapped, monkeypatch):
+    import ceeus_b200
+
+    monkeypatch.setattr(torch, "load", functools.partial(torch.load, weights_only=False))
+    rh._prepare()
+    from mbrl import torch_helpers
+
+    torch_helpers.device = torch.device("cpu")
+    ref_env = rh.make_playground_env(3) if kind == "gnn" else rh.make_construction_env(2)
+    env = ceeus_b200.playground_env(3) if kind == "gnn" else ceeus_b200.construction_env(2)
+    tp = dict(batch_size=32, epochs=2, iterations=0, learning_rate=1e-3, weight_decay=1e-3, optimizer="Adam",
+              bootstrapped=bootstrapped, train_epochs_only_with_latest_data=False)
+    if kind == "gnn":
+        mp = dict(n=5, hidden_dim=64, num_layers=2, layer_norm=True, act_fn="relu", output_act_fn="none",
+                  ignore_agent_object=variant != "edge_global", num_message_passing=2 if variant == "homog" else 1)
+        kw = dict(agent_as_global_node=variant != "homog")
+        if variant == "homog":
+            mp.update(embedding_dim=16, embedding=True)
+        from mbrl.models.gnn_ensemble import GNNForwardEnsembleModel as RefCls
+
+        Drop = ceeus_b200.B200GNNEnsemble
+    else:
+        mp = dict(n=5, hidden_dim=128, num_layers=3, act_fn="silu", output_act_fn="none", layer_norm=False)
+        kw = {}
+        from mbrl.models.mlp_ensemble import ParallelNNDeterministicEnsemble as RefCls
+
+        Drop = ceeus_b200.B200MLPEnsemble
+    common = dict(use_input_normalization=True, use_output_normalization=True, target_is_delta=True,
+                  normalize_w_running_stats=running, **kw)
+    torch.manual_seed(0)
+    ref = RefCls(env=ref_env, model_params=dict(mp), train_params=dict(tp), **common)
+    drop = Drop(env=env, model_params=dict(mp), train_params=dict(tp), **common)
+    drop.sync_from(ref)
+    rs = np.random.RandomState(4)
+    buf, ev = _transitions(rs, env, 150), _transitions(rs, env, 40)
+    np.random.seed(11)
+    ref.train(buf, ev)
+    np.random.seed(11)
+    stats = drop.train(buf, ev)
+    assert stats is not None and np.isfinite(float(stats["epoch_train_loss"]))
+    # normalisers updated identically
+    for name, (m, s) in drop._read_reference_normalizers(ref).items():
+        np.testing.assert_allclose(drop._normalizers[name][0], np.asarray(m, np.float32).reshape(-1), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(drop._normalizers[name][1], np.asarray(s, np.float32).reshape(-1), rtol=1e-5, atol=1e-6)
+    # weights after 2 epochs x 5 Adam steps on the same batches
+    moved = 0.0
+    for k, v in ref.model.state_dict().items():
+        got = drop.state_dict()[k].cpu()
+        np.testing.assert_allclose(got.numpy(), v.numpy(), rtol=2e-3, atol=2e-5, err_msg=k)
+        moved = max(moved, float((v - torch.as_tensor(v)).abs().max()))
+    # and the trained weights reach the planner: a predict through the CUDA kernels equals the reference's predict
+    E, B = 5, 6
+    O, U = env.observation_space.shape[0], env.action_space.shape[0]
+    sd = env.observation_space_size_preproc
+    goal = np.zeros(O - sd, np.float32)
+    env.goal, ref_env.goal = goal.copy(), goal.copy()
+    obs = (rs.standard_normal((E, B, O)) * 0.3 + 0.5).astype(np.float32)
+    obs[..., sd:] = goal
+    act = rs.uniform(-1, 1, (E, B, U)).astype(np.float32)
+    want, _, _ = ref.predict(observations=torch.from_numpy(obs), states=None, actions=torch.from_numpy(act))
+    got, _, _ = drop.predict(observations=torch.from_numpy(obs), states=None, actions=torch.from_numpy(act))
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-4)
