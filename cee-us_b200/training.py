@@ -236,6 +236,11 @@ class EnsembleTrainer:
             accum += loss.item()
             if (i + 1) % epoch_length == 0 or i == 0:
                 if ev is not None:
+                    if self.m.model_kind == "mlp":
+                        # the dense model evaluates through a shuffled iterator (mlp_ensemble.py:223-253): the loss is the mean over
+                        # the whole set either way, but the E permutations it draws advance np.random between training batches
+                        for _ in range(E):
+                            np.random.permutation(ev[0].shape[1])
                     with torch.no_grad():
                         test_loss = self.loss_and_per_model(*ev).sum()
                     if self.save_best_val:  # abstract_models.py maybe_get_best_weights: relative improvement above the threshold
