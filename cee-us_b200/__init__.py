@@ -5,6 +5,6 @@ root aliases it).  Everything arithmetic lives in ``libceeus_b200.so`` (csrc/, C
 from . import _lib  # noqa: F401
 from .controllers import B200CuriosityMpcICem, B200MpcICem  # noqa: F401
 from .engine import Engine  # noqa: F401
-from .envs import TensorEnv, construction_env, describe_env, playground_env  # noqa: F401
+from .envs import TensorEnv, construction_env, describe_env, playground_env, robodesk_env  # noqa: F401
 from .models import B200GNNEnsemble, B200MLPEnsemble  # noqa: F401
 from .rollout_buffer import RolloutView  # noqa: F401

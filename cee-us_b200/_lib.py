@@ -13,7 +13,9 @@ ACT = {"none": 0, None: 0, "relu": 1, "silu": 2, "swish": 2, "tanh": 3}
 # "tc" = tcgen05 tensor cores with fp16 operands (10-bit mantissa, the TF32 mantissa width) and fp32 accumulation; it is NOT
 # TF32 (5-bit exponent: the kernels saturate and raise a range flag, ceeus_tc_status), so no "tf32" alias is offered.
 PREC = {"fp32": 0, "tc": 1, "fp16": 1}
-ENV_NONE, ENV_CONSTRUCTION, ENV_PLAYGROUND, ENV_EXTERNAL = 0, 1, 2, 3
+ENV_NONE, ENV_CONSTRUCTION, ENV_PLAYGROUND, ENV_EXTERNAL, ENV_ROBODESK = 0, 1, 2, 3, 4
+ROBODESK_TASKS = ("open_slide", "open_drawer", "push_red", "push_green", "push_blue", "ball_off_table",
+                  "upright_block_off_table", "flat_block_off_table")  # CEEUS_RD_*
 CASE_TOWER, CASE_PICKANDPLACE, CASE_FLIP, CASE_SLIDE = 0, 1, 2, 3
 COST = {"sum": 0, "best": 1}
 

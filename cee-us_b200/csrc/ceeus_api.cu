@@ -211,7 +211,7 @@ int validate(const CeeusConfig& c, std::string& why) {
   if (c.num_layers < 1 || c.num_layers + 1 > kMaxLayers) return bad("num_layers must be in [1,3]");
   if (c.hidden_dim != 64 && c.hidden_dim != 128 && c.hidden_dim != 256) return bad("hidden_dim must be 64, 128 or 256");
   if (c.model_kind == CEEUS_MODEL_GNN) {
-    if (c.hidden_dim == 256) return bad("GNN hidden_dim must be 64 or 128");
+    if (c.hidden_dim == 256 && c.precision != CEEUS_PREC_FP32) return bad("GNN hidden_dim 256 runs on the CEEUS_PREC_FP32 path only");
     if (c.n_obj < 2 && c.gnn_variant == 0) return bad("GNN needs n_obj >= 2 (gnn_modules.py:190-241: row undefined for one node)");
     if (c.gnn_variant != 0 && c.gnn_variant != 1) return bad("gnn_variant");
     if (c.gnn_variant == 1 && (c.embedding_dim < 1 || c.embedding_dim > 64 || c.n_obj < 1))
@@ -236,7 +236,9 @@ int validate(const CeeusConfig& c, std::string& why) {
   if (c.precision != CEEUS_PREC_FP32 && c.precision != CEEUS_PREC_TC) return bad("precision");
   const bool need_env = !c.curiosity || c.extrinsic_reward;
   if (need_env && c.env_kind == CEEUS_ENV_NONE) return bad("task cost requested but env_kind is NONE");
-  if (c.env_kind < CEEUS_ENV_NONE || c.env_kind > CEEUS_ENV_EXTERNAL) return bad("env_kind");
+  if (c.env_kind < CEEUS_ENV_NONE || c.env_kind > CEEUS_ENV_ROBODESK) return bad("env_kind");
+  if (c.env_kind == CEEUS_ENV_ROBODESK && (c.agent_dim < 24 || c.dyn_dim != 13 || c.n_obj < 8 || c.cost_case < 0 || c.cost_case > 7))
+    return bad("RoboDesk layout: agent_dim >= 24, 8 objects of 13 dynamic features (robodesk_env.py:20-23), cost_case = CEEUS_RD_*");
   if (c.env_kind == CEEUS_ENV_CONSTRUCTION && (c.goal_dim != 3 * c.n_obj + 3 || c.dyn_dim < 3 || c.agent_dim < 3))
     return bad("construction layout: goal_dim must be 3N+3");
   if (c.env_kind == CEEUS_ENV_PLAYGROUND && (c.goal_dim != 2 * c.n_obj || c.dyn_dim < 2)) return bad("playground layout: goal_dim must be 2N");

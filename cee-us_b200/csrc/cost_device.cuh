@@ -54,6 +54,31 @@ __device__ inline float env_cost_row(const float* __restrict__ row, const float*
       }
     return sqrtf(s);
   }
+  if (cd.env_kind == CEEUS_ENV_ROBODESK) {
+    // Robodesk.cost_fn = -reward (robodesk_env.py:53-135); observation indices are the reference's (agent 24, objects of 13
+    // dynamic features in the order drawer, slide, red / green / blue button, ball, upright block, flat block)
+    const float gx = ld_l2(row), gy = ld_l2(row + 1), gz = ld_l2(row + 2);
+    auto dist = [&](float x, float y, float z) { const float a = gx - x, b = gy - y, c = gz - z; return sqrtf(a * a + b * b + c * c); };
+    float rew;
+    if (cd.cost_case == CEEUS_RD_OPEN_SLIDE) {               // :75-86
+      const float t = __fsub_rn(__fadd_rn(ld_l2(row + 37), 0.3f), 0.55f);
+      rew = cd.sparse ? (t >= 0.f ? 1.f : 0.f) : __fsub_rn(t, __fmul_rn(0.05f, dist(ld_l2(row + 37), ld_l2(row + 38), ld_l2(row + 39))));
+    } else if (cd.cost_case == CEEUS_RD_OPEN_DRAWER) {       // :88-101
+      const float t = __fsub_rn(-0.2f, __fsub_rn(ld_l2(row + 25), 0.85f));
+      rew = cd.sparse ? (t >= 0.f ? 1.f : 0.f) : __fsub_rn(t, __fmul_rn(0.05f, dist(ld_l2(row + 24), ld_l2(row + 25), ld_l2(row + 26))));
+    } else if (cd.cost_case <= CEEUS_RD_PUSH_BLUE) {         // :103-123 (button z at 52 / 65 / 78, static z 0.76)
+      const int zi = 52 + 13 * (cd.cost_case - CEEUS_RD_PUSH_RED);
+      const float t = __fsub_rn(-0.0005238f, __fsub_rn(ld_l2(row + zi), 0.76f));
+      rew = cd.sparse ? (t >= 0.001f ? 1.f : 0.f) : __fsub_rn(t, __fmul_rn(0.05f, dist(ld_l2(row + zi - 2), ld_l2(row + zi - 1), 0.76f)));
+    } else {                                                 // :125-137 (block x at 89 / 102 / 115)
+      const int k = cd.cost_case - CEEUS_RD_BALL_OFF_TABLE, bx = 89 + 13 * k;
+      const float z0 = k == 0 ? 0.79963282f : k == 1 ? 0.84978449f : 0.77478449f;
+      const float z = ld_l2(row + bx + 2);
+      rew = cd.sparse ? (z < 0.6f ? 1.f : 0.f)
+                      : __fsub_rn(__fsub_rn(1.f, __fdiv_rn(z, z0)), __fmul_rn(0.001f, dist(ld_l2(row + bx), ld_l2(row + bx + 1), z)));
+    }
+    return -rew;
+  }
   if (cd.cost_case == CEEUS_CASE_FLIP || cd.cost_case == CEEUS_CASE_SLIDE) {
     // per-coordinate distances (:297-355): achieved goal = euler angles (Flip, dims 3..5 of a block) or positions (Slide)
     const int ao = cd.cost_case == CEEUS_CASE_FLIP ? 3 : 0;

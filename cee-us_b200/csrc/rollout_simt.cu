@@ -38,10 +38,15 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 
 // acc[4][NC] (+)= X[64][K] * W[K][16*NC].  Thread (tx = tid&15, ty = tid>>4) owns rows ty*4..+3 and the column
 // quads {j*64 + tx*4 .. +3}.  W rows are staged kKChunk at a time through a 2-deep cp.async ring.
+// weight rows staged per cp.async chunk: 32, or 16 for 256-wide outputs (keeps the ring at 32 KB so that a hidden-256 GNN fits)
+__host__ __device__ constexpr int kchunk_of(int nout) { return nout >= 256 ? 16 : kKChunk; }
+__host__ __device__ constexpr int wbuf_floats(int hd) { return 2 * kchunk_of(hd) * hd; }
+
 template <int NC>
 __device__ __forceinline__ void gemm_tile(const float* __restrict__ Wg, int Kpad, const float* __restrict__ X, int XS,
                                           float* __restrict__ Wbuf, float (&acc)[4][NC]) {
   constexpr int NOUT = 16 * NC;
+  constexpr int kKChunk = kchunk_of(NOUT);  // (shadows the namespace constant inside this function)
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -247,8 +252,8 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_simt_kernel(const
   const float* __restrict__ wm = ra.weights + (size_t)e * md.member_stride;
   const float* __restrict__ nrm = ra.norm;
 
-  float* Wbuf = smem;                          // 2 * kKChunk * HD
-  float* Xe = Wbuf + 2 * kKChunk * HD;         // 64 * XSe   edge tile, later the global-MLP tile
+  float* Wbuf = smem;                          // weight ring (wbuf_floats)
+  float* Xe = Wbuf + wbuf_floats(HD);          // 64 * XSe   edge tile, later the global-MLP tile
   float* Xn = Xe + kTileRows * XSe;            // 64 * XSn   node-MLP tile [node_i | agent | action | agg_i]
   float* aggG = Xn + kTileRows * XSn;          // G * HD     per-trajectory mean of all edge messages
   float* sraw = aggG + G * HD;                 // G * sd     raw (un-normalised) state
@@ -509,8 +514,8 @@ __global__ void __launch_bounds__(kSimtThreads, 1) rollout_gnn_homog_simt_kernel
   const float* __restrict__ wm = ra.weights + (size_t)e * md.member_stride;
   const float* __restrict__ nrm = ra.norm;
 
-  float* Wbuf = smem;                          // 2 * kKChunk * HD
-  float* Xe = Wbuf + 2 * kKChunk * HD;         // 64 * XSe   edge tile; also the input tile of the embeddings / output heads
+  float* Wbuf = smem;                          // weight ring (wbuf_floats)
+  float* Xe = Wbuf + wbuf_floats(HD);          // 64 * XSe   edge tile; also the input tile of the embeddings / output heads
   float* Xn = Xe + kTileRows * XSe;            // 64 * XSn   node-MLP tile [f_i | action | agg_i]
   float* Fm = Xn + kTileRows * XSn;            // 64 * FD    node features, row b * M + node
   float* sraw = Fm + kTileRows * FD;           // G * sd
@@ -796,7 +801,7 @@ static GnnTiling make_homog_tiling(const ModelDesc& md) {
   t.XSe = pick_xs(kmax_e);
   const int kn = md.mlp[1].layer[0].Kpad;
   t.XSn = pick_xs(kn > Hd ? kn : Hd);
-  const size_t fl = (size_t)2 * kKChunk * Hd + (size_t)kTileRows * t.XSe + (size_t)kTileRows * t.XSn + (size_t)kTileRows * md.emb +
+  const size_t fl = (size_t)wbuf_floats(Hd) + (size_t)kTileRows * t.XSe + (size_t)kTileRows * t.XSn + (size_t)kTileRows * md.emb +
                     (size_t)t.G * md.sd + (size_t)t.G * (md.sd + md.U) + (size_t)kTileRows * md.D + (size_t)t.G * md.A;
   t.smem_bytes = fl * sizeof(float);
   return t;
@@ -818,7 +823,7 @@ GnnTiling make_gnn_tiling(const ModelDesc& md) {
   if (md.edge_global && md.mlp[3].layer[0].Kpad > kmax_e) kmax_e = md.mlp[3].layer[0].Kpad;
   t.XSe = pick_xs(kmax_e);
   t.XSn = pick_xs(kn > Hd ? kn : Hd);
-  const size_t fl = (size_t)2 * kKChunk * Hd + (size_t)kTileRows * t.XSe + (size_t)kTileRows * t.XSn + (size_t)t.G * Hd +
+  const size_t fl = (size_t)wbuf_floats(Hd) + (size_t)kTileRows * t.XSe + (size_t)kTileRows * t.XSn + (size_t)t.G * Hd +
                     (size_t)t.G * md.sd + (size_t)t.G * (md.sd + md.U) + (size_t)kTileRows * md.D + (size_t)t.G * md.A +
                     (md.edge_global ? (size_t)t.G * Hd : 0);
   t.smem_bytes = fl * sizeof(float);
@@ -845,6 +850,7 @@ cudaError_t launch_rollout_gnn_simt(const ModelDesc& md, const RolloutArgs& ra, 
   switch (md.Hd) {
     case 64: return launch_gnn<4>(md, ra, tl, num_sms, fc, st);
     case 128: return launch_gnn<8>(md, ra, tl, num_sms, fc, st);
+    case 256: return launch_gnn<16>(md, ra, tl, num_sms, fc, st);  // robodesk/common/gnn_ensemble.yaml
     default: return cudaErrorInvalidValue;
   }
 }

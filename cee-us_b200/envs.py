@@ -66,6 +66,14 @@ def playground_env(num_objs):
                      action_dim=2, goal_dim=2 * num_objs, case="playground", threshold=0.23, buffer_threshold=0.23)
 
 
+def robodesk_env(task="open_slide", reward="dense"):
+    """mbrl/environments/robodesk_env.py:14-31 (dims), robodesk/robodesk.py:70-95 (8 bodies, 6 object types, 8 action dims)."""
+    env = TensorEnv(name="Robodesk", kind="robodesk", n_obj=8, agent_dim=24, dyn_dim=13, stat_dim=6, action_dim=8, goal_dim=0,
+                    case=task, sparse=reward == "sparse", shaped_reward=False, threshold=0.0, buffer_threshold=0.0)
+    env.task, env.reward = task, reward
+    return env
+
+
 def _arr(x):
     if hasattr(x, "detach"):
         x = x.detach().cpu().numpy()
@@ -77,7 +85,8 @@ def describe_env(env):
     kind = getattr(env, "kind", None)
     if kind is None:
         cls = type(env).__name__
-        kind = "construction" if "Construction" in cls else "playground" if "Playground" in cls else "unknown"
+        kind = ("construction" if "Construction" in cls else "playground" if "Playground" in cls else
+                "robodesk" if cls == "Robodesk" else "unknown")
     A, D, S, N = int(env.agent_dim), int(env.object_dyn_dim), int(env.object_stat_dim), int(env.nObj)
     O = int(env.observation_space.shape[0])
     U = int(env.action_space.shape[0])
@@ -85,10 +94,12 @@ def describe_env(env):
     d = dict(kind=kind, n_obj=N, agent_dim=A, dyn_dim=D, stat_dim=S, action_dim=U, goal_dim=O - sd, obs_dim=O,
              state_dim=sd, action_low=np.asarray(env.action_space.low, np.float32),
              action_high=np.asarray(env.action_space.high, np.float32))
-    d["env_kind"] = {"construction": _lib.ENV_CONSTRUCTION, "playground": _lib.ENV_PLAYGROUND}.get(kind, _lib.ENV_NONE)
+    d["env_kind"] = {"construction": _lib.ENV_CONSTRUCTION, "playground": _lib.ENV_PLAYGROUND,
+                     "robodesk": _lib.ENV_ROBODESK}.get(kind, _lib.ENV_NONE)
     case = getattr(env, "case", "")
     d["case"] = case
-    d["task_cost_supported"] = kind in ("construction", "playground")
+    task = getattr(env, "task", None)
+    d["task_cost_supported"] = kind in ("construction", "playground") or (kind == "robodesk" and task in _lib.ROBODESK_TASKS)
     # any other environment: its own cost_fn is called on the materialised trajectories (SURVEY.md 8b "Env hand-off")
     d["external_cost"] = (not d["task_cost_supported"] or bool(getattr(env, "force_external_cost", False))) and \
         callable(getattr(env, "cost_fn", None))
@@ -97,6 +108,9 @@ def describe_env(env):
     d["cost_case"] = (_lib.CASE_FLIP if case == "Flip" else _lib.CASE_SLIDE if case == "Slide" else
                       _lib.CASE_TOWER if ("tower" in case or case == "Pyramid") else _lib.CASE_PICKANDPLACE)
     d["sparse"] = int(bool(getattr(env, "sparse", False)))
+    if kind == "robodesk" and d["task_cost_supported"]:  # robodesk_env.py:53-73: cost_case = task, sparse = (reward == "sparse")
+        d["cost_case"] = _lib.ROBODESK_TASKS.index(task)
+        d["sparse"] = int(getattr(env, "reward", "dense") == "sparse")
     d["shaped_reward"] = int(bool(getattr(env, "shaped_reward", False)))
     d["threshold"] = float(getattr(env, "threshold", 0.0))
     bt = _arr(getattr(env, "buffer_threshold", 0.025))

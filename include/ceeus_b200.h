@@ -59,7 +59,13 @@ enum { CEEUS_ACT_NONE = 0, CEEUS_ACT_RELU = 1, CEEUS_ACT_SILU = 2, CEEUS_ACT_TAN
 enum { CEEUS_PREC_FP32 = 0, CEEUS_PREC_TC = 1 };
 /* CEEUS_ENV_EXTERNAL: the task cost of this environment is not built in; the caller evaluates env.cost_fn on the
  * materialised trajectories and hands the [nE*P,E,H] result to ceeus_plan_iter_costs (SURVEY.md 8b "Env hand-off") */
-enum { CEEUS_ENV_NONE = 0, CEEUS_ENV_CONSTRUCTION = 1, CEEUS_ENV_PLAYGROUND = 2, CEEUS_ENV_EXTERNAL = 3 };
+enum { CEEUS_ENV_NONE = 0, CEEUS_ENV_CONSTRUCTION = 1, CEEUS_ENV_PLAYGROUND = 2, CEEUS_ENV_EXTERNAL = 3,
+       CEEUS_ENV_ROBODESK = 4 /* mbrl/environments/robodesk_env.py:53-135; cost_case = CEEUS_RD_*, sparse = (reward == "sparse") */ };
+/* RoboDesk tasks (robodesk_env.py:58-73) */
+enum {
+  CEEUS_RD_OPEN_SLIDE = 0, CEEUS_RD_OPEN_DRAWER = 1, CEEUS_RD_PUSH_RED = 2, CEEUS_RD_PUSH_GREEN = 3, CEEUS_RD_PUSH_BLUE = 4,
+  CEEUS_RD_BALL_OFF_TABLE = 5, CEEUS_RD_UPRIGHT_BLOCK_OFF_TABLE = 6, CEEUS_RD_FLAT_BLOCK_OFF_TABLE = 7
+};
 /* construction cost branches, fpp_construction_env.py:475-508 */
 enum {
   CEEUS_CASE_TOWER = 0 /* "*tower*" and "Pyramid" */,

@@ -182,6 +182,9 @@ def synth_start_obs(spec: EnvSpec, seed: int) -> Tuple[np.ndarray, np.ndarray]:
     """Synthetic start observation + goal (SURVEY.md 8d "Synthetic inputs")."""
     rs = np.random.RandomState(seed)
     N = spec.n_obj
+    if spec.kind == "robodesk":
+        obs = np.concatenate([0.3 * rs.standard_normal(spec.state_dim) + 0.5]).astype(np.float32)
+        return obs, np.zeros(0, np.float32)
     if spec.kind == "construction":
         agent = np.concatenate([[1.34, 0.75, 0.53], rs.uniform(0, 0.05, 2), 0.01 * rs.standard_normal(5)])
         blocks = []
@@ -502,7 +505,42 @@ def playground_cost(spec: EnvSpec, next_obs: torch.Tensor) -> torch.Tensor:
     return torch.norm(torch.maximum(torch.abs(diff), torch.tensor(0.23)), dim=-1)
 
 
+def robodesk_spec(task: str = "open_slide", reward: str = "dense") -> EnvSpec:
+    """Robodesk (robodesk_env.py:14-31): agent 24, 8 objects x (13 dynamic + 6 static), 8 action dims, no goal."""
+    return EnvSpec("robodesk", 8, 24, 13, 6, 8, 0, -np.ones(8, np.float32), np.ones(8, np.float32), case=task,
+                   sparse=reward == "sparse", shaped_reward=False, threshold=0.0, buffer_threshold=0.0)
+
+
+def robodesk_cost(spec: EnvSpec, next_obs: torch.Tensor) -> torch.Tensor:
+    """Robodesk.cost_fn = -reward (robodesk_env.py:53-135).  [...,O] -> [...]."""
+    o, task, sparse = next_obs, spec.case, spec.sparse
+    dist = lambda t: torch.linalg.norm(o[..., :3] - t, dim=-1)
+    if task == "open_slide":
+        r = (o[..., 37] + 0.3) - 0.55
+        r = (r >= 0.0).float() if sparse else r - 0.05 * dist(o[..., 37:40])
+    elif task == "open_drawer":
+        r = -0.2 - (o[..., 25] - 0.85)
+        r = (r >= 0.0).float() if sparse else r - 0.05 * dist(o[..., 24:27])
+    elif "push" in task:
+        zi = {"push_red": 52, "push_green": 65, "push_blue": 78}[task]
+        r = -0.0005238 - (o[..., zi] - 0.76)
+        if sparse:
+            r = (r >= 0.001).float()
+        else:
+            tgt = o[..., zi - 2:zi + 1].clone()
+            tgt[..., -1] = 0.76
+            r = r - 0.05 * dist(tgt)
+    else:
+        name = task[:-len("_off_table")]
+        bx = {"ball": 89, "upright_block": 102, "flat_block": 115}[name]
+        z0 = {"ball": 0.79963282, "upright_block": 0.84978449, "flat_block": 0.77478449}[name]
+        r = (o[..., bx + 2] < 0.6).float() if sparse else 1 - (o[..., bx + 2] / z0) - 0.001 * dist(o[..., bx:bx + 3])
+    return -r
+
+
 def env_cost(spec: EnvSpec, obs: torch.Tensor, next_obs: torch.Tensor) -> torch.Tensor:
+    if spec.kind == "robodesk":
+        return robodesk_cost(spec, next_obs)
     return construction_cost(spec, obs, next_obs) if spec.kind == "construction" else playground_cost(spec, next_obs)
 
 

@@ -159,6 +159,27 @@ def make_playground_env(num_objs, goal=None):
     return env
 
 
+def make_robodesk_env(task="open_slide", reward="dense"):
+    """Robodesk without MuJoCo: the attributes cost_fn reads (robodesk_env.py:14-31, robodesk/robodesk.py:70-95)."""
+    _prepare()
+    from gym import spaces
+    from mbrl.environments.robodesk_env import Robodesk
+
+    env = object.__new__(Robodesk)
+    env.name = "Robodesk"
+    env.task, env.reward = task, reward
+    env.agent_dim, env.object_dyn_dim, env.object_stat_dim, env.nObj = 24, 13, 6, 8
+    env.num_object_types = 6
+    O = 24 + 8 * 19
+    env.observation_space = spaces.Box(-np.inf, np.inf, shape=(O,), dtype="float32")
+    env.action_space = spaces.Box(-1.0, 1.0, shape=(8,), dtype="float32")
+    env.observation_space_size_preproc = O
+    env.original_pos_z_dict = {"ball": 0.79963282, "upright_block": 0.84978449, "flat_block": 0.77478449}
+    env.block_ids = {"ball": 89, "upright_block": 102, "flat_block": 115}
+    env.goal = np.zeros(0, np.float32)
+    return env
+
+
 _TRAIN_PARAMS = dict(batch_size=125, epochs=25, iterations=0, learning_rate=1e-5, weight_decay=1e-3,
                      optimizer="Adam", bootstrapped=False, train_epochs_only_with_latest_data=False)
 

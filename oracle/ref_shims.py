@@ -82,7 +82,9 @@ def install():
     if "gym" in sys.modules and getattr(sys.modules["gym"], "__ceeus_shim__", False):
         return
     spaces = _mod("gym.spaces", Box=Box, Dict=Dict, Discrete=Discrete, Space=Space)
-    gutils = _mod("gym.utils", EzPickle=EzPickle)
+    seeding = _mod("gym.utils.seeding", np_random=lambda seed=None: (None, seed))
+    gutils = _mod("gym.utils", EzPickle=EzPickle, seeding=seeding)
+    gerror = _mod("gym.error", DependencyNotInstalled=ImportError, Error=Exception)  # robodesk.py:9-20
     gwrappers = _mod("gym.wrappers")
     gmj = _mod("gym.envs.mujoco", MujocoEnv=_MujocoEnv, mujoco_env=types.SimpleNamespace(MujocoEnv=_MujocoEnv))
     fetch_env = _mod("gym.envs.robotics.fetch_env", FetchEnv=_FetchEnv)
@@ -101,7 +103,7 @@ def install():
         robot_env=robot_env,
     )
     genvs = _mod("gym.envs", mujoco=gmj, robotics=grob)
-    _mod("gym", spaces=spaces, Env=Env, Wrapper=Wrapper, utils=gutils, wrappers=gwrappers, envs=genvs,
+    _mod("gym", spaces=spaces, Env=Env, Wrapper=Wrapper, utils=gutils, wrappers=gwrappers, envs=genvs, error=gerror,
          __ceeus_shim__=True)
     const = _mod("mujoco_py.generated.const")
     gen = _mod("mujoco_py.generated", const=const)

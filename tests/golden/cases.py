@@ -79,6 +79,11 @@ CASES = {
     "cost_c2_pyramid_unshaped": dict(kind="cost", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=24, H=6,
                                      wseed=18, identity_norm=True, running=False, oseed=20, case="Pyramid", sparse=False,
                                      shaped=False),
+    # RoboDesk task costs (robodesk_env.py:53-135) on synthetic observations around every threshold, dense and sparse
+    **{f"cost_robodesk_{t}_{r}": dict(kind="cost", env="robodesk", task=t, reward=r, n_obj=8, model="gnn", hidden=128, layers=2, P=16,
+                                      H=5, wseed=40, identity_norm=True, running=False, oseed=30 + i)
+       for i, t in enumerate(("open_slide", "open_drawer", "push_red", "push_green", "push_blue", "ball_off_table",
+                              "upright_block_off_table", "flat_block_off_table")) for r in ("dense", "sparse")},
     # full MPC steps (3 consecutive get_action calls after beginning_of_rollout)
     "mpc_gnn_c2_curious": dict(kind="mpc", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=128, H=20,
                                wseed=21, identity_norm=True, running=False, oseed=8, nseed=100, steps=3,
@@ -119,6 +124,8 @@ def build_inputs(c):
     if c["env"] == "construction":
         spec = orc.construction_spec(c["n_obj"], case=c.get("case", "Singletower"), sparse=c.get("sparse", False),
                                      shaped_reward=c.get("shaped", True))
+    elif c["env"] == "robodesk":
+        spec = orc.robodesk_spec(c["task"], c["reward"])
     else:
         spec = orc.playground_spec(c["n_obj"])
     E = 5
@@ -159,6 +166,18 @@ def cost_trajectories(c, spec, obs, goal):
     with block 0 already on its goal (-> next block id k* = 1, fpp_construction_env.py:365-383)."""
     rs = np.random.RandomState(c["oseed"] + 900)
     E, P, H, O = 5, c["P"], c["H"], spec.obs_dim
+    if spec.kind == "robodesk":
+        # every feature the rewards read scattered around its threshold (slide x 0.25, drawer y 0.65, button z 0.7595 / 0.7585,
+        # block z 0.6) and the gripper somewhere near
+        traj = (0.3 * rs.standard_normal((H + 1, E, P, O)) + 0.5).astype(np.float32)
+        traj[0] = obs
+        traj[1:, ..., 37] = 0.25 + rs.uniform(-0.1, 0.1, (H, E, P))
+        traj[1:, ..., 25] = 0.65 + rs.uniform(-0.1, 0.1, (H, E, P))
+        for zi in (52, 65, 78):
+            traj[1:, ..., zi] = 0.759 + rs.uniform(-0.002, 0.002, (H, E, P))
+        for bx in (89, 102, 115):
+            traj[1:, ..., bx + 2] = 0.6 + rs.uniform(-0.2, 0.25, (H, E, P))
+        return traj.astype(np.float32)
     A, D, N, sd = spec.agent_dim, spec.dyn_dim, spec.n_obj, spec.state_dim
     start = obs.copy()
     start[A:A + 3] = goal[0:3] + np.float32(0.004)

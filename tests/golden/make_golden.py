@@ -80,11 +80,14 @@ def gen_cost_case(c):
     """env.cost_fn of the reference on the synthetic near-goal trajectories of cases.cost_trajectories."""
     rh._prepare()
     spec, weights, norms, obs, goal = build_inputs(c)
-    env, _ = build_reference(c, spec, weights, norms, goal)
+    if c["env"] == "robodesk":
+        env = rh.make_robodesk_env(c["task"], c["reward"])
+    else:
+        env, _ = build_reference(c, spec, weights, norms, goal)
     traj = torch.from_numpy(cost_trajectories(c, spec, obs, goal))
     o, n = traj[:-1].permute(2, 1, 0, 3), traj[1:].permute(2, 1, 0, 3)
     a = torch.zeros(c["P"], 5, c["H"], spec.action_dim)
-    return dict(env_cost=env.cost_fn(o, a, n).numpy().copy())
+    return dict(env_cost=np.asarray(env.cost_fn(o, a, n).numpy(), np.float32).copy())
 
 
 def gen_mpc_case(c):

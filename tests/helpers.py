@@ -23,6 +23,8 @@ def product_env(c, goal):
     if c["env"] == "construction":
         env = ceeus_b200.construction_env(c["n_obj"], case=c.get("case", "Singletower"), sparse=c.get("sparse", False),
                                           shaped_reward=c.get("shaped", True))
+    elif c["env"] == "robodesk":
+        env = ceeus_b200.robodesk_env(c["task"], c["reward"])
     else:
         env = ceeus_b200.playground_env(c["n_obj"])
     env.goal = np.asarray(goal, np.float32).copy()

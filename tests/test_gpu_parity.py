@@ -296,3 +296,33 @@ def test_planner_costs_from_compact_scratch_equal_cost_kernel_on_materialised_tr
     # arrival counters are self-resetting: a second launch over the same scratch gives the same answer
     e.plan_iter_local(0)
     assert torch.equal(e.costs_, fused_costs) and torch.equal(e.costs_per_model_, fused_cpm)  # and the tail is deterministic
+
+
+@pytest.mark.parametrize("task,reward", [("open_slide", "dense"), ("push_green", "sparse"), ("flat_block_off_table", "dense")])
+def test_robodesk_planning_step_on_device_matches_oracle(task, reward):
+    """The RoboDesk zero-shot setting (robodesk/common/gnn_ensemble.yaml: GNN ensemble with hidden 256 over 8 objects of 13 + 6
+    features, agent 24, action 8; controller_tasks.yaml: task cost) entirely on the device: hidden-256 fp32 rollout kernel, the
+    task cost of robodesk_env.py:53-135 reduced on the device -- no env.cost_fn round trip.  One MPC step against the oracle."""
+    c = dict(kind="mpc", env="robodesk", task=task, reward=reward, n_obj=8, model="gnn", hidden=256, layers=2, P=40, H=6,
+             wseed=61, identity_norm=False, running=False, oseed=62, nseed=63, curiosity=False, cost="sum",
+             sampler=dict(opt_iterations=2, init_std=0.5))
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    ctrl = product_controller(c, env, product_model(c, env, weights, norms))
+    assert not ctrl.engine.external_cost
+    om = oracle_model(c, spec, weights, norms)
+    feed = {}
+    oc = orc.ICEMOracle(om, oracle_params(c), lambda size: feed["replay"](size))
+    oc.set_goal(goal)
+    oc.beginning_of_rollout()
+    ctrl.beginning_of_rollout(observation=obs, state=None, mode="train")
+    noise = SeededNoise(c["nseed"], 3.5)
+    e = ctrl.engine
+    for s in range(2):
+        flat, feed["replay"] = step_noise(noise, c, spec, e.has_elites(), e.n_kept, DEV)
+        a = ctrl.get_action(obs, None, noise=flat)
+        want = oc.get_action(obs)
+        it = oc.trace[-1]["iters"][-1]
+        assert rel_err(ctrl.costs_.cpu().numpy(), it["costs"].numpy()[: c["P"]]) < TOL_COST_OWN_ROLLOUT
+        np.testing.assert_array_equal(e.elite_idx_[0].cpu().numpy(), it["elite_idx"].numpy())
+        np.testing.assert_allclose(a, want, rtol=1e-5, atol=1e-6)

@@ -49,7 +49,8 @@ def test_task_cost_on_near_goal_trajectories_matches_reference(name):
     spec, weights, norms, obs, goal = build_inputs(c)
     traj = torch.from_numpy(cost_trajectories(c, spec, obs, goal))
     got = orc.env_cost(spec, traj[:-1].permute(2, 1, 0, 3), traj[1:].permute(2, 1, 0, 3)).numpy()
-    assert len(np.unique(np.round(g["env_cost"], 3))) >= 3  # the fixture really spans several branches
+    # the fixture really spans several branches (a sparse RoboDesk reward only has the two values 0 / -1)
+    assert len(np.unique(np.round(g["env_cost"], 3))) >= (2 if c.get("reward") == "sparse" else 3)
     np.testing.assert_allclose(got, g["env_cost"], rtol=1e-5, atol=1e-6)
 
 
