@@ -212,6 +212,8 @@ class Engine:
         _lib.check(self.lib.ceeus_set_normalizers(self.handle, flat.ctypes.data_as(C.c_void_p), flat.size), self.handle)
 
     def set_goal(self, goal):
+        if self.env_desc["goal_dim"] == 0:  # environments without goal dims in the observation (RoboDesk)
+            return
         g = np.ascontiguousarray(np.broadcast_to(np.asarray(goal, np.float32).reshape(-1, self.env_desc["goal_dim"]),
                                                  (self.nE, self.env_desc["goal_dim"])))
         _lib.check(self.lib.ceeus_set_goal(self.handle, g.ctypes.data_as(C.c_void_p)), self.handle)
