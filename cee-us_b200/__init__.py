@@ -7,4 +7,5 @@ from .controllers import B200CuriosityMpcICem, B200MpcICem  # noqa: F401
 from .engine import Engine  # noqa: F401
 from .envs import TensorEnv, construction_env, describe_env, playground_env, robodesk_env  # noqa: F401
 from .models import B200GNNEnsemble, B200MLPEnsemble  # noqa: F401
+from .rnd import B200RndMpcICem  # noqa: F401
 from .rollout_buffer import RolloutView  # noqa: F401

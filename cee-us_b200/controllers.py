@@ -187,14 +187,18 @@ class B200MpcICem:
                 # the environment's own cost_fn on the materialised rollout (mpc_torch.py:121-125); everything else stays on
                 # the device path
                 e.plan_iter_rollout(i, ni, ns)
-                view = RolloutView.from_device_buffers(e.traj_, e.actions_)
-                e.plan_iter_costs(self.env.cost_fn(view["observations"], view["actions"], view["next_observations"]))
+                e.plan_iter_costs(self._cost_from_rollout(RolloutView.from_device_buffers(e.traj_, e.actions_)))
             else:
                 e.plan_iter_local(i, ni, ns)
             e.plan_iter_update(i, gather_candidates(e.cand_).contiguous() if e.world_size > 1 else e.cand_)
         e.plan_finish()
         self._iterated = True
         return e.action_out_
+
+    def _cost_from_rollout(self, view):
+        """Costs [P,E,H] of a materialised rollout for environments whose task cost the library does not know: the environment's
+        own cost_fn (mpc_torch.py:121-125); subclasses put other caller-side costs here (rnd.py)."""
+        return self.env.cost_fn(view["observations"], view["actions"], view["next_observations"])
 
     def _distributed_step(self, obs, noise):
         e = self._engine

@@ -207,7 +207,9 @@ int validate(const CeeusConfig& c, std::string& why) {
   };
   if (c.abi_version != CEEUS_ABI_VERSION) return bad("abi_version mismatch");
   if (c.model_kind != CEEUS_MODEL_GNN && c.model_kind != CEEUS_MODEL_MLP) return bad("model_kind");
-  if (c.ensemble_size < 2 || c.ensemble_size > kMaxEnsemble) return bad("ensemble_size must be in [2,8]");
+  // (one member is enough where nothing is reduced over the ensemble: task costs of a single model, the RND controller)
+  const int min_members = (c.curiosity || c.use_ensemble_cost_std) ? 2 : 1;
+  if (c.ensemble_size < min_members || c.ensemble_size > kMaxEnsemble) return bad("ensemble_size must be in [2,8] (>= 1 without an ensemble statistic)");
   if (c.num_layers < 1 || c.num_layers + 1 > kMaxLayers) return bad("num_layers must be in [1,3]");
   if (c.hidden_dim != 64 && c.hidden_dim != 128 && c.hidden_dim != 256) return bad("hidden_dim must be 64, 128 or 256");
   if (c.model_kind == CEEUS_MODEL_GNN) {

@@ -48,7 +48,7 @@ class Engine:
     def __init__(self, *, env, model_kind, ensemble_size, hidden_dim, num_layers, act_fn, layer_norm, aggr_fn="mean",
                  horizon, num_traj, sampler=None, cost_along_trajectory="sum", curiosity=True, extrinsic_reward=False,
                  extrinsic_reward_scale=1.0, num_envs=1, world_size=1, rank=0, precision="fp32", seed=0,
-                 device=None, cost_in_rollout_tail=False, gnn_variant=0, edge_global=False, num_message_passing=1,
+                 device=None, external_cost=None, cost_in_rollout_tail=False, gnn_variant=0, edge_global=False, num_message_passing=1,
                  embedding_dim=0):
         if not torch.cuda.is_available():
             raise RuntimeError("ceeus_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -66,7 +66,9 @@ class Engine:
             num_elites = 2
         num_kept = int(num_elites * float(sp["fraction_elites_reused"]))
         need_env = (not curiosity) or extrinsic_reward
-        self.external_cost = bool(need_env and d["external_cost"])
+        self.external_cost = bool(need_env and (d["external_cost"] if external_cost is None else external_cost))
+        if self.external_cost:
+            d["env_kind"] = _lib.ENV_EXTERNAL
         if need_env and not d["task_cost_supported"] and not self.external_cost:
             raise NotImplementedError(f"task cost for env kind={d['kind']} case={d['case']} is not built in and the "
                                       "environment has no cost_fn to call")

@@ -3,10 +3,12 @@
 INTEGRATION.md shows the two-line patch that merges them upstream."""
 from .controllers import B200CuriosityMpcICem, B200MpcICem
 from .models import B200GNNEnsemble, B200MLPEnsemble
+from .rnd import B200RndMpcICem
 
 CONTROLLERS = {
     "mpc-icem-b200": B200MpcICem,
     "mpc-curiosity-icem-b200": B200CuriosityMpcICem,
+    "mpc-rnd-icem-b200": B200RndMpcICem,
 }
 FORWARD_MODELS = {
     "ParallelGNNDeterministicEnsembleB200": B200GNNEnsemble,
