@@ -74,6 +74,8 @@ SIGNATURES = {
     "ceeus_plan_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ceeus_plan_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ceeus_plan_step_resident": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ceeus_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ceeus_p2p_import": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ceeus_comm_unique_id": (C.c_int, [C.c_void_p]),
     "ceeus_comm_init": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ceeus_kernel_launches": (C.c_int64, [C.c_void_p]),

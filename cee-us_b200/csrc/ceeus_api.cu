@@ -103,6 +103,12 @@ struct CeeusHandle_t {
   // gathered candidate records of all ranks [world,nE,k,rec]
   void* comm = nullptr;
   float* d_cand_all = nullptr;
+  // NVLink peer-memory exchange (ceeus_p2p_export / _import): this rank's gather double buffer + arrival flags in ONE allocation
+  // that the peers map through CUDA IPC; p2p_buf[r] / p2p_flags[r] are the mapped buffers of all ranks (own included)
+  void* p2p_local = nullptr;
+  float* p2p_buf[8] = {nullptr};
+  unsigned long long* p2p_flags[8] = {nullptr};
+  bool p2p_ready = false;
   bool bound = false, weights_set = false, norms_set = false;
   bool has_elites = false;
   unsigned long long* d_step_ctr = nullptr;  // MPC steps planned so far (base of the Philox stream ids), lives on the device
@@ -420,6 +426,9 @@ void ceeus_destroy(CeeusHandle h) {
   if (!h) return;
   drop_graphs(h);
   if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+  for (int r = 0; r < 8; ++r)
+    if (h->p2p_ready && r != h->cfg.rank && h->p2p_buf[r]) cudaIpcCloseMemHandle(h->p2p_buf[r]);
+  cudaFree(h->p2p_local);
   cudaFree(h->d_cand_all);
   if (h->gstream) cudaStreamDestroy(h->gstream);
   if (h->gevent) cudaEventDestroy(h->gevent);
@@ -703,7 +712,13 @@ int ceeus_plan_iter_costs(CeeusHandle h, const float* env_cost_dev, void* stream
   return CEEUS_OK;
 }
 
+static int plan_iter_update_impl(CeeusHandle h, int iter, const float* cand_all_dev, void* stream, bool p2p);
+
 int ceeus_plan_iter_update(CeeusHandle h, int iter, const float* cand_all_dev, void* stream) {
+  return plan_iter_update_impl(h, iter, cand_all_dev, stream, false);
+}
+
+static int plan_iter_update_impl(CeeusHandle h, int iter, const float* cand_all_dev, void* stream, bool p2p) {
   if (!h || !cand_all_dev) return fail(h, CEEUS_ERR_INVALID, "plan_iter_update: null argument");
   if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
   const CeeusConfig& c = h->cfg;
@@ -715,6 +730,11 @@ int ceeus_plan_iter_update(CeeusHandle h, int iter, const float* cand_all_dev, v
   u.n_kept_in = (iter > 0 && c.keep_previous_elites) ? c.num_kept : 0;  // mpc_torch.py:319-321
   u.pop_fresh = (long long)c.num_traj * c.world_size;
   u.alpha = c.alpha;
+  if (p2p) {
+    u.step_ctr = h->d_step_ctr; u.flags = h->p2p_flags[c.rank]; u.iters_per_step = c.opt_iterations; u.iter = iter;
+    u.half_stride = (long long)c.world_size * c.num_envs * c.num_elites * u.rec;
+    u.err = h->d_tc_err;
+  }
   LAUNCH(h, launch_update(u, S(stream)));
   return CEEUS_OK;
 }
@@ -754,6 +774,19 @@ static int enqueue_plan_step(CeeusHandle h, const float* noise_dev_or_null, void
     }
     if (int rc = ceeus_plan_iter_local(h, i, obs_dev, ni, ns, stream)) return rc;
     const float* cand_all = h->bufs.cand;
+    if (c.world_size > 1 && h->p2p_ready) {
+      // the ranks' k best candidates -> every rank's gather buffer by direct NVLink stores + a flag (no NCCL launch); the merge
+      // kernel waits for the flags of this exchange and reads the matching half of its double buffer
+      ExchangeArgs x{};
+      x.cand = h->bufs.cand; x.world = c.world_size; x.rank = c.rank;
+      x.count = c.num_envs * c.num_elites * ceeus_cand_record_len(h);
+      x.half_stride = (long long)c.world_size * x.count;
+      x.step_ctr = h->d_step_ctr; x.iters_per_step = c.opt_iterations; x.iter = i;
+      for (int r = 0; r < c.world_size; ++r) { x.peer_buf[r] = h->p2p_buf[r]; x.peer_flags[r] = h->p2p_flags[r]; }
+      LAUNCH(h, launch_exchange(x, st));
+      if (int rc = plan_iter_update_impl(h, i, h->p2p_buf[c.rank], stream, true)) return rc;
+      continue;
+    }
     if (c.world_size > 1) {
       // the ranks' k best candidates -> every rank (a few KB, latency bound); captured into the step's CUDA graph like any kernel
       const size_t cnt = (size_t)c.num_envs * c.num_elites * ceeus_cand_record_len(h);
@@ -811,8 +844,8 @@ static int launch_plan_graph(CeeusHandle h, cudaStream_t caller, bool resident, 
 
 static int plan_step_checks(CeeusHandle h) {
   if (!h->bound) return fail(h, CEEUS_ERR_STATE, "plan before bind_buffers");
-  if (h->cfg.world_size != 1 && !h->comm)
-    return fail(h, CEEUS_ERR_STATE, "world_size > 1: call ceeus_comm_init first (or drive plan_iter_local / plan_iter_update "
+  if (h->cfg.world_size != 1 && !h->comm && !h->p2p_ready)
+    return fail(h, CEEUS_ERR_STATE, "world_size > 1: call ceeus_p2p_export / _import or ceeus_comm_init first (or drive plan_iter_local / plan_iter_update "
                                     "yourself with an all-gather of the candidate records in between)");
   const bool need_env = !h->cd.curiosity || h->cd.extrinsic;
   if (need_env && h->cd.env_kind == CEEUS_ENV_EXTERNAL)
@@ -849,6 +882,49 @@ int ceeus_plan_step_resident(CeeusHandle h, const float* noise_dev_or_null, void
   if (noise_dev_or_null == nullptr && !no_graph && !h->prof_on) return launch_plan_graph(h, S(stream), true, false);
   if (int rc = enqueue_plan_step(h, noise_dev_or_null, stream, true)) return rc;
   h->has_elites = true;
+  return CEEUS_OK;
+}
+
+// ---- NVLink peer-memory exchange: buffer export / import through CUDA IPC ----
+static size_t p2p_bytes(CeeusHandle h) {
+  const size_t cnt = (size_t)h->cfg.world_size * h->cfg.num_envs * h->cfg.num_elites * ceeus_cand_record_len(h);
+  return 2 * cnt * sizeof(float) + 8 * sizeof(unsigned long long);
+}
+
+int ceeus_p2p_export(CeeusHandle h, uint8_t* handle_out) {
+  if (!h || !handle_out) return fail(h, CEEUS_ERR_INVALID, "p2p_export: null argument");
+  if (h->cfg.world_size < 2 || h->cfg.world_size > 8) return fail(h, CEEUS_ERR_INVALID, "p2p exchange needs 2..8 ranks");
+  if (!h->p2p_local) {
+    CU_CHECK(h, cudaMalloc(&h->p2p_local, p2p_bytes(h)));
+    CU_CHECK(h, cudaMemset(h->p2p_local, 0, p2p_bytes(h)));
+  }
+  cudaIpcMemHandle_t mh;
+  CU_CHECK(h, cudaIpcGetMemHandle(&mh, h->p2p_local));
+  static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(handle_out, &mh, sizeof(mh));
+  return CEEUS_OK;
+}
+
+int ceeus_p2p_import(CeeusHandle h, const uint8_t* handles) {
+  if (!h || !handles) return fail(h, CEEUS_ERR_INVALID, "p2p_import: null argument");
+  if (!h->p2p_local) return fail(h, CEEUS_ERR_STATE, "p2p_import before p2p_export");
+  const size_t flags_off = p2p_bytes(h) - 8 * sizeof(unsigned long long);
+  for (int r = 0; r < h->cfg.world_size; ++r) {
+    void* base = h->p2p_local;
+    if (r != h->cfg.rank) {
+      cudaIpcMemHandle_t mh;
+      std::memcpy(&mh, handles + (size_t)r * 64, sizeof(mh));
+      CU_CHECK(h, cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->p2p_buf[r] = reinterpret_cast<float*>(base);
+    h->p2p_flags[r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + flags_off);
+  }
+  if (!h->d_tc_err) {
+    CU_CHECK(h, cudaMalloc(&h->d_tc_err, sizeof(int)));
+    CU_CHECK(h, cudaMemset(h->d_tc_err, 0, sizeof(int)));
+  }
+  h->p2p_ready = true;
+  drop_graphs(h);
   return CEEUS_OK;
 }
 

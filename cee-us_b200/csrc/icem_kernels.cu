@@ -301,6 +301,23 @@ __global__ void __launch_bounds__(kUpdThreads) update_kernel(const UpdateArgs a,
   const int M = nc + a.n_kept_in;
   const int body = a.E + HU;
   float* stage = sm;  // [k][body]
+  const float* cand_all = a.cand_all;
+  if (a.step_ctr != nullptr) {
+    // peer-memory exchange: wait until every rank has delivered the records of THIS exchange (bounded: a rank that never plans
+    // must surface as an error flag, not as a hung GPU), then read the half of the double buffer they were written to
+    const unsigned long long x = *a.step_ctr * (unsigned long long)a.iters_per_step + (unsigned long long)a.iter;
+    if (tid < a.world) {
+      const volatile unsigned long long* f = a.flags + tid;
+      unsigned long long spins = 0;
+      while (*f < x + 1ull) {
+        __nanosleep(100);
+        if (++spins > (1ull << 24)) { if (a.err) atomicExch(a.err, 21); break; }
+      }
+    }
+    __syncthreads();
+    __threadfence_system();
+    cand_all += (x & 1ull) * a.half_stride;
+  }
   float* el_act = a.elite_actions + (size_t)env * a.k * HU;
   float* el_cost = a.elite_costs + (size_t)env * a.k;
   float* el_cpm = a.elite_cpm + (size_t)env * a.k * a.E;
@@ -310,9 +327,9 @@ __global__ void __launch_bounds__(kUpdThreads) update_kernel(const UpdateArgs a,
     Key k;
     if (t < nc) {
       const int w = t / a.k, j = t % a.k;
-      const float* rec = a.cand_all + (((size_t)w * a.nE + env) * a.k + j) * a.rec;
-      k.c = rec[0];
-      k.i = __float_as_int(rec[1]);
+      const float* rec = cand_all + (((size_t)w * a.nE + env) * a.k + j) * a.rec;
+      k.c = __ldcg(rec);  // (L2 loads: with the peer-memory exchange the records were stored by other GPUs)
+      k.i = __float_as_int(__ldcg(rec + 1));
     } else {
       const int j = t - nc;
       k.c = el_cost[j];
@@ -335,7 +352,7 @@ __global__ void __launch_bounds__(kUpdThreads) update_kernel(const UpdateArgs a,
     float v;
     if (t < nc) {
       const int w = t / a.k, j = t % a.k;
-      v = a.cand_all[(((size_t)w * a.nE + env) * a.k + j) * a.rec + 2 + q];
+      v = __ldcg(cand_all + (((size_t)w * a.nE + env) * a.k + j) * a.rec + 2 + q);
     } else {
       const int j = t - nc;
       v = q < a.E ? el_cpm[j * a.E + q] : el_act[j * HU + (q - a.E)];
@@ -468,6 +485,25 @@ cudaError_t launch_update(const UpdateArgs& a, cudaStream_t st) {
   }
   const float oma = (float)(1.0 - (double)a.alpha);
   update_kernel<<<a.nE, kUpdThreads, smem, st>>>(a, oma);
+  return cudaGetLastError();
+}
+
+// one block per destination rank: coalesced stores of the records into the peer's buffer, system-scope fence, flag
+__global__ void __launch_bounds__(256) exchange_kernel(const ExchangeArgs a) {
+  const int dst = blockIdx.x;
+  const unsigned long long x = *a.step_ctr * (unsigned long long)a.iters_per_step + (unsigned long long)a.iter;
+  float* out = a.peer_buf[dst] + (x & 1ull) * a.half_stride + (size_t)a.rank * a.count;
+  for (int i = threadIdx.x; i < a.count; i += blockDim.x) out[i] = a.cand[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned long long*>(a.peer_flags[dst] + a.rank) = x + 1ull;
+    __threadfence_system();
+  }
+}
+
+cudaError_t launch_exchange(const ExchangeArgs& a, cudaStream_t st) {
+  exchange_kernel<<<a.world, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -178,8 +178,28 @@ struct UpdateArgs {
   int world, nE, k, E, H, U, rec, n_kept_in;  // n_kept_in: kept elites joining the population (0 if none)
   long long pop_fresh;                         // P * world: global index of the first kept elite
   float alpha;
+  // peer-memory exchange (launch_exchange): cand_all is the rank's own double buffer [2][world,nE,k,rec]; the kernel picks the half of
+  // exchange number x = *step_ctr * iters_per_step + iter and first waits until every rank's flag has reached x + 1
+  const unsigned long long* step_ctr;          // null: cand_all is a plain gathered array (NCCL / caller-gathered)
+  const unsigned long long* flags;             // [world] arrival flags written by the peers
+  int iters_per_step, iter;
+  long long half_stride;                       // floats per half of the double buffer
+  int* err;                                    // set to 21 if a peer never arrives
 };
 cudaError_t launch_update(const UpdateArgs& a, cudaStream_t st);
+
+// Candidate exchange over NVLink peer memory: every rank stores its k candidate records straight into every peer's gather buffer
+// (slot `rank` of the half picked by the exchange number) and then raises its flag there -- a few KB per peer, no NCCL launch.
+struct ExchangeArgs {
+  const float* cand;            // [nE,k,rec] this rank's records
+  float* peer_buf[8];           // gather double buffers of all ranks (own included), [2][world,nE,k,rec]
+  unsigned long long* peer_flags[8];  // [world] flags of all ranks
+  int world, rank, count;       // count = nE*k*rec floats
+  long long half_stride;
+  const unsigned long long* step_ctr;
+  int iters_per_step, iter;
+};
+cudaError_t launch_exchange(const ExchangeArgs& a, cudaStream_t st);
 
 struct FinishArgs {
   float* mean;

@@ -276,10 +276,31 @@ class Engine:
             _lib.check(self.lib.ceeus_plan_step_resident(self.handle, _ptr(noise), _stream()), self.handle)
         return self.action_out_
 
-    def comm_init(self, group=None):
-        """Collective over the ranks of ``group``: creates the NCCL communicator of the library (the id travels through
-        torch.distributed).  Afterwards plan_step / plan_step_resident are one graph launch at any world size."""
+    def comm_init(self, group=None, p2p=True):
+        """Collective over the ranks of ``group``.  On one node (<= 8 ranks) the ranks map each other's candidate buffers through
+        CUDA IPC (the handles travel through torch.distributed) and exchange by direct NVLink stores; otherwise / on failure the
+        library creates an NCCL communicator.  Afterwards plan_step / plan_step_resident are one graph launch at any world size."""
         import torch.distributed as dist
+
+        if p2p and 2 <= self.world_size <= 8:
+            buf = (C.c_uint8 * 64)()
+            with torch.cuda.device(self.device):
+                rc = self.lib.ceeus_p2p_export(self.handle, buf)
+            mine = torch.tensor(list(buf), dtype=torch.uint8)
+            ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32)
+            on_dev = dist.get_backend(group) == "nccl"
+            allh = torch.zeros(self.world_size * 64, dtype=torch.uint8, device=self.device if on_dev else "cpu")
+            dist.all_gather_into_tensor(allh, mine.to(allh.device), group=group)
+            raw = (C.c_uint8 * (64 * self.world_size))(*allh.cpu().tolist())
+            if rc == 0:
+                with torch.cuda.device(self.device):
+                    rc = self.lib.ceeus_p2p_import(self.handle, raw)
+            ok[0] = 1 if rc == 0 else 0
+            ok = ok.to(allh.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # all ranks take the same path
+            if int(ok.item()) == 1:
+                self.comm_ready = True
+                return
 
         ident = torch.zeros(128, dtype=torch.uint8)
         if self.rank == 0:

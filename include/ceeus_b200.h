@@ -248,6 +248,12 @@ int ceeus_plan_step_resident(CeeusHandle h, const float* noise_dev_or_null, void
  * broadcasts it through torch.distributed); every rank then calls ceeus_comm_init (collective).  NCCL is bound at run time
  * (dlopen of libnccl.so.2, preferably the copy already loaded into the process; CEEUS_NCCL_LIB overrides the path).
  * Reference precedent for sharding trajectories over workers: ParallelGroundTruthModel.predict_n_steps, mbrl/models/gt_par_model.py:91-128. */
+/* Preferred exchange on one NVSwitch node (2..8 ranks): every rank exports its gather buffer as a CUDA IPC handle (64 bytes), the
+ * handles of all ranks are gathered by the caller and imported; from then on the candidate records travel as direct NVLink stores
+ * from a small kernel into the peers' buffers, followed by a flag -- no NCCL launch on the planning path.  A rank that stops
+ * planning surfaces in its peers as protocol error 21 (ceeus_tc_status), not as a hang. */
+int ceeus_p2p_export(CeeusHandle h, uint8_t* handle_out /* [64] */);
+int ceeus_p2p_import(CeeusHandle h, const uint8_t* handles /* [world_size][64], rank-major */);
 int ceeus_comm_unique_id(uint8_t* id_out /* [128] */);
 int ceeus_comm_init(CeeusHandle h, const uint8_t* unique_id /* [128] */);
 

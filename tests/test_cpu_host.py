@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     import ceeus_b200
 
     src = open(HEADER).read()
-    declared = set(re.findall(r"\b(ceeus_[a-z_]+)\s*\(", src))
+    declared = set(re.findall(r"\b(ceeus_[a-z0-9_]+)\s*\(", src))
     assert declared, "no declarations parsed"
     assert declared == set(ceeus_b200._lib.SIGNATURES), declared ^ set(ceeus_b200._lib.SIGNATURES)
     for name in declared:
