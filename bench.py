@@ -334,7 +334,8 @@ def gpu_measure(name, steps, warmup, precision, world, rank, dev, flush, dist, s
         "dtype": "f32" if not tc_mode else "f16 operands, f32 accumulate",
         "config": {"workload": desc, "global_traj": c["P"] * nenv * world, "traj_per_gpu": c["P"] * nenv, "horizon": c["H"],
                    "ensemble": E, "icem_iters": ITERS, "num_envs": nenv, "precision": precision,
-                   "parallelism": (f"traj-sharded x{world} (one candidate all-gather per iteration inside the step's CUDA graph)"
+                   "parallelism": (f"traj-sharded x{world} (per iteration the ranks' k best candidates are exchanged by NVLink peer-memory stores + flags, "
+                                    "or one NCCL all-gather, inside the step's CUDA graph)"
                                    if traj_sharded else f"env-sharded x{world} (no collective)") if world > 1 else "single GPU",
                    "scaling": scaling,
                    "l2": "256 MiB buffer written between timed steps (outside the timed interval)"},

@@ -1,11 +1,21 @@
-# Round measurement on one B200: GPU tests, the five BASELINE configs, the reference arm, the launch list of the default
-# bench command and one `ncu --set full` capture of the rollout kernel (configs c2 and c3).  Outputs under gpurun_out/.
-set -x
-R=${ROUND:-r1}
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for c in c1 c2 c3 c4 c5; do timeout 600 python bench.py --config $c --steps 10 --warmup 5 > gpurun_out/bench_${R}_$c.json 2>gpurun_out/bench_${R}_$c.err; tail -c 300 gpurun_out/bench_${R}_$c.json; done
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_${R}_reference.json 2>&1; tail -c 400 gpurun_out/bench_${R}_reference.json
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_ll.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${R}_tc.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_ll.log 2>&1
-bash scripts/ncu_top.sh c2 prof_${R}_tc_c2
-bash scripts/ncu_top.sh c3 prof_${R}_tc_c3
-bash scripts/ncu_top.sh c5 prof_${R}_tc_c5
+# Round measurement on one B200: launch list of the default bench command, `ncu --set full` captures of the dominant kernels.
+# Outputs under gpurun_out/ (copy the summaries into profiles/).
+R=${ROUND:-r2}
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-per-config > gpurun_out/plain_ll.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 600 --csv --log-file gpurun_out/launches_${R}_tc.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-per-config > gpurun_out/ncu_ll.log 2>&1
+cap() {  # config kernel-regex out-name [env]
+  env $4 ncu --set full --clock-control none --graph-profiling node --import-source on -k regex:$2 -s 4 -c 1 -f -o gpurun_out/$3 python bench.py --config $1 --steps 2 --warmup 3 --no-cpu-baseline --no-per-config > gpurun_out/$3_ncu.log 2>&1
+}
+cap c2 rollout_gnn_tc prof_${R}_tc_c2 A=1
+cap c3 rollout_gnn_tc prof_${R}_tc_c3 A=1
+cap c4 rollout_gnn_tc prof_${R}_tc_c4 A=1
+cap c5 rollout_mlp_tc prof_${R}_tc_c5 A=1
+cap c2 cost_compact prof_${R}_cost_c2 A=1
+cap c5 cost_compact prof_${R}_cost_c5 A=1
+cap c2 rollout_gnn_tc prof_${R}_tc_c2_tail CEEUS_COST_TAIL=1
+cap c2 rollout_gnn_tc prof_${R}_tc_c2_tail_nodiscard "CEEUS_COST_TAIL=1 CEEUS_NO_DISCARD=1"
+ls -la gpurun_out/*.ncu-rep
+# the reports are too large to travel together: summarise on the box, keep only the summaries (+ the c2 rollout report)
+for f in gpurun_out/prof_${R}_*.ncu-rep; do python profiles/summarize_ncu.py $f > ${f%.ncu-rep}.summary.txt 2>/dev/null; done
+for f in gpurun_out/prof_${R}_*.ncu-rep; do case $f in *prof_${R}_tc_c2.ncu-rep) ;; *) rm -f $f;; esac; done
+rm -f gpurun_out/*_ncu.log
