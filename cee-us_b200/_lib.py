@@ -34,7 +34,7 @@ class CeeusConfig(C.Structure):
         ("gripper_init", C.c_float * 3),
         ("world_size", C.c_int32), ("rank", C.c_int32), ("cost_in_rollout_tail", C.c_int32),
         ("gnn_variant", C.c_int32), ("edge_global", C.c_int32), ("num_message_passing", C.c_int32),
-        ("embedding_dim", C.c_int32), ("reserved0", C.c_int32),
+        ("embedding_dim", C.c_int32), ("tc_row_layout", C.c_int32),
         ("seed", C.c_uint64)]
 
 
@@ -83,6 +83,7 @@ SIGNATURES = {
     "ceeus_profile_rollouts": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_int]),
     "ceeus_tc_status": (C.c_int, [C.c_void_p]),
     "ceeus_tc_tiling": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ceeus_tc_row_layout": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -72,6 +72,7 @@ class B200MpcICem:
             raise ValueError("num_simulated_trajectories must be divisible by the number of GPUs")
         kw = self.forward_model.engine_kwargs()
         kw["precision"] = self.backend_params.get("precision", kw.get("precision", "fp32"))
+        kw["tc_row_layout"] = self.backend_params.get("tc_row_layout", kw.get("tc_row_layout", "auto"))
         self._engine = Engine(horizon=self.horizon, num_traj=self.num_sim_traj // world,
                               sampler=self.action_sampler_params, cost_along_trajectory=self.cost_along_trajectory,
                               curiosity=self._curiosity, num_envs=self.backend_params.get("num_envs", 1),

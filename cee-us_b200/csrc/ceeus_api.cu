@@ -381,7 +381,16 @@ int ceeus_create(const CeeusConfig* cfg, CeeusHandle* out) {
     if (e == cudaSuccess) e = cudaMemset(h->d_tc_err, 0, sizeof(int));
   } else if (e == cudaSuccess && c.precision == CEEUS_PREC_TC) {
     std::vector<int> kmap(4096, -1);
-    if (c.model_kind != CEEUS_MODEL_GNN || !make_tc_layout(md, h->num_sms, &h->tc, kmap.data())) {
+    int grow = 0;
+    if (c.model_kind == CEEUS_MODEL_GNN) {
+      grow = c.tc_row_layout == 1 ? 0 : c.tc_row_layout == 2 ? 1 : tc_pick_grow(md, h->num_sms, c.num_envs * c.num_traj);
+      if (c.tc_row_layout == 0) {
+        const char* ov = getenv("CEEUS_TC_ROWS");  // development / A-B override of the automatic choice
+        if (ov && ov[0] == 'n') grow = 0;
+        if (ov && ov[0] == 'g') grow = 1;
+      }
+    }
+    if (c.model_kind != CEEUS_MODEL_GNN || !make_tc_layout(md, h->num_sms, &h->tc, kmap.data(), grow)) {
       ceeus_destroy(h);
       return fail(nullptr, CEEUS_ERR_INVALID,
                   "CEEUS_PREC_TC supports the GNN ensemble with hidden_dim 64/128, 2 hidden layers, n_obj <= 32, "
@@ -853,6 +862,15 @@ static int plan_step_checks(CeeusHandle h) {
   return CEEUS_OK;
 }
 
+// status word of the tensor-core kernels: protocol error code (bounded mbarrier wait timed out) and / or CEEUS_TC_RANGE
+static int tc_error(CeeusHandle h, int st) {
+  if (st & ~CEEUS_TC_RANGE)
+    return fail(h, CEEUS_ERR_CUDA, "tensor-core rollout kernel reported protocol error " + std::to_string(st & ~CEEUS_TC_RANGE));
+  return fail(h, CEEUS_ERR_STATE,
+              "CEEUS_PREC_TC: an fp16 operand (normalised observation / action, or a hidden activation of a model without LayerNorm) "
+              "exceeded +-65504 and was saturated; the plan is unreliable -- use precision fp32 for this model / these states");
+}
+
 int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, const float* noise_dev_or_null, void* stream) {
   if (!h || !obs_host || !action_host) return fail(h, CEEUS_ERR_INVALID, "plan_step: null argument");
   if (int rc = plan_step_checks(h)) return rc;
@@ -867,8 +885,7 @@ int ceeus_plan_step(CeeusHandle h, const float* obs_host, float* action_host, co
     if (!h->capturing) h->has_elites = true;
     CU_CHECK(h, cudaStreamSynchronize(st));
   }
-  if (h->d_tc_err && *h->h_tc_err != 0)
-    return fail(h, CEEUS_ERR_CUDA, "tensor-core rollout kernel reported protocol error " + std::to_string(*h->h_tc_err));
+  if (h->d_tc_err && *h->h_tc_err != 0) return tc_error(h, *h->h_tc_err);
   std::memcpy(action_host, h->h_action, (size_t)c.num_envs * h->md.U * sizeof(float));
   return CEEUS_OK;
 }
@@ -1028,6 +1045,12 @@ int ceeus_tc_tiling(CeeusHandle h, int n, int32_t* rounds_out, int32_t* uneven_o
     }
   }
   return CEEUS_OK;
+}
+
+int ceeus_tc_row_layout(CeeusHandle h) {
+  if (!h) return CEEUS_ERR_INVALID;
+  if (h->cfg.precision != CEEUS_PREC_TC || h->md.kind != CEEUS_MODEL_GNN) return 0;
+  return h->tc.grow ? 2 : 1;
 }
 
 int ceeus_tc_status(CeeusHandle h) {

@@ -57,6 +57,13 @@ struct TcLayout {
   int so_obs, obs_bytes, so_glob, so_snrm, so_tail, so_actn;  // offsets inside a slot region; bytes of one warp's observation staging
   int pairs;               // CTA pairs in the grid
   int scratch_floats;      // per member: logical fp32 matrices built by the pack kernels
+  // "global row" tiling (grow = 1): a trajectory owns N node rows + 1 global row of the tile, the node and the global MLP run as
+  // ONE K-stacked stage each (NG1, NG2, NG3: 2(N-1) + 3 stages per model step instead of 2(N-1) + 6).  The raw-input K blocks
+  // ([hdr | x_i] of the node rows, [hdr] of the global rows) and the constant-one bias blocks are shared-memory A operands.
+  int grow;
+  int so_xa;               // inside a slot region: A tile [6 chunks][128 rows][16 B]: hdr_N(2) | x_i(2) | hdr_G(2)
+  int sm_one;              // per CTA: constant A tile [4 chunks][128 rows][16 B]: one-hot(node rows)(2) | one-hot(global rows)(2)
+  int sm_neg;              // per CTA: HD floats of -60000 (LayerNorm beta that zeroes a row through the ReLU)
 };
 // How the n trajectories of one launch are dealt to the CTA pairs / slots of one ensemble member (shared by the kernel and by
 // ceeus_tc_tiling, so the parity tests can assert which tiling branch a case exercises).
@@ -79,7 +86,10 @@ __host__ __device__ inline TcTile tc_tile(int pairs, int E, int pair, int n, int
   t.uneven = (t.T > 3 * tpw && t.q_un <= tpw) ? 1 : 0;
   return t;
 }
-bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_host /* [kmap_len] or null */);
+bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_host /* [kmap_len] or null */, int grow = 0);
+// Row layout of the tensor-core GNN rollout for launches over n trajectories: 1 if the "global row" tiling is expected to be
+// faster (fewer stages per step at the price of N + 1 instead of N tile rows per trajectory), by a stage-count / MMA-time model.
+int tc_pick_grow(const ModelDesc& md, int num_sms, int n);
 cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, const int* kmap_dev, float* scratch,
                            uint8_t* wimg, float* wpar, cudaStream_t st);
 cudaError_t launch_rollout_gnn_tc(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,

@@ -141,6 +141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
   tmem_st4(t_one + 4, make_uint4(0u, 0u, 0u, 0u));
   tmem_wait_st();
 
+  uint32_t satm = 0u;  // record of saturated fp16 operand conversions of this thread (tc_common.cuh: sat_track)
   for (int rd = 0; rd < rounds; ++rd) {
     const int w_lo = min(ra.n, worker * per_worker), w_hi = min(ra.n, w_lo + per_worker);
     const int p0 = w_lo + rd * T;
@@ -159,7 +160,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
     for (int idx = tid; idx < Gc * in; idx += kMlpThreads) {
       const int b = idx / in, c = idx % in;
       const float x = c < sd ? s_state[b * sd + c] : __ldg(ra.actions + ((size_t)(p0 + b) * ra.H) * U + (c - sd));
-      snrm[b * SNS + c] = __float2half_rn((x - nrm[md.nrm.in_all + c]) * nrm[md.nrm.in_all + in + c]);
+      satm = sat_track1(satm, snrm[b * SNS + c] = half_sat((x - nrm[md.nrm.in_all + c]) * nrm[md.nrm.in_all + in + c]));
     }
     if (tid < 128 && live) snrm[tid * SNS + in] = __float2half_rn(1.f);
     // the goal part of every predicted observation (env.obs_postproc) is constant along the horizon: written here, once
@@ -211,7 +212,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
               tmem_ld32(t_acc + hf * W + c0, *reinterpret_cast<uint32_t(*)[32]>(&x[0]));
               tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) hc[j / 2] = pack_half2(mlp_act<SILU>(x[j], act), mlp_act<SILU>(x[j + 1], act));
+              for (int j = 0; j < 32; j += 2) {
+                hc[j / 2] = pack_half2(mlp_act<SILU>(x[j], act), mlp_act<SILU>(x[j + 1], act));
+                // no LayerNorm bounds these activations: record a saturated conversion (SiLU >= -0.28: positive side only)
+                satm = SILU ? sat_track_pos(satm, hc[j / 2]) : sat_track(satm, hc[j / 2]);
+              }
               tmem_st16(t_a + (hf * W + c0) / 2, hc);
             }
           }
@@ -241,6 +246,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
                     if (d0 + j < sd) outr[d0 + j] = na;
                     if (d0 + j + 1 < sd) outr[d0 + j + 1] = nb;
                     pk[j / 2] = pack_half2((na - ta.z) * ta.w, (nb - tb.z) * tb.w);
+                    satm = sat_track(satm, pk[j / 2]);
                   }
                   __half* dst = snrm + row * SNS + d0;
                   if (d0 + 16 <= sd) {
@@ -258,13 +264,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
           if (hf == 1 && live && h + 1 < ra.H) {
             asm volatile("cp.async.wait_all;" ::: "memory");
             for (int j = 0; j < U; ++j)
-              snrm[row * SNS + sd + j] = __float2half_rn((s_act[row * 8 + j] - nrm[md.nrm.in_all + sd + j]) * nrm[md.nrm.in_all + in + sd + j]);
+              satm = sat_track1(satm, snrm[row * SNS + sd + j] = half_sat((s_act[row * 8 + j] - nrm[md.nrm.in_all + sd + j]) * nrm[md.nrm.in_all + in + sd + j]));
           }
           tc_fence_before();
         }
       }
       cta_sync();  // snrm of the next step is complete
     }
+    if (sat_hit(satm)) atomicOr(err, kTcRangeFlag);  // an fp16 operand left the representable range somewhere in this round
   }
   // ---- fused cost tail (planner launches), after the round loop so that nothing of the step loop is live here ----
   // This member's rollouts of the CTA's tiles are complete: warp w arrives for the trajectories w, w + 8, ... of every tile and

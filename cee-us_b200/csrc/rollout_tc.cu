@@ -27,6 +27,8 @@
 //     LayerNorm statistics stay fp32.  Parity bar: 1e-3 (BASELINE.json north_star, tf32/bf16 mode).
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -68,7 +70,8 @@ __device__ __forceinline__ void store_hidden(uint32_t taddr, const uint32_t (&h)
 // one FFMA per element and one parameter vector (pbe = beta / |gamma|).  General path: xhat * gamma + beta, any activation.
 template <int HD, bool RELU, bool FOLD>
 __device__ __forceinline__ void epi_row(uint32_t tacc, const float* __restrict__ pb, const float* __restrict__ pg,
-                                        const float* __restrict__ pbe, bool ln, bool fold, int act, uint32_t (&h)[HD / 2]) {
+                                        const float* __restrict__ pbe, bool ln, bool fold, int act, uint32_t (&h)[HD / 2],
+                                        uint32_t& satm) {
   float x[HD];
 #pragma unroll
   for (int c0 = 0; c0 < HD; c0 += 32) tmem_ld32(tacc + c0, *reinterpret_cast<uint32_t(*)[32]>(&x[c0]));
@@ -123,6 +126,11 @@ __device__ __forceinline__ void epi_row(uint32_t tacc, const float* __restrict__
 #pragma unroll 4
     for (int j = 0; j < HD; j += 2) h[j / 2] = pack_half2(act_fn(x[j], act), act_fn(x[j + 1], act));
   }
+  // without a LayerNorm nothing bounds the hidden activations: record a saturated conversion (with one, |xhat| <= sqrt(HD))
+  if (!ln) {
+#pragma unroll
+    for (int j = 0; j < HD / 2; ++j) satm = sat_track(satm, h[j]);
+  }
 }
 
 // MMA issue of one stage (leader CTA, one warp): wait for both CTAs' A operands, issue the K steps, commit to both CTAs.
@@ -161,6 +169,76 @@ __device__ __forceinline__ void tc_issue_stage(volatile int* abort_flag, int* er
   __syncwarp();
 }
 
+// "Global row" tiling (TcLayout::grow): stage kinds of one model step.  The node MLP (rows (b, i)) and the global MLP (rows (b, N))
+// run as ONE stage each: the two layers are stacked along K -- a row presents its input in the K block of its own role and zeros in
+// the other role's block, so one accumulation chain applies N-weights to node rows and G-weights to global rows.
+enum { GK_E1 = 0, GK_E2, GK_NG1, GK_NG2, GK_NG3 };
+
+// MMA issue of one stage of the global-row tiling.  TMEM A blocks: R1 = [m_acc + HD, +HD/2) and R2 = [m_acc + 3 HD / 2, +HD/2).
+//   E1 : R1[0:48 halves) = [hdr | x_i | x_j]                                  x E1
+//   E2 : R1 = hidden of E1                                                     x E2[0:HD)      + one(node rows) x E2[HD:HD+16) (bias)
+//   NG1: smem [hdr_N | x_i] x N1[0:32), smem [hdr_G] x G1[0:16), R2 (node aggregate) x N1[32:), R1 (global aggregate) x G1[16:)
+//   NG2: R2 x N2[0:HD), R1 x G2[0:HD), one(node) x N2[HD:+16), one(global) x G2[HD:+16)
+//   NG3: R2 x N3, R1 x G3 (16 output columns)
+// Node rows keep R1 = 0 and global rows R2 = 0 from the last E2 epilogue to the end of the step.
+template <int HD, int KIND>
+__device__ __forceinline__ void tc_issue_grow(volatile int* abort_flag, int* err, uint64_t* a_bar, uint32_t aph, uint64_t* d_bar,
+                                              uint32_t wbase, const TcLayout& tl, uint32_t m_acc, uint32_t xa_addr, uint32_t one_addr) {
+  Ctx cx;
+  cx.abort = abort_flag; cx.err = err;
+  const bool ok = wait_bar_spin(cx, a_bar, aph, 2);
+  tc_fence_after();
+  if (ok) {
+    const uint32_t elected = elect_one();
+    constexpr int KH = HD / 16;  // K steps of a hidden row
+    constexpr uint32_t idesc_h = make_idesc_f16(256, HD), idesc_o = make_idesc_f16(256, 16);
+    constexpr uint32_t lbo_h = (uint32_t)(HD / 2) * 16, lbo_o = 8u * 16u;
+    constexpr uint32_t st_h = (2u * lbo_h) >> 4, st_o = (2u * lbo_o) >> 4;  // descriptor start-address advance per K step
+    constexpr uint32_t st_a = (2u * 2048u) >> 4;                            // shared-memory A tiles: 2048 bytes per 8-half K chunk
+    const uint32_t m_r1 = m_acc + HD, m_r2 = m_r1 + HD / 2;
+    uint32_t acc = 0u;
+    auto ts = [&](uint32_t a_col, uint64_t db, uint32_t idesc) { umma_f16_ts_cg2_elect(m_acc, a_col, db, idesc, acc, elected); acc = 1u; };
+    auto ss = [&](uint64_t da, uint64_t db, uint32_t idesc) { umma_f16_ss_cg2_elect(m_acc, da, db, idesc, acc, elected); acc = 1u; };
+    auto bh = [&](int m) { return make_smem_desc(wbase + (uint32_t)tl.mat[m].off, lbo_h, 128); };
+    auto bo = [&](int m) { return make_smem_desc(wbase + (uint32_t)tl.mat[m].off, lbo_o, 128); };
+    if constexpr (KIND == GK_E1) {
+      const uint64_t db = bh(TC_E1);
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks) ts(m_r1 + 8u * ks, db + (uint64_t)(ks * st_h), idesc_h);
+    } else if constexpr (KIND == GK_E2) {
+      const uint64_t db = bh(TC_E2);
+#pragma unroll
+      for (int ks = 0; ks < KH; ++ks) ts(m_r1 + 8u * ks, db + (uint64_t)(ks * st_h), idesc_h);
+      ss(make_smem_desc(one_addr, 2048, 128), db + (uint64_t)(KH * st_h), idesc_h);
+    } else if constexpr (KIND == GK_NG1) {
+      const uint64_t dn = bh(TC_N1), dg = bh(TC_G1), da = make_smem_desc(xa_addr, 2048, 128);
+      ss(da, dn, idesc_h);
+      ss(da + st_a, dn + st_h, idesc_h);
+      ss(da + 2 * st_a, dg, idesc_h);
+#pragma unroll
+      for (int j = 0; j < KH; ++j) ts(m_r2 + 8u * j, dn + (uint64_t)((2 + j) * st_h), idesc_h);
+#pragma unroll
+      for (int j = 0; j < KH; ++j) ts(m_r1 + 8u * j, dg + (uint64_t)((1 + j) * st_h), idesc_h);
+    } else if constexpr (KIND == GK_NG2) {
+      const uint64_t dn = bh(TC_N2), dg = bh(TC_G2), d1 = make_smem_desc(one_addr, 2048, 128);
+#pragma unroll
+      for (int j = 0; j < KH; ++j) ts(m_r2 + 8u * j, dn + (uint64_t)(j * st_h), idesc_h);
+#pragma unroll
+      for (int j = 0; j < KH; ++j) ts(m_r1 + 8u * j, dg + (uint64_t)(j * st_h), idesc_h);
+      ss(d1, dn + (uint64_t)(KH * st_h), idesc_h);
+      ss(d1 + st_a, dg + (uint64_t)(KH * st_h), idesc_h);
+    } else {
+      const uint64_t dn = bo(TC_N3), dg = bo(TC_G3);
+#pragma unroll
+      for (int j = 0; j < KH; ++j) ts(m_r2 + 8u * j, dn + (uint64_t)(j * st_o), idesc_o);
+#pragma unroll
+      for (int j = 0; j < KH; ++j) ts(m_r1 + 8u * j, dg + (uint64_t)(j * st_o), idesc_o);
+    }
+    umma_commit_cg2_mc_elect(d_bar, 0x3, elected);
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Row layout ("node major"): TMEM lane == tile row == (trajectory b, node i); a warp owns 32 / N whole trajectories, so every
 // exchange between the rows of a trajectory stays inside one warp (__syncwarp, no block barriers in the step loop).
@@ -169,7 +247,7 @@ __device__ __forceinline__ void tc_issue_stage(volatile int* abort_flag, int* er
 //   * the sum over all edges of a trajectory (global aggregate) is formed once per step from the N node aggregates through a
 //     warp-private staging buffer and parked in shared memory until the global tile needs it.
 //   * node tile rows == the same lanes; global tile row of trajectory b == lane (b, 0).
-template <int HD, bool RELU, bool DBG, bool FOLD>
+template <int HD, bool RELU, bool DBG, bool FOLD, bool GROW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::value, 1)
     rollout_gnn_tc_kernel(const ModelDesc md, const RolloutArgs ra, const TcLayout tl, const uint8_t* __restrict__ wimg,
                           const float* __restrict__ wpar, int* __restrict__ err, long long* __restrict__ dbg,
@@ -192,7 +270,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
   const TcTile tt = tc_tile(tl.pairs, md.E, pair, ra.n, NS, tl.Tmax, tl.tpw);
   const int e = tt.e, lp = tt.lp, np = tt.np, per_worker = tt.per_worker, rounds = tt.rounds, T = tt.T, q_un = tt.q_un;
   const bool uneven = tt.uneven != 0;
-  const int n_stage = 2 * (N - 1) + 6;
+  const int n_stage = 2 * (N - 1) + (GROW ? 3 : 6);
+  const int R = N + (GROW ? 1 : 0);  // tile rows per trajectory
 
   uint8_t* sW = smem + tl.sm_w;
   float* sPar = reinterpret_cast<float*>(smem + tl.sm_par);
@@ -228,6 +307,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     const bool inv = (i >= md.nrm.in_agent + md.A && i < md.nrm.in_dyn) || (i >= md.nrm.in_dyn + md.D && i < md.nrm.in_stat) ||
                      (i >= md.nrm.in_stat + md.S && i < md.nrm.in_action) || (i >= md.nrm.in_action + md.U && i < md.nrm.out_agent);
     sNrm[i] = inv ? 1.f / v : v;
+  }
+  if constexpr (GROW) {
+    // constant A tile of the bias K blocks: chunks 0-1 = [1, 0 ..] on node rows, chunks 2-3 = [1, 0 ..] on global rows; the
+    // slots' [hdr | x_i | hdr] tiles start out zero (a row only ever writes the chunks of its own role)
+    uint8_t* sOne = smem + tl.sm_one;
+    for (int i = tid; i < 4 * 128; i += kTcThreads) {
+      const int chunk = i >> 7, r = i & 127, ln = r & 31;
+      const int bwr = ln / R, nir = ln - bwr * R;
+      const bool okr = bwr < tl.tpw, isg = nir == N;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (okr && ((chunk == 0 && !isg) || (chunk == 2 && isg))) v.x = 0x00003c00u;
+      *reinterpret_cast<uint4*>(sOne + chunk * 2048 + r * 16) = v;
+    }
+    for (int sl = 0; sl < NS; ++sl)
+      for (int i = tid; i < 6 * 128; i += kTcThreads)
+        *reinterpret_cast<uint4*>(smem + tl.sm_slot[sl] + tl.so_xa + i * 16) = make_uint4(0u, 0u, 0u, 0u);
+    float* sNegI = reinterpret_cast<float*>(smem + tl.sm_neg);
+    for (int i = tid; i < HD; i += kTcThreads) sNegI[i] = -60000.f;
+    fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
@@ -281,7 +379,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     const uint32_t t_acc = lane_base, t_r1 = lane_base + HD, t_r2 = lane_base + HD + HD / 2;
     uint32_t dph = 0;
     int dbg_n = 0;
-    const bool dbg_on = DBG && dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool dbg_on = DBG && dbg != nullptr && (long long)blockIdx.x == (dbg[499] >> 8) && tid == 0;  // probed CTA: flag >> 8
     auto stamp = [&](int tag) {
       if constexpr (!DBG) return;  // the timeline probes exist only in the profiling instantiation
       if (dbg_on && dbg_n < 250) { dbg[2 * dbg_n] = tag; dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
@@ -291,9 +389,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     // The warps of a slot are filled with trajectories in order; odd slots fill from the last scheduler backwards, so that at
     // partial fill the busy warps of neighbouring slots sit on different schedulers.
     const int qf = (s & 1) ? 3 - q : q;
-    const int bw = lane / N, ni = lane - bw * N;  // trajectory inside the warp, node
+    const int bw = lane / R, ni = lane - bw * R;  // trajectory inside the warp, node (GROW: ni == N is the trajectory's global row)
     const bool lane_ok = bw < tpw;
+    const bool is_g = GROW && (ni == N || !lane_ok);  // idle lanes behave like (dead) global rows
     const int b = qf * tpw + min(bw, tpw - 1);  // group-local trajectory of this row (clamped for the idle lanes)
+    const int nix = GROW ? min(ni, N - 1) : ni;  // (global rows ride through the edge stages on finite filler data)
+    const float* sNeg = reinterpret_cast<const float*>(smem + tl.sm_neg);
+    uint8_t* xa_row = slot + tl.so_xa + row * 16;
 
     // ---- MMA issue: the last-filled warp of the warpgroup in the leader CTA waits for both CTAs' A operands and issues ----
     const bool issuer_warp = rank == 0 && qf == 3;
@@ -303,17 +405,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     auto mma_stage = [&](int kind) {
       if (!issuer_warp) return;
       stamp(70 + kind);
-      const uint32_t wd = wbase + (uint32_t)tl.mat[kind].off;
-      const int n2 = N == 2;
-      switch (kind) {
-        case TC_E1: tc_issue_stage<HD, TC_E1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
-        case TC_E2: tc_issue_stage<HD, TC_E2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
-        case TC_N1: tc_issue_stage<HD, TC_N1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
-        case TC_N2: tc_issue_stage<HD, TC_N2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
-        case TC_N3: tc_issue_stage<HD, TC_N3>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
-        case TC_G1: tc_issue_stage<HD, TC_G1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
-        case TC_G2: tc_issue_stage<HD, TC_G2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
-        default: tc_issue_stage<HD, TC_G3>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+      if constexpr (GROW) {
+        const uint32_t xa = smem_u32(slot + tl.so_xa), one = smem_u32(smem + tl.sm_one);
+        switch (kind) {
+          case GK_E1: tc_issue_grow<HD, GK_E1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wbase, tl, m_acc, xa, one); break;
+          case GK_E2: tc_issue_grow<HD, GK_E2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wbase, tl, m_acc, xa, one); break;
+          case GK_NG1: tc_issue_grow<HD, GK_NG1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wbase, tl, m_acc, xa, one); break;
+          case GK_NG2: tc_issue_grow<HD, GK_NG2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wbase, tl, m_acc, xa, one); break;
+          default: tc_issue_grow<HD, GK_NG3>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wbase, tl, m_acc, xa, one); break;
+        }
+      } else {
+        const uint32_t wd = wbase + (uint32_t)tl.mat[kind].off;
+        const int n2 = N == 2;
+        switch (kind) {
+          case TC_E1: tc_issue_stage<HD, TC_E1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+          case TC_E2: tc_issue_stage<HD, TC_E2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+          case TC_N1: tc_issue_stage<HD, TC_N1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+          case TC_N2: tc_issue_stage<HD, TC_N2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+          case TC_N3: tc_issue_stage<HD, TC_N3>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+          case TC_G1: tc_issue_stage<HD, TC_G1>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+          case TC_G2: tc_issue_stage<HD, TC_G2>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+          default: tc_issue_stage<HD, TC_G3>(abort_flag, err, &a_ready[s], aph, &d_ready[s], wd, m_acc, n2); break;
+        }
       }
       aph ^= 1u;
       stamp(90 + kind);
@@ -332,6 +445,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     constexpr bool kStateInSmem = HD == 64;
     float* s_actn = reinterpret_cast<float*>(slot + tl.so_actn) + (size_t)row * 8;
     float dyn[16], agent[16], act_next[8];
+    uint32_t satm = 0u;  // record of saturated fp16 operand conversions of this thread (sat_track)
 #pragma unroll
     for (int j = 0; j < 16; ++j) { dyn[j] = 0.f; agent[j] = 0.f; }  // padded entries take part in the vectorised output update
 
@@ -350,9 +464,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       }
       const int p0 = w_lo + rd * Tw;
       int Gc = max(0, min(Tw, w_hi - p0));  // live trajectories of this group (0: pure lock-step filler)
-      if (DBG && dbg != nullptr && dbg[499] == 1 && s == 1) Gc = 0;  // profiling aid: slot 1 idles, slot 0 runs without SIMT contention
+      if (DBG && dbg != nullptr && (dbg[499] & 1) && s == 1) Gc = 0;  // profiling aid: slot 1 idles, slot 0 runs without SIMT contention
       const bool live = lane_ok && b < Gc;
-      const bool live_g = live && ni == 0;
+      const bool live_n = GROW ? (live && !is_g) : live;              // row carries a node of a live trajectory
+      const bool live_g = GROW ? (live && is_g) : (live && ni == 0);  // row carries the agent / global features of a live trajectory
       const bool warp_on = qf * tpw < Gc;  // this warp owns at least one live trajectory
       const uint4* sb = reinterpret_cast<const uint4*>(snrm + b * SNs);  // this row's trajectory: [hdr(2) | node blocks (2 each)]
       wg_sync(s);
@@ -375,7 +490,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
         const int tb = idx / tail, c = idx % tail;
         s_obs[tb * O + (A + N * D) + c] = qf * tpw + tb < Gc ? s_tail[(qf * tpw + tb) * tail + c] : 0.f;
       }
-      if (live) {
+      if (live_n) {
         const float* so = ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O;
         __half* dst = snrm + b * SNs + kAU + ni * kNA;
 #pragma unroll
@@ -384,10 +499,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
             const float v0 = __ldg(so + A + ni * D + j);
             dyn[j] = v0;
             s_obs[bw * O + A + ni * D + j] = v0;
-            dst[j] = __float2half_rn((v0 - nrm[md.nrm.in_dyn + j]) * nrm[md.nrm.in_dyn + D + j]);
+            dst[j] = half_sat((v0 - nrm[md.nrm.in_dyn + j]) * nrm[md.nrm.in_dyn + D + j]);
+            satm = sat_track1(satm, dst[j]);
           }
         for (int j = 0; j < S; ++j)
-          dst[D + j] = __float2half_rn((__ldg(so + A + N * D + ni * S + j) - nrm[md.nrm.in_stat + j]) * nrm[md.nrm.in_stat + S + j]);
+          satm = sat_track1(satm, dst[D + j] = half_sat((__ldg(so + A + N * D + ni * S + j) - nrm[md.nrm.in_stat + j]) * nrm[md.nrm.in_stat + S + j]));
       }
       if (live_g) {
         const float* so = ra.start_obs + (size_t)((p0 + b) / ra.traj_per_start) * O;
@@ -398,22 +514,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
             const float v0 = __ldg(so + j);
             agent[j] = v0;
             s_obs[bw * O + j] = v0;
-            dst[j] = __float2half_rn((v0 - nrm[md.nrm.in_agent + j]) * nrm[md.nrm.in_agent + A + j]);
+            satm = sat_track1(satm, dst[j] = half_sat((v0 - nrm[md.nrm.in_agent + j]) * nrm[md.nrm.in_agent + A + j]));
           }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (j < U) {
             const float a0 = __ldg(ra.actions + ((size_t)(p0 + b) * ra.H) * U + j);
-            dst[A + j] = __float2half_rn((a0 - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]);
+            satm = sat_track1(satm, dst[A + j] = half_sat((a0 - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]));
           }
         dst[A + U] = __float2half_rn(1.f);
       }
       wg_sync(s);
 
+      if constexpr (GROW) {
+        // TMEM A blocks start out zero: global rows keep R2 = 0 for the whole group, and nothing uninitialised (NaN patterns)
+        // can reach a block that another role's weights are applied to
+        if (warp_on) {
+          uint32_t z[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] = 0u;
+#pragma unroll
+          for (int c0 = 0; c0 < HD; c0 += 32) tmem_st32(t_r1 + c0, z);
+          tmem_wait_st();
+        }
+      }
+      // raw-input K blocks of the NG1 stage (shared-memory A tile): node rows [hdr | x_i], global rows [hdr]
+      auto write_xa = [&]() {
+        const uint4 h0 = sb[0], h1 = sb[1];
+        if (is_g) {
+          *reinterpret_cast<uint4*>(xa_row + 4 * 2048) = h0;
+          *reinterpret_cast<uint4*>(xa_row + 5 * 2048) = h1;
+        } else {
+          *reinterpret_cast<uint4*>(xa_row) = h0;
+          *reinterpret_cast<uint4*>(xa_row + 2048) = h1;
+          *reinterpret_cast<uint4*>(xa_row + 2 * 2048) = sb[2 + 2 * nix];
+          *reinterpret_cast<uint4*>(xa_row + 3 * 2048) = sb[3 + 2 * nix];
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+      };
       // A operand of edge pass jj: [hdr | x_i | x_j] of this row's edge -> R1 (KE1 = 48 halves = 24 columns)
       auto build_edge = [&](int jj) {
-        const int nj = min(jj + (jj >= ni ? 1 : 0), N - 1);
-        const uint4 h0 = sb[0], h1 = sb[1], xi0 = sb[2 + 2 * ni], xi1 = sb[3 + 2 * ni], xj0 = sb[2 + 2 * nj], xj1 = sb[3 + 2 * nj];
+        const int nj = min(jj + (jj >= nix ? 1 : 0), N - 1);
+        const uint4 h0 = sb[0], h1 = sb[1], xi0 = sb[2 + 2 * nix], xi1 = sb[3 + 2 * nix], xj0 = sb[2 + 2 * nj], xj1 = sb[3 + 2 * nj];
         const uint32_t v[16] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w, xi0.x, xi0.y, xi0.z, xi0.w, xi1.x, xi1.y, xi1.z, xi1.w};
         const uint32_t w[8] = {xj0.x, xj0.y, xj0.z, xj0.w, xj1.x, xj1.y, xj1.z, xj1.w};
         tmem_st16(t_r1, v);
@@ -442,6 +584,90 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
         for (int i = lane; i < n_out; i += 32) og[i] = s_obs[i];
       };
 
+      // node output: delta -> de-normalise, residual update (gnn_ensemble.py:302-334, 935-939); row of node ni
+      auto node_update = [&](const uint32_t (&v)[16]) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(snrm + b * SNs + kAU + ni * kNA);
+        float* og = s_obs + bw * O + A + ni * D;
+        const float4* tb = reinterpret_cast<const float4*>(sOut);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          if (4 * j4 < D) {
+            const float4 c1 = tb[j4], c0 = tb[4 + j4], mi = tb[8 + j4], is = tb[12 + j4];
+            // (padded entries: c1 = c0 = 0 and the old value is taken as 0)
+            float o0, o1, o2, o3;
+            if constexpr (kStateInSmem) {
+              o0 = 4 * j4 < D ? og[4 * j4] : 0.f; o1 = 4 * j4 + 1 < D ? og[4 * j4 + 1] : 0.f;
+              o2 = 4 * j4 + 2 < D ? og[4 * j4 + 2] : 0.f; o3 = 4 * j4 + 3 < D ? og[4 * j4 + 3] : 0.f;
+            } else {
+              o0 = dyn[4 * j4]; o1 = dyn[4 * j4 + 1]; o2 = dyn[4 * j4 + 2]; o3 = dyn[4 * j4 + 3];
+            }
+            const float n0 = o0 + fmaf(c1.x, __uint_as_float(v[4 * j4]), c0.x);
+            const float n1 = o1 + fmaf(c1.y, __uint_as_float(v[4 * j4 + 1]), c0.y);
+            const float n2 = o2 + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
+            const float n3 = o3 + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
+            if constexpr (!kStateInSmem) { dyn[4 * j4] = n0; dyn[4 * j4 + 1] = n1; dyn[4 * j4 + 2] = n2; dyn[4 * j4 + 3] = n3; }
+            if (4 * j4 < D) og[4 * j4] = n0;
+            if (4 * j4 + 1 < D) og[4 * j4 + 1] = n1;
+            if (4 * j4 + 2 < D) og[4 * j4 + 2] = n2;
+            if (4 * j4 + 3 < D) og[4 * j4 + 3] = n3;
+            // padded entries have c1 = c0 = mi = is = 0 -> exact zeros, like the zero padding of the node block
+            const uint32_t w01 = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y), w23 = pack_half2((n2 - mi.z) * is.z, (n3 - mi.w) * is.w);
+            satm = sat_track(sat_track(satm, w01), w23);
+            if (4 * j4 + 1 < D || S == 0) dst[2 * j4] = w01;
+            else reinterpret_cast<unsigned short*>(dst)[4 * j4] = (unsigned short)(w01 & 0xffffu);
+            if (4 * j4 + 3 < D || (S == 0 && 4 * j4 + 2 < D)) dst[2 * j4 + 1] = w23;
+            else if (4 * j4 + 2 < D) reinterpret_cast<unsigned short*>(dst)[4 * j4 + 2] = (unsigned short)(w23 & 0xffffu);
+          }
+        }
+      
+      };
+      // global output: agent delta, next action; row carrying the agent features
+      auto agent_update = [&](const uint32_t (&v)[16], int h) {
+        __half* dsth = snrm + b * SNs;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(dsth);
+        float* og = s_obs + bw * O;
+        const float4* tb = reinterpret_cast<const float4*>(sOut + 64);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          if (4 * j4 < A) {
+            const float4 c1 = tb[j4], c0 = tb[4 + j4], mi = tb[8 + j4], is = tb[12 + j4];
+            float o0, o1, o2, o3;
+            if constexpr (kStateInSmem) {
+              o0 = 4 * j4 < A ? og[4 * j4] : 0.f; o1 = 4 * j4 + 1 < A ? og[4 * j4 + 1] : 0.f;
+              o2 = 4 * j4 + 2 < A ? og[4 * j4 + 2] : 0.f; o3 = 4 * j4 + 3 < A ? og[4 * j4 + 3] : 0.f;
+            } else {
+              o0 = agent[4 * j4]; o1 = agent[4 * j4 + 1]; o2 = agent[4 * j4 + 2]; o3 = agent[4 * j4 + 3];
+            }
+            const float n0 = o0 + fmaf(c1.x, __uint_as_float(v[4 * j4]), c0.x);
+            const float n1 = o1 + fmaf(c1.y, __uint_as_float(v[4 * j4 + 1]), c0.y);
+            const float n2 = o2 + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
+            const float n3 = o3 + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
+            if constexpr (!kStateInSmem) { agent[4 * j4] = n0; agent[4 * j4 + 1] = n1; agent[4 * j4 + 2] = n2; agent[4 * j4 + 3] = n3; }
+            if (4 * j4 < A) og[4 * j4] = n0;
+            if (4 * j4 + 1 < A) og[4 * j4 + 1] = n1;
+            if (4 * j4 + 2 < A) og[4 * j4 + 2] = n2;
+            if (4 * j4 + 3 < A) og[4 * j4 + 3] = n3;
+            // the agent part is followed by the action in the header: only whole pairs may be written as 32 bits
+            const uint32_t w01 = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y), w23 = pack_half2((n2 - mi.z) * is.z, (n3 - mi.w) * is.w);
+            satm = sat_track(sat_track(satm, w01), w23);
+            if (4 * j4 + 1 < A) dst[2 * j4] = w01;
+            else reinterpret_cast<unsigned short*>(dsth)[4 * j4] = (unsigned short)(w01 & 0xffffu);
+            if (4 * j4 + 3 < A) dst[2 * j4 + 1] = w23;
+            else if (4 * j4 + 2 < A) reinterpret_cast<unsigned short*>(dsth)[4 * j4 + 2] = (unsigned short)(w23 & 0xffffu);
+          }
+        }
+        if (h + 1 < ra.H) {
+          if constexpr (kStateInSmem) asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < U) {
+              const float an = kStateInSmem ? s_actn[j] : act_next[j];
+              satm = sat_track1(satm, dsth[A + j] = half_sat((an - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]));
+            }
+        }
+      
+      };
+
       for (int h = 0; h < ra.H; ++h) {
         stamp(100);
         if (live_g && h + 1 < ra.H) {  // prefetch the next step's action; consumed in the G3 epilogue
@@ -453,16 +679,122 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
               else act_next[j] = __ldg(src);
             }
         }
-        if (warp_on) build_edge(0);
+        if (warp_on) {
+          if constexpr (GROW) write_xa();
+          build_edge(0);
+        }
         signal_a(cx, s, lane);
         mma_stage(TC_E1);
-        if (h > 0) flush_outputs(h - 1);
+        if (!GROW && h > 0) flush_outputs(h - 1);  // (global-row tiling: in the shadow of the longest MMA stage, NG1)
 
 #pragma unroll 1
         for (int st = 0; st < n_stage; ++st) {
           const int kind = kind_of(st);
           const int jj = st >> 1;  // edge pass (kinds E1 / E2)
           stamp(10 + kind);
+          if constexpr (GROW) {
+            // ============ global-row tiling: E1 / E2 per edge pass, then NG1, NG2, NG3 (kind = GK_*) ============
+            // parameters of this row's role: node rows take the node MLP's LayerNorm, global rows the global MLP's
+            const int mi = kind == GK_E1 ? TC_E1 : kind == GK_E2 ? TC_E2 : (is_g ? TC_G1 : TC_N1) + (kind - GK_NG1);
+            const TcMat& m = tl.mat[mi];
+            const float* pg = parp(m.par_gamma);
+            const float* pbe = parp(m.par_beta);
+            const bool lnm = ln && m.ln;
+            // global rows ride through the edge stages on filler data and must hand ZEROS to the node-aggregate weights (R2): where
+            // the epilogue is relu(x * rstd + beta') a beta' of -60000 does it for free, otherwise the row is cleared explicitly
+            const bool neg_trick = lnm && (FOLD || (RELU && fold));
+            if (kind == GK_E2 && is_g && neg_trick) pbe = sNeg;
+            wait_bar(cx, &d_ready[s], dph, 10 + kind);
+            dph ^= 1u;
+            tc_fence_after();
+            stamp(20 + kind);
+            if (kind != GK_NG3) {
+              if (warp_on) {
+                uint32_t hreg[HD / 2];
+                uint32_t sat_row = 0u;
+                epi_row<HD, RELU, FOLD>(t_acc, nullptr, pg, pbe, lnm, fold, act, hreg, sat_row);
+                if (live && !(is_g && kind <= GK_E2)) satm = __vmaxu2(satm, sat_row);  // (filler / dead rows do not count)
+                stamp(110 + kind);
+                if (kind == GK_E1) {
+                  store_hidden<HD>(t_r1, hreg);
+                } else if (kind == GK_E2) {
+                  if (!neg_trick && is_g) {
+#pragma unroll
+                    for (int j = 0; j < HD / 2; ++j) hreg[j] = 0u;
+                  }
+                  // node aggregate: running sum over this row's outgoing edges in the row's own TMEM lane (R2); W3 is folded
+                  if (jj > 0) {
+#pragma unroll
+                    for (int c0 = 0; c0 < HD / 2; c0 += 32) {
+                      uint32_t cur[32];
+                      tmem_ld32(t_r2 + c0, cur);
+                      tmem_wait_ld();
+#pragma unroll
+                      for (int j = 0; j < 32; ++j) {
+                        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&hreg[c0 + j]), *reinterpret_cast<const __half2*>(&cur[j]));
+                        hreg[c0 + j] = *reinterpret_cast<const uint32_t*>(&sum);
+                      }
+                    }
+                  }
+                  store_hidden<HD>(t_r2, hreg);
+                  if (jj == N - 2) {
+                    // global aggregate: sum of the trajectory's N node aggregates (adjacent lanes, segmented shuffle tree into lane
+                    // (b, 0)), handed to the trajectory's global row (lane (b, N)) as ITS aggregate block R1; node rows clear R1
+                    for (int off = 1; off < N; off <<= 1) {
+                      const bool take = ni + off < N;
+#pragma unroll
+                      for (int j = 0; j < HD / 2; ++j) {
+                        uint32_t o = __shfl_down_sync(FULL, hreg[j], off);
+                        o = take ? o : 0u;
+                        const __half2 sum = __hadd2(*reinterpret_cast<const __half2*>(&hreg[j]), *reinterpret_cast<const __half2*>(&o));
+                        hreg[j] = *reinterpret_cast<const uint32_t*>(&sum);
+                      }
+                    }
+#pragma unroll
+                    for (int j = 0; j < HD / 2; ++j) {
+                      const uint32_t o = __shfl_up_sync(FULL, hreg[j], N);
+                      hreg[j] = is_g ? o : 0u;
+                    }
+                    store_hidden<HD>(t_r1, hreg);
+                  } else {
+                    build_edge(jj + 1);
+                  }
+                } else {
+                  // NG1 / NG2: hidden row -> the block of the row's own role (node rows R2, global rows R1), zeros -> the other
+                  const uint32_t mg = is_g ? 0xffffffffu : 0u, mn = ~mg;
+#pragma unroll
+                  for (int c0 = 0; c0 < HD / 2; c0 += 32) {
+                    uint32_t t2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t2[j] = hreg[c0 + j] & mn;
+                    tmem_st32(t_r2 + c0, t2);
+                  }
+#pragma unroll
+                  for (int c0 = 0; c0 < HD / 2; c0 += 32) {
+                    uint32_t t1[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) t1[j] = hreg[c0 + j] & mg;
+                    tmem_st32(t_r1 + c0, t1);
+                  }
+                }
+              }
+              stamp(30 + kind);
+              signal_a(cx, s, lane);
+              stamp(120 + kind);
+              mma_stage(kind_of(st + 1));
+              if (kind == GK_E2 && jj == N - 2 && h > 0) flush_outputs(h - 1);  // the NG1 MMAs (3 + 2 HD / 16 K steps) run meanwhile
+            } else {
+              // NG3: 16 output columns -- node rows: delta of the dynamic features, global rows: agent delta + next action
+              if (warp_on) {
+                uint32_t v[16];
+                tmem_ld16(t_acc, v);
+                tmem_wait_ld();
+                if (live_n) node_update(v);
+                if (live_g) agent_update(v, h);
+              }
+            }
+            continue;
+          }
           // stage parameters are fetched before the wait, so their (indexed constant bank) latency hides behind the MMA
           const TcMat& m = tl.mat[kind];
           const float* pg = parp(m.par_gamma);
@@ -478,7 +810,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
             if (warp_on) {
               uint32_t hreg[HD / 2];
               // (no bias operand: hidden-layer biases ride in a constant-one K column, or -- E2 with N >= 3 -- in the accumulator)
-              epi_row<HD, RELU, FOLD>(t_acc, nullptr, pg, pbe, lnm, fold, act, hreg);
+              uint32_t sat_row = 0u;
+              epi_row<HD, RELU, FOLD>(t_acc, nullptr, pg, pbe, lnm, fold, act, hreg, sat_row);
+              if (live && (kind < TC_G1 || ni == 0)) satm = __vmaxu2(satm, sat_row);  // (the global tile only lives on the rows (b, 0))
               stamp(110 + kind);
               if (kind != TC_E2) {
                 store_hidden<HD>(t_r1, hreg);
@@ -558,39 +892,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
               uint32_t v[16];
               tmem_ld16(t_acc, v);
               tmem_wait_ld();
-              if (live) {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(snrm + b * SNs + kAU + ni * kNA);
-                float* og = s_obs + bw * O + A + ni * D;
-                const float4* tb = reinterpret_cast<const float4*>(sOut);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                  if (4 * j4 < D) {
-                    const float4 c1 = tb[j4], c0 = tb[4 + j4], mi = tb[8 + j4], is = tb[12 + j4];
-                    // (padded entries: c1 = c0 = 0 and the old value is taken as 0)
-                    float o0, o1, o2, o3;
-                    if constexpr (kStateInSmem) {
-                      o0 = 4 * j4 < D ? og[4 * j4] : 0.f; o1 = 4 * j4 + 1 < D ? og[4 * j4 + 1] : 0.f;
-                      o2 = 4 * j4 + 2 < D ? og[4 * j4 + 2] : 0.f; o3 = 4 * j4 + 3 < D ? og[4 * j4 + 3] : 0.f;
-                    } else {
-                      o0 = dyn[4 * j4]; o1 = dyn[4 * j4 + 1]; o2 = dyn[4 * j4 + 2]; o3 = dyn[4 * j4 + 3];
-                    }
-                    const float n0 = o0 + fmaf(c1.x, __uint_as_float(v[4 * j4]), c0.x);
-                    const float n1 = o1 + fmaf(c1.y, __uint_as_float(v[4 * j4 + 1]), c0.y);
-                    const float n2 = o2 + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
-                    const float n3 = o3 + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
-                    if constexpr (!kStateInSmem) { dyn[4 * j4] = n0; dyn[4 * j4 + 1] = n1; dyn[4 * j4 + 2] = n2; dyn[4 * j4 + 3] = n3; }
-                    if (4 * j4 < D) og[4 * j4] = n0;
-                    if (4 * j4 + 1 < D) og[4 * j4 + 1] = n1;
-                    if (4 * j4 + 2 < D) og[4 * j4 + 2] = n2;
-                    if (4 * j4 + 3 < D) og[4 * j4 + 3] = n3;
-                    // padded entries have c1 = c0 = mi = is = 0 -> exact zeros, like the zero padding of the node block
-                    if (4 * j4 + 1 < D || S == 0) dst[2 * j4] = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y);
-                    else reinterpret_cast<__half*>(dst)[4 * j4] = __float2half_rn((n0 - mi.x) * is.x);
-                    if (4 * j4 + 3 < D || (S == 0 && 4 * j4 + 2 < D)) dst[2 * j4 + 1] = pack_half2((n2 - mi.z) * is.z, (n3 - mi.w) * is.w);
-                    else if (4 * j4 + 2 < D) reinterpret_cast<__half*>(dst)[4 * j4 + 2] = __float2half_rn((n2 - mi.z) * is.z);
-                  }
-                }
-              }
+              if (live_n) node_update(v);
               // A operand of the global tile (row of trajectory b == lane (b, 0)): [hdr] -> R1, sum over all edges -> R2
               {
                 const uint4 h0 = sb[0], h1 = sb[1];
@@ -613,48 +915,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
               uint32_t v[16];
               tmem_ld16(t_acc, v);
               tmem_wait_ld();
-              if (live_g) {
-                __half* dsth = snrm + b * SNs;
-                uint32_t* dst = reinterpret_cast<uint32_t*>(dsth);
-                float* og = s_obs + bw * O;
-                const float4* tb = reinterpret_cast<const float4*>(sOut + 64);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
-                  if (4 * j4 < A) {
-                    const float4 c1 = tb[j4], c0 = tb[4 + j4], mi = tb[8 + j4], is = tb[12 + j4];
-                    float o0, o1, o2, o3;
-                    if constexpr (kStateInSmem) {
-                      o0 = 4 * j4 < A ? og[4 * j4] : 0.f; o1 = 4 * j4 + 1 < A ? og[4 * j4 + 1] : 0.f;
-                      o2 = 4 * j4 + 2 < A ? og[4 * j4 + 2] : 0.f; o3 = 4 * j4 + 3 < A ? og[4 * j4 + 3] : 0.f;
-                    } else {
-                      o0 = agent[4 * j4]; o1 = agent[4 * j4 + 1]; o2 = agent[4 * j4 + 2]; o3 = agent[4 * j4 + 3];
-                    }
-                    const float n0 = o0 + fmaf(c1.x, __uint_as_float(v[4 * j4]), c0.x);
-                    const float n1 = o1 + fmaf(c1.y, __uint_as_float(v[4 * j4 + 1]), c0.y);
-                    const float n2 = o2 + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
-                    const float n3 = o3 + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
-                    if constexpr (!kStateInSmem) { agent[4 * j4] = n0; agent[4 * j4 + 1] = n1; agent[4 * j4 + 2] = n2; agent[4 * j4 + 3] = n3; }
-                    if (4 * j4 < A) og[4 * j4] = n0;
-                    if (4 * j4 + 1 < A) og[4 * j4 + 1] = n1;
-                    if (4 * j4 + 2 < A) og[4 * j4 + 2] = n2;
-                    if (4 * j4 + 3 < A) og[4 * j4 + 3] = n3;
-                    // the agent part is followed by the action in the header: only whole pairs may be written as 32 bits
-                    if (4 * j4 + 1 < A) dst[2 * j4] = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y);
-                    else dsth[4 * j4] = __float2half_rn((n0 - mi.x) * is.x);
-                    if (4 * j4 + 3 < A) dst[2 * j4 + 1] = pack_half2((n2 - mi.z) * is.z, (n3 - mi.w) * is.w);
-                    else if (4 * j4 + 2 < A) dsth[4 * j4 + 2] = __float2half_rn((n2 - mi.z) * is.z);
-                  }
-                }
-                if (h + 1 < ra.H) {
-                  if constexpr (kStateInSmem) asm volatile("cp.async.wait_all;" ::: "memory");
-#pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (j < U) {
-                      const float an = kStateInSmem ? s_actn[j] : act_next[j];
-                      dsth[A + j] = __float2half_rn((an - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]);
-                    }
-                }
-              }
+              if (live_g) agent_update(v, h);
             }
           }
         }
@@ -662,6 +923,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
         stamp(60);
       }
       flush_outputs(ra.H - 1);
+      if (sat_hit(satm)) atomicOr(err, kTcRangeFlag);  // an fp16 operand left the representable range somewhere in this round
     }
     // ---- fused cost tail (planner launches) ----
     // This member's rollouts of the warp's trajectories (all rounds) are complete in global memory.  For every one of them the
@@ -749,7 +1011,8 @@ __global__ void __launch_bounds__(128 * NWG + 32, 1) epi_bench_kernel(long long*
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r) {
       uint32_t hreg[64];
-      epi_row<128, true, false>(base, (with_bias & 1) ? par : nullptr, par + 128, par + 256, true, (with_bias & 2) != 0, CEEUS_ACT_RELU, hreg);
+      uint32_t satm = 0u;
+      epi_row<128, true, false>(base, (with_bias & 1) ? par : nullptr, par + 128, par + 256, true, (with_bias & 2) != 0, CEEUS_ACT_RELU, hreg, satm);
       store_hidden<128>(base, hreg);
       tmem_wait_st();
     }
@@ -956,7 +1219,7 @@ cudaError_t launch_epi_bench(int nwg, int with_bias, int with_mma, long long* ou
 
 #endif  // CEEUS_DEBUG_TOOLS
 
-bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_host) {
+bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_host, int grow) {
   TcLayout t{};
   if (md.kind != CEEUS_MODEL_GNN || (md.Hd != 64 && md.Hd != 128) || md.L != 2) return false;
   if (md.D > 16 || md.A > 16 || md.U > 8 || md.N < 2) return false;
@@ -972,14 +1235,16 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
   t.KXn = t.AUp + t.NAp;
   t.KXg = t.AUp;
   if (t.KE1 > Hd) return false;  // R1 holds the edge input (KE1/2 columns) and the hidden row (Hd/2)
-  t.tpw = 32 / N;       // whole trajectories per warp: every row of a trajectory lives in one warp
+  t.grow = grow ? 1 : 0;
+  t.tpw = 32 / (N + t.grow);  // whole trajectories per warp: every row of a trajectory (+ its global row) lives in one warp
+  if (t.tpw < 1) return false;
   t.Tmax = 4 * t.tpw;   // trajectories per group (one 128-row tile per CTA and slot)
   t.tail = N * md.S + md.G;
   auto mat = [&](int m, int kx, int kagg, int n, int lnf) {
     t.mat[m].K = kx + kagg; t.mat[m].kx = kx; t.mat[m].N = n; t.mat[m].nloc = n / 2; t.mat[m].ln = lnf;
   };
   mat(TC_E1, t.KE1, 0, Hd, 1);
-  mat(TC_E2, Hd, N == 2 ? 16 : 0, Hd, 1);  // + constant-one K block (bias) in R2 where R2 is free during the MMA
+  mat(TC_E2, Hd, (N == 2 || grow) ? 16 : 0, Hd, 1);  // + constant-one K block (bias): in R2 where R2 is free during the MMA, or (grow) a shared-memory A tile
   mat(TC_N1, t.KXn, Hd, Hd, 1);
   mat(TC_N2, Hd, 16, Hd, 1);
   mat(TC_N3, Hd, 0, 16, 0);
@@ -1041,13 +1306,17 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
     int so = 0;
     t.obs_bytes = round_up(t.tpw * md.O * 4, 16);  // per warp: staged next observations of its trajectories
     t.so_obs = so; so += 4 * t.obs_bytes;
-    t.so_glob = so; so += round_up(t.Tmax, 8) * Hd * 2;
+    t.so_glob = so; so += grow ? 0 : round_up(t.Tmax, 8) * Hd * 2;  // (grow: the global aggregate goes lane to lane into the global row's TMEM block)
+    if (grow) so = round_up(so, 128);
+    t.so_xa = so; so += grow ? 6 * 2048 : 0;
     t.so_snrm = so; so += round_up(t.Tmax * t.SNs * 2, 16);
     t.so_tail = so; so += round_up(t.Tmax * t.tail * 4, 16);
     t.so_actn = so; so += 128 * 8 * 4;  // per row: the next step's raw action (cp.async prefetch)
     so = round_up(so, 128);
     for (int i = 0; i < t.NS; ++i) { t.sm_slot[i] = sm; sm += so; }
     t.sm_bar = sm; sm += 128;
+    t.sm_one = sm; sm += grow ? 4 * 2048 : 0;
+    t.sm_neg = sm; sm += grow ? Hd * 4 : 0;
     t.smem_bytes = sm;
     if (t.smem_bytes > 227 * 1024) return false;
   }
@@ -1055,6 +1324,33 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
   if (t.pairs < md.E) return false;
   *out = t;
   return true;
+}
+
+// Row layout for launches over n trajectories.  Measured on B200: a stage of the global-row tiling costs about
+// 1.3x a node-major stage (two K-stacked layers per MMA stage, role-masked operand stores), and a busy issuing warp costs either
+// layout ~30 %; so the global-row tiling (2(N-1) + 3 instead of 2(N-1) + 6 stages per step) is taken where both layouts need the
+// same number of rounds, no member's issuing warp has to carry trajectories, and the stage count wins after the 1.3x.
+int tc_pick_grow(const ModelDesc& md, int num_sms, int n) {
+  if (md.N + 1 > 32) return 0;
+  TcLayout t0{}, t1{};
+  if (!make_tc_layout(md, num_sms, &t1, nullptr, 1)) return 0;
+  if (!make_tc_layout(md, num_sms, &t0, nullptr, 0)) return 1;
+  const int N = md.N;
+  auto worst = [&](const TcLayout& t, int* busy) {
+    int r = 1;
+    *busy = 0;
+    for (int pair = 0; pair < t.pairs; ++pair) {
+      const TcTile tt = tc_tile(t.pairs, md.E, pair, n, t.NS, t.Tmax, t.tpw);
+      r = std::max(r, tt.rounds);
+      if (tt.T > 3 * t.tpw && tt.uneven == 0) *busy = 1;
+    }
+    return r;
+  };
+  int busy0 = 0, busy1 = 0;
+  const int r0 = worst(t0, &busy0), r1 = worst(t1, &busy1);
+  const double c0 = r0 * (2 * (N - 1) + 6) * (busy0 ? 1.3 : 1.0);
+  const double c1 = r1 * (2 * (N - 1) + 3) * 1.3 * (busy1 ? 1.3 : 1.0);
+  return c1 < 0.95 * c0 ? 1 : 0;
 }
 
 cudaError_t launch_tc_pack(const float* w32, const ModelDesc& md, const TcLayout& tl, const int* kmap_dev, float* scratch,
@@ -1072,10 +1368,13 @@ template <int HD, bool RELU>
 static cudaError_t launch_tc_n(const ModelDesc& md, const RolloutArgs& ra, const TcLayout& tl, const uint8_t* wimg,
                                const float* wpar, int* err_flag, long long* dbg, bool all_fold, const costdev::FusedCost& fc,
                                cudaStream_t st) {
-  auto kern = rollout_gnn_tc_kernel<HD, RELU, false, false>;
-  if (RELU && all_fold) kern = rollout_gnn_tc_kernel<HD, RELU, false, RELU>;
+  const bool fold = RELU && all_fold;
+  auto kern = tl.grow ? (fold ? rollout_gnn_tc_kernel<HD, RELU, false, RELU, true> : rollout_gnn_tc_kernel<HD, RELU, false, false, true>)
+                      : (fold ? rollout_gnn_tc_kernel<HD, RELU, false, RELU, false> : rollout_gnn_tc_kernel<HD, RELU, false, false, false>);
 #ifdef CEEUS_DEBUG_TOOLS  // the timeline-probe instantiations exist only in the debug build
-  if (dbg != nullptr) kern = (RELU && all_fold) ? rollout_gnn_tc_kernel<HD, RELU, true, RELU> : rollout_gnn_tc_kernel<HD, RELU, true, false>;
+  if (dbg != nullptr)
+    kern = tl.grow ? (fold ? rollout_gnn_tc_kernel<HD, RELU, true, RELU, true> : rollout_gnn_tc_kernel<HD, RELU, true, false, true>)
+                   : (fold ? rollout_gnn_tc_kernel<HD, RELU, true, RELU, false> : rollout_gnn_tc_kernel<HD, RELU, true, false, false>);
 #endif
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tl.smem_bytes);
   if (e != cudaSuccess) return e;

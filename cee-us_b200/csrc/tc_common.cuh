@@ -240,6 +240,15 @@ __device__ __forceinline__ void umma_f16_ts_cg2_elect(uint32_t tmem_d, uint32_t 
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
       : "memory");
 }
+// Same with the A operand in shared memory (SS form); TS and SS MMAs may accumulate into the same TMEM tile back to back.
+__device__ __forceinline__ void umma_f16_ss_cg2_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                                                      uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_cg2_mc_elect(uint64_t* bar, uint16_t cta_mask, uint32_t elected) {
   asm volatile(
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
@@ -259,17 +268,31 @@ __device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_m
                : "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+// ---- fp32 -> fp16 operand conversions: SATURATING (fp16 has a 5-bit exponent; a value beyond +-65504 becomes +-65504, never inf)
+// plus a cheap record that a saturation happened, surfaced as kTcRangeFlag in the kernels' status word (ceeus_tc_status) ----
+constexpr int kTcRangeFlag = 0x40000000;
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
-
 // {lo, hi} -> packed fp16 pair with ReLU fused into the conversion
 __device__ __forceinline__ uint32_t pack_half2_relu(float lo, float hi) {
   uint32_t d;
-  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+__device__ __forceinline__ __half half_sat(float a) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(a));
+  return __ushort_as_half(h);
+}
+// running per-16-bit-lane maximum of |h| over packed fp16 pairs; sat_hit: some |h| reached the largest finite fp16 (or is NaN)
+__device__ __forceinline__ uint32_t sat_track(uint32_t m, uint32_t w) { return __vmaxu2(m, w & 0x7fff7fffu); }
+__device__ __forceinline__ uint32_t sat_track1(uint32_t m, __half h) { return __vmaxu2(m, (uint32_t)(__half_as_ushort(h) & 0x7fffu)); }
+// (packed pairs known to be >= -1: only the positive side can saturate, the sign bit keeps negative lanes out of a SIGNED maximum)
+__device__ __forceinline__ uint32_t sat_track_pos(uint32_t m, uint32_t w) { return __vmaxs2(m, w); }
+__device__ __forceinline__ bool sat_hit(uint32_t m) { return (m & 0xffffu) >= 0x7bffu || (m >> 16) >= 0x7bffu; }
 
 // ---- packed fp32 pairs (Blackwell FFMA2 / FADD2): two fp32 lanes per instruction ------------------------------------
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {

@@ -49,7 +49,7 @@ class Engine:
                  horizon, num_traj, sampler=None, cost_along_trajectory="sum", curiosity=True, extrinsic_reward=False,
                  extrinsic_reward_scale=1.0, num_envs=1, world_size=1, rank=0, precision="fp32", seed=0,
                  device=None, external_cost=None, cost_in_rollout_tail=False, gnn_variant=0, edge_global=False, num_message_passing=1,
-                 embedding_dim=0):
+                 embedding_dim=0, tc_row_layout="auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("ceeus_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -107,6 +107,7 @@ class Engine:
             getattr(cfg, name)[:] = [float(v) for v in d[name]]
         cfg.world_size, cfg.rank, cfg.seed = world_size, rank, seed
         cfg.cost_in_rollout_tail = int(bool(cost_in_rollout_tail))
+        cfg.tc_row_layout = {"auto": 0, None: 0, "node": 1, "global": 2}[tc_row_layout]
         cfg.gnn_variant, cfg.edge_global = int(gnn_variant), int(bool(edge_global))
         cfg.num_message_passing, cfg.embedding_dim = int(num_message_passing), int(embedding_dim or 0)
         self.gnn_variant, self.edge_global = int(gnn_variant), bool(edge_global)
@@ -357,6 +358,10 @@ class Engine:
         r, u = (C.c_int32 * self.E)(), (C.c_int32 * self.E)()
         _lib.check(self.lib.ceeus_tc_tiling(self.handle, int(n), r, u), self.handle)
         return list(r), list(u)
+
+    def tc_row_layout(self):
+        """'node' / 'global': the tile row layout of the tensor-core GNN rollout of this handle (ceeus_tc_row_layout)."""
+        return {0: None, 1: "node", 2: "global"}[int(self.lib.ceeus_tc_row_layout(self.handle))]
 
     def kernel_launches(self):
         return int(self.lib.ceeus_kernel_launches(self.handle))

@@ -126,7 +126,8 @@ class _B200Ensemble:
         return dict(env=self.env, model_kind=self.model_kind, ensemble_size=self.ensemble_size,
                     hidden_dim=self.hidden_dim, num_layers=self.num_layers, act_fn=self.act_fn,
                     layer_norm=self.layer_norm, aggr_fn=getattr(self, "aggr_fn", "mean"),
-                    precision=self.backend_params.get("precision", "fp32"), **self._variant_kwargs())
+                    precision=self.backend_params.get("precision", "fp32"),
+                    tc_row_layout=self.backend_params.get("tc_row_layout", "auto"), **self._variant_kwargs())
 
     def _variant_kwargs(self):
         return {}

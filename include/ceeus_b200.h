@@ -145,7 +145,12 @@ typedef struct CeeusConfig {
   int32_t edge_global;
   int32_t num_message_passing;
   int32_t embedding_dim;
-  int32_t reserved0;
+  /* ---- CEEUS_PREC_TC, GNN: how a trajectory is laid out on the 128-row MMA tile (csrc/rollout_tc.cu) ----
+   * 0: chosen per handle from a stage-count / MMA-time model of a launch over num_envs * num_traj trajectories (env CEEUS_TC_ROWS =
+   *    node | global overrides); 1: "node major" -- N rows per trajectory, node MLP and global MLP as separate stages (2(N-1) + 6
+   *    stages per model step); 2: "global row" -- N + 1 rows per trajectory, node and global MLP K-stacked into one stage each
+   *    (2(N-1) + 3 stages per step).  Results agree to the CEEUS_PREC_TC bar either way. */
+  int32_t tc_row_layout;
   uint64_t seed;         /* Philox key of the on-device noise sampler */
 } CeeusConfig;
 
@@ -262,13 +267,21 @@ int64_t ceeus_kernel_launches(CeeusHandle h);
  * a CUDA-event pair on its launch stream (up to 256 launches between two reads).  Each call first copies the durations (ms) of
  * the pairs recorded since the previous call into ms_out_host (may be NULL) and returns their number, then sets the mode. */
 int ceeus_profile_rollouts(CeeusHandle h, int enable, float* ms_out_host, int max_out);
-/* CEEUS_PREC_TC only: 0 = the tensor-core kernel's mbarrier protocol never timed out; synchronises the device. */
+/* CEEUS_PREC_TC only: status word of the tensor-core kernels since the handle was created; synchronises the device.
+ * 0 = clean.  Bits below CEEUS_TC_RANGE: protocol error code (a bounded mbarrier wait timed out; 21 = a peer rank never arrived).
+ * CEEUS_TC_RANGE: an fp16 operand was saturated -- the operands are fp16 (5-bit exponent), conversions clamp to +-65504 instead of
+ * producing inf, and the event is recorded here; ceeus_plan_step / _resident then fail with CEEUS_ERR_STATE.  With LayerNorm the
+ * hidden activations cannot saturate; normalised observations / actions beyond +-65504 can. */
+#define CEEUS_TC_RANGE 0x40000000
 int ceeus_tc_status(CeeusHandle h);
 /* CEEUS_PREC_TC: how a launch over n trajectories is tiled, per ensemble member e: rounds_out[e] = trajectory groups each
  * warpgroup ("slot") takes through the horizon one after the other, uneven_out[e] = 1 if the member's CTA pairs use the 3/4
  * split that keeps the MMA-issuing warp empty (GNN kernel only).  The parity tests assert with it that every tiling branch
  * of the kernels is compared with the oracle. */
 int ceeus_tc_tiling(CeeusHandle h, int n, int32_t* rounds_out /* [E] */, int32_t* uneven_out /* [E] */);
+/* CEEUS_PREC_TC, GNN: the tile row layout this handle runs (1 = node major, 2 = global row; see CeeusConfig.tc_row_layout); 0 for
+ * the dense-MLP kernel. */
+int ceeus_tc_row_layout(CeeusHandle h);
 /* 1 once elites from a previous MPC step exist (controls whether shift noise is consumed) */
 int ceeus_has_elites(CeeusHandle h);
 

@@ -46,7 +46,7 @@ def product_model(c, env, weights, norms, precision="fp32"):
             mp.update(embedding_dim=c["emb"], num_message_passing=c.get("n_mp", 1))
             kw["agent_as_global_node"] = False
         m = ceeus_b200.B200GNNEnsemble(env=env, model_params=mp, normalize_w_running_stats=c.get("running", False),
-                                       backend_params=dict(precision=precision), **kw)
+                                       backend_params=dict(precision=precision, tc_row_layout=c.get("tc_rows", "auto")), **kw)
     else:
         m = ceeus_b200.B200MLPEnsemble(env=env, model_params=dict(n=5, hidden_dim=c["hidden"], num_layers=c["layers"],
                                                                    act_fn="silu", layer_norm=False),
@@ -66,7 +66,7 @@ def product_controller(c, env, model, precision="fp32", **backend):
     sp.update(c.get("sampler", {}))
     kw = dict(env=env, forward_model=model, horizon=c["H"], num_simulated_trajectories=c["P"],
               action_sampler_params=sp, cost_along_trajectory=c.get("cost", "sum"), logging=False,
-              backend_params=dict(precision=precision, **backend))
+              backend_params=dict(precision=precision, tc_row_layout=c.get("tc_rows", "auto"), **backend))
     if c.get("curiosity", True):
         return ceeus_b200.B200CuriosityMpcICem(extrinsic_reward=c.get("extrinsic", False), **kw)
     return ceeus_b200.B200MpcICem(**kw)

@@ -29,9 +29,10 @@ class _Policy:
 GNN_ROLLOUTS = [k for k, c in CASES.items() if c["kind"] == "rollout" and c["model"] == "gnn" and "variant" not in c]
 
 
+@pytest.mark.parametrize("rows", ["node", "global"])
 @pytest.mark.parametrize("name", GNN_ROLLOUTS)
-def test_tc_rollout_matches_reference_fixture(name):
-    c = CASES[name]
+def test_tc_rollout_matches_reference_fixture(name, rows):
+    c = dict(CASES[name], tc_rows=rows)
     g = np.load(os.path.join(GOLD, name + ".npz"))
     spec, weights, norms, obs, goal = build_inputs(c)
     env = product_env(c, goal)
@@ -56,10 +57,12 @@ def test_tc_rollout_matches_reference_fixture(name):
     ("playground", 4, 64, 200, 30), ("playground", 2, 128, 33, 4), ("construction", 2, 128, 3000, 10),
     ("construction", 8, 128, 50, 3), ("construction", 12, 128, 9, 2), ("playground", 7, 64, 70, 4),
     ("construction", 2, 128, 40, 1), ("construction", 6, 128, 5, 1), ("playground", 4, 64, 2, 1)])
-def test_tc_rollout_matches_oracle_fresh_inputs(env_kind, n_obj, hidden, P, H):
-    """Ragged populations (partial groups, empty lock-step groups), every N / hidden width, per-trajectory start states."""
+@pytest.mark.parametrize("rows", ["node", "global"])
+def test_tc_rollout_matches_oracle_fresh_inputs(env_kind, n_obj, hidden, P, H, rows):
+    """Ragged populations (partial groups, empty lock-step groups), every N / hidden width, per-trajectory start states, on both
+    tile row layouts."""
     c = dict(kind="rollout", env=env_kind, n_obj=n_obj, model="gnn", hidden=hidden, layers=2, P=P, H=H,
-             wseed=2000 + n_obj + hidden, identity_norm=False, running=False, oseed=177 + P)
+             wseed=2000 + n_obj + hidden, identity_norm=False, running=False, oseed=177 + P, tc_rows=rows)
     spec, weights, norms, obs, goal = build_inputs(c)
     env = product_env(c, goal)
     pm = product_model(c, env, weights, norms, precision="tc")
@@ -143,13 +146,14 @@ def test_tc_step_is_deterministic_and_unsupported_shapes_are_refused():
 
 @pytest.mark.parametrize("variant", ["signed_gamma", "zero_gamma"])
 @pytest.mark.parametrize("env_kind,n_obj,hidden", [("construction", 2, 128), ("construction", 4, 128), ("playground", 4, 64)])
-def test_tc_rollout_with_trained_like_layernorm(env_kind, n_obj, hidden, variant):
+@pytest.mark.parametrize("rows", ["node", "global"])
+def test_tc_rollout_with_trained_like_layernorm(env_kind, n_obj, hidden, variant, rows):
     """Non-trivial LayerNorm affine parameters.  `signed_gamma`: gamma of either sign, beta != 0 -> the pack-time folding
     (sign into this layer's weight columns, |gamma| into the consumer's rows, beta / |gamma| in the epilogue) is active;
     `zero_gamma`: one gamma is exactly 0, which cannot be folded -> the general epilogue path must be taken."""
     P, H = 97, 12
     c = dict(kind="rollout", env=env_kind, n_obj=n_obj, model="gnn", hidden=hidden, layers=2, P=P, H=H,
-             wseed=4100 + n_obj + hidden, identity_norm=False, running=False, oseed=903)
+             wseed=4100 + n_obj + hidden, identity_norm=False, running=False, oseed=903, tc_rows=rows)
     spec, weights, norms, obs, goal = build_inputs(c)
     rs = np.random.RandomState(77)
     weights = dict(weights)
@@ -222,7 +226,8 @@ def test_tc_mlp_rollout_matches_oracle_fresh_inputs(n_obj, hidden, layers, P, H)
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tc", TOL_TC)])
 @pytest.mark.parametrize("act,layer_norm,aggr", [("relu", True, "sum"), ("silu", True, "mean"), ("tanh", False, "sum"),
                                                  ("relu", False, "mean")])
-def test_gnn_model_param_variants(act, layer_norm, aggr, precision, tol):
+@pytest.mark.parametrize("rows", ["node", "global"])
+def test_gnn_model_param_variants(act, layer_norm, aggr, precision, tol, rows):
     """The other values `model_params` can take on this path (gnn_modules.py:17-131: act_fn, layer_norm, aggr_fn): sum
     aggregation (the folded W3 then carries no 1/(N-1) scale), non-ReLU activations and no LayerNorm (general epilogue)."""
     import ceeus_b200
@@ -236,9 +241,11 @@ def test_gnn_model_param_variants(act, layer_norm, aggr, precision, tol):
     env = product_env(c, goal)
     pm = ceeus_b200.B200GNNEnsemble(env=env, model_params=dict(n=5, hidden_dim=hidden, num_layers=2, layer_norm=layer_norm,
                                                                 act_fn=act, aggr_fn=aggr),
-                                    backend_params=dict(precision=precision))
+                                    backend_params=dict(precision=precision, tc_row_layout=rows))
     pm.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
     pm.set_normalizers(norms)
+    if precision == "fp32" and rows == "global":
+        pytest.skip("the row layout only exists on the tensor-core path")
     om = orc.GNNEnsembleOracle(spec=spec, weights=weights, normalizers=norms, hidden=hidden, num_layers=2, act=act,
                                layer_norm=layer_norm, aggr=aggr)
     acts = rollout_actions(c, spec)
@@ -251,3 +258,79 @@ def test_gnn_model_param_variants(act, layer_norm, aggr, precision, tol):
     assert eng.tc_status() == 0 and np.isfinite(got).all()
     assert rel_l2(got, want) < tol
     assert rel_err(got, want) < 5 * tol
+
+
+# ---- fp16 operand range: saturating conversions + CEEUS_TC_RANGE in the status word (include/ceeus_b200.h) ----------------
+TC_RANGE = 0x40000000
+
+
+@pytest.mark.parametrize("rows", ["node", "global"])
+def test_tc_layernorm_free_model_full_horizon_stays_in_range(rows):
+    """layer_norm=False at H=30 with observations of magnitude ~100: nothing bounds the hidden activations but the weights, the
+    fp16 operands stay far inside their range -> no flag, and the rollout still meets the tensor-core bar."""
+    import ceeus_b200
+
+    n_obj, hidden, P, H = 2, 128, 200, 30
+    c = dict(kind="rollout", env="construction", n_obj=n_obj, model="gnn", hidden=hidden, layers=2, P=P, H=H,
+             wseed=5200, identity_norm=False, running=False, oseed=32)
+    spec, weights, norms, obs, goal = build_inputs(c)
+    weights = {k: v for k, v in weights.items() if not (k.endswith(".gamma") or k.endswith(".beta"))}
+    env = product_env(c, goal)
+    pm = ceeus_b200.B200GNNEnsemble(env=env, model_params=dict(n=5, hidden_dim=hidden, num_layers=2, layer_norm=False, act_fn="relu"),
+                                    backend_params=dict(precision="tc", tc_row_layout=rows))
+    pm.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+    pm.set_normalizers(norms)
+    om = orc.GNNEnsembleOracle(spec=spec, weights=weights, normalizers=norms, hidden=hidden, num_layers=2, act="relu", layer_norm=False)
+    acts = rollout_actions(c, spec)
+    rs = np.random.RandomState(3)
+    starts = np.tile(obs, (P, 1))
+    starts[:, :spec.state_dim] += (100.0 * rs.standard_normal((P, spec.state_dim))).astype(np.float32)
+    want = orc.rollout(om, torch.from_numpy(starts), torch.from_numpy(acts), torch.from_numpy(goal)).numpy()
+    pm.predict_n_steps(start_observations=torch.from_numpy(starts).to(DEV), start_states=None,
+                       policy=_Policy(torch.from_numpy(acts).to(DEV)), horizon=H)
+    eng = pm._rollout_engine(P, H)
+    got = eng.traj_.cpu().numpy()
+    assert eng.tc_status() == 0 and np.isfinite(got).all()
+    assert rel_l2(got, want) < TOL_TC
+
+
+@pytest.mark.parametrize("model", ["gnn", "gnn-no-layernorm", "mlp"])
+def test_tc_saturated_operands_raise_the_range_flag_and_stay_finite(model):
+    """Observations far outside the fp16 range (1e7 after normalisation) / exploding LayerNorm-free activations: the conversions
+    saturate (no inf / NaN anywhere in the rollout of a LayerNorm model or the dense MLP), the status word carries CEEUS_TC_RANGE, and a planning step refuses to return
+    an action computed from saturated operands."""
+    import ceeus_b200
+
+    P, H = 96, 6
+    gnn = model != "mlp"
+    c = dict(kind="mpc", env="construction", n_obj=2 if gnn else 4, model="gnn" if gnn else "mlp", hidden=128 if gnn else 256,
+             layers=2 if gnn else 3, P=P, H=H, wseed=5300, identity_norm=True, running=False, oseed=33, curiosity=True, cost="sum")
+    spec, weights, norms, obs, goal = build_inputs(c)
+    env = product_env(c, goal)
+    if model == "gnn-no-layernorm":
+        weights = {k: (v * 40.0 if k.endswith(".weight") or k.endswith(".w") else v) for k, v in weights.items()
+                   if not (k.endswith(".gamma") or k.endswith(".beta"))}
+        pm = ceeus_b200.B200GNNEnsemble(env=env, model_params=dict(n=5, hidden_dim=128, num_layers=2, layer_norm=False, act_fn="relu"),
+                                        backend_params=dict(precision="tc"))
+        pm.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()})
+        pm.set_normalizers(norms)
+        scale = 1.0e3
+    else:
+        pm = product_model(c, env, weights, norms, precision="tc")
+        scale = 1.0e7
+    acts = torch.from_numpy(rollout_actions(dict(c, kind="rollout"), spec)).to(DEV)
+    start = np.tile(obs, (P, 1))
+    start[:, :spec.state_dim] *= scale
+    start[:, :spec.state_dim] += scale
+    pm.predict_n_steps(start_observations=torch.from_numpy(start).to(DEV), start_states=None, policy=_Policy(acts), horizon=H)
+    eng = pm._rollout_engine(P, H)
+    st = eng.tc_status()
+    assert st & TC_RANGE and (st & ~TC_RANGE) == 0, hex(st)
+    if model != "gnn-no-layernorm":  # (there the fp16 SUMS of saturated activations may still overflow: flagged, not finite)
+        assert torch.isfinite(eng.traj_).all()
+    # the same through the planner: ceeus_plan_step fails loudly instead of returning an action
+    ctrl = product_controller(c, env, pm, precision="tc", seed=3)
+    big = (obs * scale + scale).astype(np.float32)
+    ctrl.beginning_of_rollout(observation=big, state=None, mode="train")
+    with pytest.raises(RuntimeError, match="saturated"):
+        ctrl.get_action(big, None)

@@ -1,6 +1,8 @@
 """GPU: the tensor-core rollout kernels on the code paths the BENCHMARK runs -- every BASELINE.json size and every tiling
 branch of the kernels (trajectory groups taken one after the other by a warpgroup = ``rounds`` >= 2, the uneven 3/4 split
-that keeps the MMA-issuing warp empty) -- against the CPU oracle at the tf32/bf16-mode bar (1e-3 relative).
+that keeps the MMA-issuing warp empty, both tile row layouts of the GNN kernel: "node" = N rows per trajectory with separate
+node / global stages, "global" = N + 1 rows with the node and global MLP K-stacked into one stage each) -- against the CPU
+oracle at the tf32/bf16-mode bar (1e-3 relative).
 
 Which branch a case runs is asserted through the library itself (``ceeus_tc_tiling``), not through a copy of the formula,
 so a change of the tiling cannot silently take these cases off the branches they are here for."""
@@ -27,12 +29,14 @@ def _engine_for(c, weights, norms, goal, num_envs=1):
     return eng
 
 
-def _check_rollout(c, want_rounds=None, want_uneven=None, num_envs=1):
+def _check_rollout(c, want_rounds=None, want_uneven=None, num_envs=1, want_rows=None):
     """One launch over c['P'] trajectories (num_envs start observations / goals) against the oracle."""
     spec, weights, norms, obs, goal = build_inputs(c)
     P, H = c["P"], c["H"]
     eng = _engine_for(c, weights, norms, goal, num_envs)
     rounds, uneven = eng.tc_tiling(P)
+    if c["model"] == "gnn":
+        assert eng.tc_row_layout() == (want_rows or c.get("tc_rows", "node")), eng.tc_row_layout()
     if want_rounds is not None:
         assert rounds == want_rounds, (rounds, want_rounds)
     if want_uneven is not None:
@@ -83,24 +87,46 @@ def _check_rollout(c, want_rounds=None, want_uneven=None, num_envs=1):
 def test_tc_rollout_config2_full_size():
     """configs[1]: construction N=2, 4096 trajectories, H=30 -> two rounds per slot."""
     c = dict(kind="rollout", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=4096, H=30, wseed=5,
-             identity_norm=True, running=False, oseed=1)
-    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[0] * 5)
+             identity_norm=True, running=False, oseed=1, tc_rows="auto")
+    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[0] * 5, want_rows="node")
+
+
+def test_tc_rollout_config2_full_size_global_rows():
+    """configs[1] forced onto the global-row layout: N + 1 = 3 rows per trajectory, 5 stages per model step."""
+    c = dict(kind="rollout", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=4096, H=30, wseed=5,
+             identity_norm=True, running=False, oseed=1, tc_rows="global")
+    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[1, 1, 1, 1, 0])
+
+
+def test_tc_rollout_config1_size_picks_global_rows():
+    """configs[0] (the population the reference's yamls ship: 128 trajectories, H=20) is latency bound -- one round at 3 % fill --
+    so the library picks the layout with fewer stages per step."""
+    c = dict(kind="rollout", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=128, H=20, wseed=5,
+             identity_norm=True, running=False, oseed=1, tc_rows="auto")
+    _check_rollout(c, want_rounds=[1] * 5, want_uneven=[0] * 5, want_rows="global")
 
 
 def test_tc_rollout_config3_full_size():
     """configs[2] per GPU: construction N=6 (30 edges), 2048 trajectories, H=30 -> two rounds, uneven split for the members
     that own 15 CTA pairs."""
     c = dict(kind="rollout", env="construction", n_obj=6, model="gnn", hidden=128, layers=2, P=2048, H=30, wseed=5,
-             identity_norm=True, running=False, oseed=1)
-    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[1, 1, 1, 1, 0])
+             identity_norm=True, running=False, oseed=1, tc_rows="auto")
+    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[1, 1, 1, 1, 0], want_rows="node")
 
 
 def test_tc_rollout_config4_full_size():
     """configs[3] per GPU: playground N=4, Hd=64, 8 environments x 1024 trajectories, H=30 -> three rounds, uneven split
     for the 14-pair member; per-environment start observation and goal."""
     c = dict(kind="rollout", env="playground", n_obj=4, model="gnn", hidden=64, layers=2, P=8192, H=30, wseed=5,
-             identity_norm=False, running=True, oseed=1)
+             identity_norm=False, running=True, oseed=1, tc_rows="node")
     _check_rollout(c, want_rounds=[3] * 5, want_uneven=[0, 0, 0, 0, 1], num_envs=8)
+
+
+def test_tc_rollout_config4_full_size_global_rows():
+    """configs[3] per GPU on the global-row layout (Hd = 64, four slots, 5 rows per trajectory): four rounds for the 14-pair member."""
+    c = dict(kind="rollout", env="playground", n_obj=4, model="gnn", hidden=64, layers=2, P=8192, H=30, wseed=5,
+             identity_norm=False, running=True, oseed=1, tc_rows="global")
+    _check_rollout(c, want_rounds=[3, 3, 3, 3, 4], want_uneven=[0, 0, 0, 0, 1], num_envs=8)
 
 
 def test_tc_mlp_rollout_config5_full_size():
@@ -129,7 +155,30 @@ def test_tc_mlp_rollout_config5_full_size():
     ("playground", 4, 64, 8647, 2, [3] * 5, [1] * 5)])
 def test_tc_rollout_every_tiling_branch(env_kind, n_obj, hidden, P, H, rounds, uneven):
     c = dict(kind="rollout", env=env_kind, n_obj=n_obj, model="gnn", hidden=hidden, layers=2, P=P, H=H,
-             wseed=2300 + n_obj + hidden, identity_norm=False, running=False, oseed=400 + P)
+             wseed=2300 + n_obj + hidden, identity_norm=False, running=False, oseed=400 + P, tc_rows="node")
+    _check_rollout(c, want_rounds=rounds, want_uneven=uneven)
+
+
+@pytest.mark.parametrize("env_kind,n_obj,hidden,P,H,rounds,uneven", [
+    ("construction", 2, 128, 333, 4, [1] * 5, [0] * 5),
+    ("construction", 2, 128, 1850, 3, [1] * 5, [1] * 5),
+    ("construction", 2, 128, 2300, 2, [1, 1, 1, 1, 2], [0] * 5),
+    ("construction", 2, 128, 3000, 2, [2] * 5, [0] * 5),
+    ("construction", 2, 128, 3700, 2, [2] * 5, [1] * 5),
+    ("construction", 2, 128, 4900, 2, [3] * 5, [0] * 5),
+    ("construction", 3, 128, 1500, 3, [1] * 5, [1] * 5),
+    ("construction", 3, 128, 2000, 2, [2] * 5, [0] * 5),
+    ("construction", 6, 128, 750, 3, [1] * 5, [1] * 5),
+    ("construction", 6, 128, 1000, 2, [2] * 5, [0] * 5),
+    ("construction", 6, 128, 1500, 2, [2] * 5, [1] * 5),
+    ("playground", 4, 64, 2200, 3, [1] * 5, [1] * 5),
+    ("playground", 4, 64, 3000, 2, [2] * 5, [0] * 5),
+    ("playground", 4, 64, 4400, 2, [2] * 5, [1] * 5),
+    ("playground", 4, 64, 5800, 2, [3] * 5, [0] * 5)])
+def test_tc_rollout_every_tiling_branch_global_rows(env_kind, n_obj, hidden, P, H, rounds, uneven):
+    """The same tiling branches on the global-row layout (N + 1 tile rows per trajectory, K-stacked node / global stages)."""
+    c = dict(kind="rollout", env=env_kind, n_obj=n_obj, model="gnn", hidden=hidden, layers=2, P=P, H=H,
+             wseed=2300 + n_obj + hidden, identity_norm=False, running=False, oseed=400 + P, tc_rows="global")
     _check_rollout(c, want_rounds=rounds, want_uneven=uneven)
 
 
@@ -151,6 +200,7 @@ def test_tc_full_step_config2_agrees_with_fp32_and_oracle():
     a_tc = ctrl.get_action(obs, None)
     e = ctrl.engine
     assert e.tc_status() == 0
+    assert e.tc_row_layout() == "node"  # the layout the benchmark's config-2 step runs (picked by the library)
     ctrl32 = product_controller(c, env, product_model(c, env, weights, norms), seed=11)
     ctrl32.beginning_of_rollout(observation=obs, state=None, mode="train")
     ctrl32.get_action(obs, None)
@@ -173,14 +223,14 @@ def test_tc_full_step_config2_agrees_with_fp32_and_oracle():
     assert np.all(np.isfinite(a_tc)) and np.all(np.abs(a_tc) <= 1.0)
 
 
-@pytest.mark.parametrize("cfg", ["c2", "c3"])
+@pytest.mark.parametrize("cfg", ["c2", "c3", "c2-global", "c3-global"])
 def test_tc_sharding_and_permutation_invariance_full_size(cfg):
     """A trajectory's tensor-core result does not depend on the launch it is part of or the tile row it lands in: halves
     rolled out separately (one round each at c2) equal the full launch (two rounds) bit for bit; so does a permutation."""
-    n_obj, P = (2, 4096) if cfg == "c2" else (6, 2048)
+    n_obj, P = (2, 4096) if cfg.startswith("c2") else (6, 2048)
     H = 8
     c = dict(kind="rollout", env="construction", n_obj=n_obj, model="gnn", hidden=128, layers=2, P=P, H=H, wseed=5,
-             identity_norm=True, running=False, oseed=1)
+             identity_norm=True, running=False, oseed=1, tc_rows="global" if cfg.endswith("global") else "node")
     spec, weights, norms, obs, goal = build_inputs(c)
     eng = _engine_for(c, weights, norms, goal)
     eng.set_goal(goal)
