@@ -334,6 +334,7 @@ def gpu_measure(name, steps, warmup, precision, world, rank, dev, flush, dist, s
         "dtype": "f32" if not tc_mode else "f16 operands, f32 accumulate",
         "config": {"workload": desc, "global_traj": c["P"] * nenv * world, "traj_per_gpu": c["P"] * nenv, "horizon": c["H"],
                    "ensemble": E, "icem_iters": ITERS, "num_envs": nenv, "precision": precision,
+                   "tc_row_layout": eng.tc_row_layout() if tc_mode else None,
                    "parallelism": (f"traj-sharded x{world} (per iteration the ranks' k best candidates are exchanged by NVLink peer-memory stores + flags, "
                                     "or one NCCL all-gather, inside the step's CUDA graph)"
                                    if traj_sharded else f"env-sharded x{world} (no collective)") if world > 1 else "single GPU",
