@@ -9,3 +9,4 @@ from .envs import TensorEnv, construction_env, describe_env, playground_env, rob
 from .models import B200GNNEnsemble, B200MLPEnsemble  # noqa: F401
 from .rnd import B200RndMpcICem  # noqa: F401
 from .rollout_buffer import RolloutView  # noqa: F401
+from .rollout_manager import B200RolloutManager, BatchedEnvView, Rollout  # noqa: F401
