@@ -566,7 +566,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       const int n_traj_w = max(0, min(tpw, Gc - qf * tpw));  // live trajectories of this warp
       const int n_out = n_traj_w * O;
       auto flush_outputs = [&](int hh) {
-#ifndef EXP_OLD_FLUSH
         if (fused) {
           // planner: only the predicted dims, into the trajectory's own block [H][E][Op] of the compact scratch
           float* og = fc.pred + (size_t)(p0 + qf * tpw) * fc.ps + (size_t)hh * fc.hs + (size_t)e * fc.es;
@@ -578,7 +577,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
           }
           return;
         }
-#endif
         float* og = ra.traj + (((size_t)(hh + 1) * md.E + e) * ra.n + p0 + qf * tpw) * O;
 #pragma unroll 4
         for (int i = lane; i < n_out; i += 32) og[i] = s_obs[i];
