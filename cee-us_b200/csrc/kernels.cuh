@@ -64,6 +64,7 @@ struct TcLayout {
   int so_xa;               // inside a slot region: A tile [6 chunks][128 rows][16 B]: hdr_N(2) | x_i(2) | hdr_G(2)
   int sm_one;              // per CTA: constant A tile [4 chunks][128 rows][16 B]: one-hot(node rows)(2) | one-hot(global rows)(2)
   int sm_neg;              // per CTA: HD floats of -60000 (LayerNorm beta that zeroes a row through the ReLU)
+  int even_rounds;         // 1: split a worker's trajectories evenly over its rounds (A/B switch; default: whole warps first)
 };
 // How the n trajectories of one launch are dealt to the CTA pairs / slots of one ensemble member (shared by the kernel and by
 // ceeus_tc_tiling, so the parity tests can assert which tiling branch a case exercises).

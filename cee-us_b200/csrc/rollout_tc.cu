@@ -458,7 +458,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
         w_lo = min(ra.n, u_off * q_un * rounds);
         w_hi = min(ra.n, w_lo + Tw * rounds);
       } else {
-        Tw = T;
+        // rounds are filled warp by warp -- three whole warps per round where that is enough (the issuing warp stays empty), the
+        // remainder in the last round -- instead of evenly: fewer busy warps in total, and a light last round whose two slots sit
+        // on different schedulers
+        Tw = (T <= 3 * tpw && !tl.even_rounds) ? 3 * tpw : T;
         w_lo = min(ra.n, worker * per_worker);
         w_hi = min(ra.n, w_lo + per_worker);
       }
@@ -943,7 +946,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
             w_lo = min(ra.n, u_off * q_un * rounds);
             w_hi = min(ra.n, w_lo + Tw * rounds);
           } else {
-            Tw = T;
+            Tw = (T <= 3 * tpw && !tl.even_rounds) ? 3 * tpw : T;
             w_lo = min(ra.n, worker * per_worker);
             w_hi = min(ra.n, w_lo + per_worker);
           }
@@ -1234,6 +1237,10 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
   t.KXg = t.AUp;
   if (t.KE1 > Hd) return false;  // R1 holds the edge input (KE1/2 columns) and the hidden row (Hd/2)
   t.grow = grow ? 1 : 0;
+  {
+    const char* ov = getenv("CEEUS_TC_EVEN_ROUNDS");  // development / A-B switch: the even split of round 1
+    t.even_rounds = (ov && ov[0] == '1') ? 1 : 0;
+  }
   t.tpw = 32 / (N + t.grow);  // whole trajectories per warp: every row of a trajectory (+ its global row) lives in one warp
   if (t.tpw < 1) return false;
   t.Tmax = 4 * t.tpw;   // trajectories per group (one 128-row tile per CTA and slot)
