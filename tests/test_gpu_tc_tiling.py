@@ -118,8 +118,8 @@ def test_tc_rollout_config4_full_size():
     """configs[3] per GPU: playground N=4, Hd=64, 8 environments x 1024 trajectories, H=30 -> three rounds, uneven split
     for the 14-pair member; per-environment start observation and goal."""
     c = dict(kind="rollout", env="playground", n_obj=4, model="gnn", hidden=64, layers=2, P=8192, H=30, wseed=5,
-             identity_norm=False, running=True, oseed=1, tc_rows="node")
-    _check_rollout(c, want_rounds=[3] * 5, want_uneven=[0, 0, 0, 0, 1], num_envs=8)
+             identity_norm=False, running=True, oseed=1, tc_rows="auto")
+    _check_rollout(c, want_rounds=[3] * 5, want_uneven=[0, 0, 0, 0, 1], num_envs=8, want_rows="node")
 
 
 def test_tc_rollout_config4_full_size_global_rows():
