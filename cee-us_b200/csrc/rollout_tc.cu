@@ -24,7 +24,12 @@
 //     shared memory holds the normalised fp16 copy the A tiles are built from and the warp's staged next observations,
 //     which leave as one coalesced copy per step while an MMA stage runs.
 //   * operands are fp16 (10-bit mantissa, TF32 class) with fp32 accumulation; states, residual update, normalisers and
-//     LayerNorm statistics stay fp32.  Parity bar: 1e-3 (BASELINE.json north_star, tf32/bf16 mode).
+//     LayerNorm statistics stay fp32.  Conversions saturate (never inf) and a saturation is recorded in the status word
+//     (kTcRangeFlag).  Parity bar: 1e-3 (BASELINE.json north_star, tf32/bf16 mode).
+//   * second tile row layout (template parameter GROW, TcLayout::grow, picked per handle by tc_pick_grow): a trajectory owns N node
+//     rows + 1 GLOBAL row; node MLP and global MLP run K-stacked as one stage each (NG1, NG2, NG3), their raw-input and bias K
+//     blocks come from shared-memory A tiles (SS-form MMAs accumulating into the same tile as the TS-form ones): 2(N-1) + 3
+//     stages per model step instead of 2(N-1) + 6, for launches whose step time is the stage chain, not the tile capacity.
 #include <cuda_fp16.h>
 
 #include <algorithm>
