@@ -72,7 +72,9 @@ struct TcTile {
   int e, lp, np;        // member, index of the pair inside the member, pairs of the member
   int per_worker, rounds, T;  // trajectories per worker (= slot), groups per worker, trajectories per group (<= Tmax)
   int q_un;             // uneven split: trajectories per warp and round
-  int uneven;           // leader-CTA slots get 3 warps' worth, the other CTA's slots 4 (the issuing warp stays empty)
+  int uneven;           // 1: in every round the leader-CTA slots get 3 warps' worth, the other CTA's slots 4 (the issuing warp stays
+                        // empty); 2: the first k_pure rounds do that with whole warps, the remaining rounds split the rest evenly
+  int k_pure, per_last; // uneven == 2: leading "pure issuer" rounds; trajectories per worker in each of the remaining rounds
 };
 __host__ __device__ inline TcTile tc_tile(int pairs, int E, int pair, int n, int NS, int Tmax, int tpw) {
   TcTile t;
@@ -84,8 +86,58 @@ __host__ __device__ inline TcTile tc_tile(int pairs, int E, int pair, int n, int
   if (t.rounds < 1) t.rounds = 1;
   t.T = (t.per_worker + t.rounds - 1) / t.rounds;
   t.q_un = (n + t.np * NS * 7 * t.rounds - 1) / (t.np * NS * 7 * t.rounds);
-  t.uneven = (t.T > 3 * tpw && t.q_un <= tpw) ? 1 : 0;
+  t.uneven = 0;
+  t.k_pure = 0;
+  t.per_last = 0;
+  if (t.T > 3 * tpw) {  // the even split would put trajectories on the MMA-issuing warp in every round
+    if (t.q_un <= tpw) {
+      t.uneven = 1;
+    } else {
+      // not every round can give up an eighth of its rows: as many leading rounds as the spare capacity pays for do
+      const int cap_even = t.np * 2 * NS * Tmax, cap_pure = t.np * NS * 7 * tpw;
+      int k = (t.rounds * cap_even - n) / (cap_even - cap_pure);
+      if (k > t.rounds - 1) k = t.rounds - 1;
+      if (k >= 1) {
+        const int rest = n - k * cap_pure, workers = (t.rounds - k) * t.np * 2 * NS;
+        t.uneven = 2;
+        t.k_pure = k;
+        t.per_last = (rest + workers - 1) / workers;
+      }
+    }
+  }
   return t;
+}
+// first trajectory and number of live trajectories of the group a worker (cluster rank, slot s) takes in round rd
+__host__ __device__ inline void tc_group(const TcTile& t, int n, int NS, int tpw, int rank, int s, int rd, int even_rounds, int* p0,
+                                         int* Gc) {
+  int p, Tw;
+  const int worker = (t.lp * 2 + rank) * NS + s;
+  const int u_off = t.lp * NS * 7 + (rank == 0 ? 3 * s : 3 * NS + 4 * s), units = rank == 0 ? 3 : 4;
+  if (t.uneven == 1) {
+    Tw = units * t.q_un;
+    const int lo = u_off * t.q_un * t.rounds;
+    p = lo + rd * Tw;
+    const int hi = lo + Tw * t.rounds;
+    if (hi < n) n = hi;
+  } else if (t.uneven == 2 && rd < t.k_pure) {
+    Tw = units * tpw;
+    p = rd * (t.np * NS * 7 * tpw) + u_off * tpw;
+  } else if (t.uneven == 2) {
+    Tw = t.per_last;
+    p = t.k_pure * (t.np * NS * 7 * tpw) + ((rd - t.k_pure) * t.np * 2 * NS + worker) * t.per_last;
+  } else {
+    // rounds are filled warp by warp -- three whole warps per round where that is enough (the issuing warp stays empty), the
+    // remainder in the last round -- instead of evenly: fewer busy warps in total, and a light last round
+    Tw = (t.T <= 3 * tpw && !even_rounds) ? 3 * tpw : t.T;
+    const int lo = worker * t.per_worker;
+    p = lo + rd * Tw;
+    const int hi = lo + t.per_worker;
+    if (hi < n) n = hi;
+  }
+  *p0 = p < n ? p : n;
+  int g = n - p;
+  if (g > Tw) g = Tw;
+  *Gc = g > 0 ? g : 0;
 }
 bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_host /* [kmap_len] or null */, int grow = 0);
 // Row layout of the tensor-core GNN rollout for launches over n trajectories: 1 if the "global row" tiling is expected to be

@@ -244,6 +244,16 @@ __device__ __forceinline__ void tc_issue_grow(volatile int* abort_flag, int* err
   __syncwarp();
 }
 
+// Group of (pair, cluster rank, slot) in round rd: out of line on purpose -- evaluated once per round, and inlined its operands
+// (the whole TcTile) would stay live across the 255-register step loop.  Returns the packed pair (p0, Gc).
+__device__ __noinline__ int2 tc_group_of(int pairs, int E, int pair, int n, int NS, int Tmax, int tpw, int rank, int s, int rd,
+                                         int even_rounds) {
+  const TcTile t = tc_tile(pairs, E, pair, n, NS, Tmax, tpw);
+  int p0, Gc;
+  tc_group(t, n, NS, tpw, rank, s, rd, even_rounds, &p0, &Gc);
+  return make_int2(p0, Gc);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Row layout ("node major"): TMEM lane == tile row == (trajectory b, node i); a warp owns 32 / N whole trajectories, so every
 // exchange between the rows of a trajectory stays inside one warp (__syncwarp, no block barriers in the step loop).
@@ -273,8 +283,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
   // and the same number of rounds also fits with that warp left empty (leader slots 3 warps' worth of trajectories, the other
   // CTA's slots 4), the issuer stays a pure issuer that reacts at once.  q = trajectories per warp and round.
   const TcTile tt = tc_tile(tl.pairs, md.E, pair, ra.n, NS, tl.Tmax, tl.tpw);
-  const int e = tt.e, lp = tt.lp, np = tt.np, per_worker = tt.per_worker, rounds = tt.rounds, T = tt.T, q_un = tt.q_un;
-  const bool uneven = tt.uneven != 0;
+  const int e = tt.e, rounds = tt.rounds;
   const int n_stage = 2 * (N - 1) + (GROW ? 3 : 6);
   const int R = N + (GROW ? 1 : 0);  // tile rows per trajectory
 
@@ -367,7 +376,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     const int s = warp >> 2;       // slot
     const int q = warp & 3;        // TMEM lane quadrant
     const int row = tid & 127;     // tile row == TMEM lane
-    const int worker = (lp * 2 + (int)rank) * NS + s;
     uint8_t* slot = smem + tl.sm_slot[s];
     float* s_obs = reinterpret_cast<float*>(slot + tl.so_obs + q * tl.obs_bytes);  // this warp's next observations [tpw][O] fp32
     uint8_t* s_glob = slot + tl.so_glob;  // [Tmax][HD] fp16 sums over all edges of a trajectory
@@ -455,23 +463,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     for (int j = 0; j < 16; ++j) { dyn[j] = 0.f; agent[j] = 0.f; }  // padded entries take part in the vectorised output update
 
     for (int rd = 0; rd < rounds; ++rd) {
-      int w_lo, w_hi, Tw;
-      if (uneven) {
-        const int units = rank == 0 ? 3 : 4;  // warps' worth of trajectories of this worker
-        const int u_off = lp * NS * 7 + (rank == 0 ? 3 * s : 3 * NS + 4 * s);
-        Tw = units * q_un;
-        w_lo = min(ra.n, u_off * q_un * rounds);
-        w_hi = min(ra.n, w_lo + Tw * rounds);
-      } else {
-        // rounds are filled warp by warp -- three whole warps per round where that is enough (the issuing warp stays empty), the
-        // remainder in the last round -- instead of evenly: fewer busy warps in total, and a light last round whose two slots sit
-        // on different schedulers
-        Tw = (T <= 3 * tpw && !tl.even_rounds) ? 3 * tpw : T;
-        w_lo = min(ra.n, worker * per_worker);
-        w_hi = min(ra.n, w_lo + per_worker);
-      }
-      const int p0 = w_lo + rd * Tw;
-      int Gc = max(0, min(Tw, w_hi - p0));  // live trajectories of this group (0: pure lock-step filler)
+      // first trajectory / live trajectories of this group (Gc == 0: pure lock-step filler)
+      const int2 grp = tc_group_of(tl.pairs, md.E, pair, ra.n, NS, tl.Tmax, tpw, (int)rank, s, rd, tl.even_rounds);
+      const int p0 = grp.x;
+      int Gc = grp.y;
       if (DBG && dbg != nullptr && (dbg[499] & 1) && s == 1) Gc = 0;  // profiling aid: slot 1 idles, slot 0 runs without SIMT contention
       const bool live = lane_ok && b < Gc;
       const bool live_n = GROW ? (live && !is_g) : live;              // row carries a node of a live trajectory
@@ -944,19 +939,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       // members have arrived (every CTA of this persistent grid is resident, so the wait cannot deadlock)
       for (int phase = 0; phase < 2; ++phase)
         for (int rd = 0; rd < rounds; ++rd) {
-          int w_lo, w_hi, Tw;
-          if (uneven) {
-            const int u_off = lp * NS * 7 + (rank == 0 ? 3 * s : 3 * NS + 4 * s);
-            Tw = (rank == 0 ? 3 : 4) * q_un;
-            w_lo = min(ra.n, u_off * q_un * rounds);
-            w_hi = min(ra.n, w_lo + Tw * rounds);
-          } else {
-            Tw = (T <= 3 * tpw && !tl.even_rounds) ? 3 * tpw : T;
-            w_lo = min(ra.n, worker * per_worker);
-            w_hi = min(ra.n, w_lo + per_worker);
-          }
-          const int p0 = w_lo + rd * Tw;
-          const int Gc = max(0, min(Tw, w_hi - p0));
+          const int2 grp = tc_group_of(tl.pairs, md.E, pair, ra.n, NS, tl.Tmax, tpw, (int)rank, s, rd, tl.even_rounds);
+          const int p0 = grp.x, Gc = grp.y;
           const int n_traj_w = max(0, min(tpw, Gc - qf * tpw));
           if (phase == 0) {  // lane tb arrives for trajectory tb (the stores were fenced above)
             if (lane < n_traj_w) costdev::fused_arrive_nowait(fc, p0 + qf * tpw + lane);
@@ -1338,28 +1322,27 @@ bool make_tc_layout(const ModelDesc& md, int num_sms, TcLayout* out, int* kmap_h
 
 // Row layout for launches over n trajectories.  Measured on B200: a stage of the global-row tiling costs about
 // 1.3x a node-major stage (two K-stacked layers per MMA stage, role-masked operand stores), and a busy issuing warp costs either
-// layout ~30 %; so the global-row tiling (2(N-1) + 3 instead of 2(N-1) + 6 stages per step) is taken where both layouts need the
-// same number of rounds, no member's issuing warp has to carry trajectories, and the stage count wins after the 1.3x.
+// layout ~30 % in the rounds where it carries trajectories; the global-row tiling (2(N-1) + 3 instead of 2(N-1) + 6 stages per
+// step) is taken where rounds x stages wins after both factors.
 int tc_pick_grow(const ModelDesc& md, int num_sms, int n) {
   if (md.N + 1 > 32) return 0;
   TcLayout t0{}, t1{};
   if (!make_tc_layout(md, num_sms, &t1, nullptr, 1)) return 0;
   if (!make_tc_layout(md, num_sms, &t0, nullptr, 0)) return 1;
   const int N = md.N;
-  auto worst = [&](const TcLayout& t, int* busy) {
-    int r = 1;
-    *busy = 0;
+  // slowest member: rounds weighted 1.3 where the issuing warp carries trajectories (all rounds of an even split with more than
+  // three warps' worth per round; the trailing rounds of the mixed split)
+  auto worst = [&](const TcLayout& t) {
+    double w = 0.0;
     for (int pair = 0; pair < t.pairs; ++pair) {
       const TcTile tt = tc_tile(t.pairs, md.E, pair, n, t.NS, t.Tmax, t.tpw);
-      r = std::max(r, tt.rounds);
-      if (tt.T > 3 * t.tpw && tt.uneven == 0) *busy = 1;
+      const int busy = tt.uneven == 2 ? tt.rounds - tt.k_pure : (tt.T > 3 * t.tpw && tt.uneven == 0) ? tt.rounds : 0;
+      w = std::max(w, (tt.rounds - busy) + 1.3 * busy);
     }
-    return r;
+    return w;
   };
-  int busy0 = 0, busy1 = 0;
-  const int r0 = worst(t0, &busy0), r1 = worst(t1, &busy1);
-  const double c0 = r0 * (2 * (N - 1) + 6) * (busy0 ? 1.3 : 1.0);
-  const double c1 = r1 * (2 * (N - 1) + 3) * 1.3 * (busy1 ? 1.3 : 1.0);
+  const double c0 = worst(t0) * (2 * (N - 1) + 6);
+  const double c1 = worst(t1) * (2 * (N - 1) + 3) * 1.3;
   return c1 < 0.95 * c0 ? 1 : 0;
 }
 

@@ -1,6 +1,6 @@
 """GPU: the tensor-core rollout kernels on the code paths the BENCHMARK runs -- every BASELINE.json size and every tiling
 branch of the kernels (trajectory groups taken one after the other by a warpgroup = ``rounds`` >= 2, the uneven 3/4 split
-that keeps the MMA-issuing warp empty, both tile row layouts of the GNN kernel: "node" = N rows per trajectory with separate
+that keeps the MMA-issuing warp empty in every round = ``uneven`` 1 or in the leading rounds only = ``uneven`` 2, both tile row layouts of the GNN kernel: "node" = N rows per trajectory with separate
 node / global stages, "global" = N + 1 rows with the node and global MLP K-stacked into one stage each) -- against the CPU
 oracle at the tf32/bf16-mode bar (1e-3 relative).
 
@@ -85,17 +85,18 @@ def _check_rollout(c, want_rounds=None, want_uneven=None, num_envs=1, want_rows=
 
 # ---- BASELINE.json sizes, full horizon --------------------------------------------------------------------------
 def test_tc_rollout_config2_full_size():
-    """configs[1]: construction N=2, 4096 trajectories, H=30 -> two rounds per slot."""
+    """configs[1]: construction N=2, 4096 trajectories, H=30 on the layout the library picks for it -- global rows (N + 1 = 3 rows
+    per trajectory, 5 stages per model step), two rounds per slot, the 14-pair member with one pure-issuer and one even round."""
     c = dict(kind="rollout", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=4096, H=30, wseed=5,
              identity_norm=True, running=False, oseed=1, tc_rows="auto")
-    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[0] * 5, want_rows="node")
+    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[1, 1, 1, 1, 2], want_rows="global")
 
 
-def test_tc_rollout_config2_full_size_global_rows():
-    """configs[1] forced onto the global-row layout: N + 1 = 3 rows per trajectory, 5 stages per model step."""
+def test_tc_rollout_config2_full_size_node_rows():
+    """configs[1] forced onto the node-major layout: two rounds per slot at 55 % tile fill."""
     c = dict(kind="rollout", env="construction", n_obj=2, model="gnn", hidden=128, layers=2, P=4096, H=30, wseed=5,
-             identity_norm=True, running=False, oseed=1, tc_rows="global")
-    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[1, 1, 1, 1, 0])
+             identity_norm=True, running=False, oseed=1, tc_rows="node")
+    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[0] * 5)
 
 
 def test_tc_rollout_config1_size_picks_global_rows():
@@ -108,10 +109,10 @@ def test_tc_rollout_config1_size_picks_global_rows():
 
 def test_tc_rollout_config3_full_size():
     """configs[2] per GPU: construction N=6 (30 edges), 2048 trajectories, H=30 -> two rounds, uneven split for the members
-    that own 15 CTA pairs."""
+    that own 15 CTA pairs, one pure-issuer round + one even round for the member that owns 14."""
     c = dict(kind="rollout", env="construction", n_obj=6, model="gnn", hidden=128, layers=2, P=2048, H=30, wseed=5,
              identity_norm=True, running=False, oseed=1, tc_rows="auto")
-    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[1, 1, 1, 1, 0], want_rows="node")
+    _check_rollout(c, want_rounds=[2] * 5, want_uneven=[1, 1, 1, 1, 2], want_rows="node")
 
 
 def test_tc_rollout_config4_full_size():
@@ -126,7 +127,7 @@ def test_tc_rollout_config4_full_size_global_rows():
     """configs[3] per GPU on the global-row layout (Hd = 64, four slots, 5 rows per trajectory): four rounds for the 14-pair member."""
     c = dict(kind="rollout", env="playground", n_obj=4, model="gnn", hidden=64, layers=2, P=8192, H=30, wseed=5,
              identity_norm=False, running=True, oseed=1, tc_rows="global")
-    _check_rollout(c, want_rounds=[3, 3, 3, 3, 4], want_uneven=[0, 0, 0, 0, 1], num_envs=8)
+    _check_rollout(c, want_rounds=[3, 3, 3, 3, 4], want_uneven=[2, 2, 2, 2, 1], num_envs=8)
 
 
 def test_tc_mlp_rollout_config5_full_size():
@@ -142,15 +143,20 @@ def test_tc_mlp_rollout_config5_full_size():
     ("construction", 2, 128, 3138, 2, [1] * 5, [1, 1, 1, 1, 0]),
     ("construction", 2, 128, 3586, 2, [1, 1, 1, 1, 2], [0] * 5),
     ("construction", 2, 128, 5763, 2, [2] * 5, [1] * 5),
+    ("construction", 2, 128, 6800, 2, [2] * 5, [2, 2, 2, 2, 0]),
     ("construction", 2, 128, 7681, 2, [3] * 5, [0] * 5),
+    ("construction", 2, 128, 10100, 2, [3] * 5, [2] * 5),
     ("construction", 6, 128, 905, 3, [1] * 5, [1] * 5),
     ("construction", 6, 128, 1206, 3, [2] * 5, [0] * 5),
     ("construction", 6, 128, 1801, 2, [2] * 5, [1] * 5),
+    ("construction", 6, 128, 2150, 2, [2] * 5, [2, 2, 2, 2, 0]),
     ("construction", 6, 128, 2403, 2, [3] * 5, [0] * 5),
     ("construction", 6, 128, 2704, 2, [3] * 5, [1] * 5),
+    ("construction", 6, 128, 3160, 2, [3] * 5, [2] * 5),
     ("construction", 3, 128, 3607, 2, [2] * 5, [1] * 5),
     ("playground", 4, 64, 2886, 3, [1] * 5, [1] * 5),
     ("playground", 4, 64, 5763, 2, [2] * 5, [1] * 5),
+    ("playground", 4, 64, 6800, 2, [2] * 5, [2, 2, 2, 2, 0]),
     ("playground", 4, 64, 7681, 2, [3] * 5, [0] * 5),
     ("playground", 4, 64, 8647, 2, [3] * 5, [1] * 5)])
 def test_tc_rollout_every_tiling_branch(env_kind, n_obj, hidden, P, H, rounds, uneven):
@@ -165,15 +171,20 @@ def test_tc_rollout_every_tiling_branch(env_kind, n_obj, hidden, P, H, rounds, u
     ("construction", 2, 128, 2300, 2, [1, 1, 1, 1, 2], [0] * 5),
     ("construction", 2, 128, 3000, 2, [2] * 5, [0] * 5),
     ("construction", 2, 128, 3700, 2, [2] * 5, [1] * 5),
+    ("construction", 2, 128, 4300, 2, [2] * 5, [2, 2, 2, 2, 0]),
     ("construction", 2, 128, 4900, 2, [3] * 5, [0] * 5),
+    ("construction", 2, 128, 6350, 2, [3] * 5, [2] * 5),
     ("construction", 3, 128, 1500, 3, [1] * 5, [1] * 5),
     ("construction", 3, 128, 2000, 2, [2] * 5, [0] * 5),
+    ("construction", 3, 128, 3400, 2, [2] * 5, [2, 2, 2, 2, 0]),
     ("construction", 6, 128, 750, 3, [1] * 5, [1] * 5),
     ("construction", 6, 128, 1000, 2, [2] * 5, [0] * 5),
     ("construction", 6, 128, 1500, 2, [2] * 5, [1] * 5),
+    ("construction", 6, 128, 1700, 2, [2] * 5, [2, 2, 2, 2, 0]),
     ("playground", 4, 64, 2200, 3, [1] * 5, [1] * 5),
     ("playground", 4, 64, 3000, 2, [2] * 5, [0] * 5),
     ("playground", 4, 64, 4400, 2, [2] * 5, [1] * 5),
+    ("playground", 4, 64, 5100, 2, [2] * 5, [2, 2, 2, 2, 0]),
     ("playground", 4, 64, 5800, 2, [3] * 5, [0] * 5)])
 def test_tc_rollout_every_tiling_branch_global_rows(env_kind, n_obj, hidden, P, H, rounds, uneven):
     """The same tiling branches on the global-row layout (N + 1 tile rows per trajectory, K-stacked node / global stages)."""
@@ -200,7 +211,7 @@ def test_tc_full_step_config2_agrees_with_fp32_and_oracle():
     a_tc = ctrl.get_action(obs, None)
     e = ctrl.engine
     assert e.tc_status() == 0
-    assert e.tc_row_layout() == "node"  # the layout the benchmark's config-2 step runs (picked by the library)
+    assert e.tc_row_layout() == "global"  # the layout the benchmark's config-2 step runs (picked by the library)
     ctrl32 = product_controller(c, env, product_model(c, env, weights, norms), seed=11)
     ctrl32.beginning_of_rollout(observation=obs, state=None, mode="train")
     ctrl32.get_action(obs, None)

@@ -93,7 +93,10 @@ def test_train_matches_reference_train(kind, variant, running, bootstrapped, mon
     moved = 0.0
     for k, v in ref.model.state_dict().items():
         got = drop.state_dict()[k].cpu()
-        np.testing.assert_allclose(got.numpy(), v.numpy(), rtol=2e-3, atol=2e-5, err_msg=k)
+        # (CPU fp32 vs cuBLAS fp32 gradients differ in the last bits and Adam's g / (sqrt(v) + 1e-4) amplifies that on weights
+        # whose gradient is ~eps; the bound leaves 2.5x head-room over the worst excursion seen in a full-suite run -- a wrong
+        # batch order, loss scale or optimiser setting moves the weights by O(lr * steps) = 1e-2)
+        np.testing.assert_allclose(got.numpy(), v.numpy(), rtol=5e-3, atol=5e-5, err_msg=k)
         moved = max(moved, float((v - torch.as_tensor(v)).abs().max()))
     # and the trained weights reach the planner: a predict through the CUDA kernels equals the reference's predict
     E, B = 5, 6
@@ -106,4 +109,4 @@ def test_train_matches_reference_train(kind, variant, running, bootstrapped, mon
     act = rs.uniform(-1, 1, (E, B, U)).astype(np.float32)
     want, _, _ = ref.predict(observations=torch.from_numpy(obs), states=None, actions=torch.from_numpy(act))
     got, _, _ = drop.predict(observations=torch.from_numpy(obs), states=None, actions=torch.from_numpy(act))
-    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=5e-3, atol=5e-4)
