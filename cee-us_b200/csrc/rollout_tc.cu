@@ -515,7 +515,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
         for (int j = 0; j < 16; ++j)
           if (j < A) {
             const float v0 = __ldg(so + j);
-            agent[j] = v0;
+            if constexpr (GROW) dyn[j] = v0; else agent[j] = v0;  // (GROW: a row has ONE role, its state lives in dyn[])
             s_obs[bw * O + j] = v0;
             satm = sat_track1(satm, dst[j] = half_sat((v0 - nrm[md.nrm.in_agent + j]) * nrm[md.nrm.in_agent + A + j]));
           }
@@ -669,6 +669,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
       
       };
 
+      // Global-row tiling: every row has exactly one role, so the two output updates above run as ONE pass with the role's tables
+      // and destinations (node rows: dyn block of node ni; global rows: agent part of the header + next action) instead of two
+      // divergent passes through the NG3 epilogue.
+      auto row_update = [&](const uint32_t (&v)[16], int h) {
+        const int dim = is_g ? A : D;
+        __half* dsth = snrm + b * SNs + (is_g ? 0 : kAU + ni * kNA);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(dsth);
+        float* og = s_obs + bw * O + (is_g ? 0 : A + ni * D);
+        const float4* tb = reinterpret_cast<const float4*>(sOut + (is_g ? 64 : 0));
+        const bool tight = !is_g && S == 0;  // a node block without static features ends in zero padding: whole words may be written
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          if (4 * j4 < dim) {
+            const float4 c1 = tb[j4], c0 = tb[4 + j4], mi = tb[8 + j4], is = tb[12 + j4];
+            float o0, o1, o2, o3;
+            if constexpr (kStateInSmem) {
+              o0 = 4 * j4 < dim ? og[4 * j4] : 0.f; o1 = 4 * j4 + 1 < dim ? og[4 * j4 + 1] : 0.f;
+              o2 = 4 * j4 + 2 < dim ? og[4 * j4 + 2] : 0.f; o3 = 4 * j4 + 3 < dim ? og[4 * j4 + 3] : 0.f;
+            } else {
+              o0 = dyn[4 * j4]; o1 = dyn[4 * j4 + 1]; o2 = dyn[4 * j4 + 2]; o3 = dyn[4 * j4 + 3];
+            }
+            const float n0 = o0 + fmaf(c1.x, __uint_as_float(v[4 * j4]), c0.x);
+            const float n1 = o1 + fmaf(c1.y, __uint_as_float(v[4 * j4 + 1]), c0.y);
+            const float n2 = o2 + fmaf(c1.z, __uint_as_float(v[4 * j4 + 2]), c0.z);
+            const float n3 = o3 + fmaf(c1.w, __uint_as_float(v[4 * j4 + 3]), c0.w);
+            if constexpr (!kStateInSmem) { dyn[4 * j4] = n0; dyn[4 * j4 + 1] = n1; dyn[4 * j4 + 2] = n2; dyn[4 * j4 + 3] = n3; }
+            if (4 * j4 < dim) og[4 * j4] = n0;
+            if (4 * j4 + 1 < dim) og[4 * j4 + 1] = n1;
+            if (4 * j4 + 2 < dim) og[4 * j4 + 2] = n2;
+            if (4 * j4 + 3 < dim) og[4 * j4 + 3] = n3;
+            const uint32_t w01 = pack_half2((n0 - mi.x) * is.x, (n1 - mi.y) * is.y), w23 = pack_half2((n2 - mi.z) * is.z, (n3 - mi.w) * is.w);
+            satm = sat_track(sat_track(satm, w01), w23);
+            if (4 * j4 + 1 < dim || tight) dst[2 * j4] = w01;
+            else reinterpret_cast<unsigned short*>(dsth)[4 * j4] = (unsigned short)(w01 & 0xffffu);
+            if (4 * j4 + 3 < dim || (tight && 4 * j4 + 2 < dim)) dst[2 * j4 + 1] = w23;
+            else if (4 * j4 + 2 < dim) reinterpret_cast<unsigned short*>(dsth)[4 * j4 + 2] = (unsigned short)(w23 & 0xffffu);
+          }
+        }
+        if (is_g && h + 1 < ra.H) {
+          if constexpr (kStateInSmem) asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j < U) {
+              const float an = kStateInSmem ? s_actn[j] : act_next[j];
+              satm = sat_track1(satm, dsth[A + j] = half_sat((an - nrm[md.nrm.in_action + j]) * nrm[md.nrm.in_action + U + j]));
+            }
+        }
+      };
+
       for (int h = 0; h < ra.H; ++h) {
         stamp(100);
         if (live_g && h + 1 < ra.H) {  // prefetch the next step's action; consumed in the G3 epilogue
@@ -790,8 +839,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
                 uint32_t v[16];
                 tmem_ld16(t_acc, v);
                 tmem_wait_ld();
-                if (live_n) node_update(v);
-                if (live_g) agent_update(v, h);
+                if (live) row_update(v, h);
               }
             }
             continue;
