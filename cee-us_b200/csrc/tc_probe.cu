@@ -308,3 +308,38 @@ extern "C" int ceeus_selftest_umma(int cta_group, const void* a_dev, const void*
   *status_host = e == cudaSuccess ? st : -(int)e;
   return e == cudaSuccess ? CEEUS_OK : CEEUS_ERR_CUDA;
 }
+
+// Host-only check of the tensor-core rollout tiling (kernels.cuh: tc_tile / tc_group): how often every trajectory of a launch over
+// n trajectories is covered by the groups of all (pair, cluster rank, slot, round), per ensemble member.  cover_out[e * n + p] must
+// come out as exactly 1.  Returns the largest group size seen (must be <= 4 * tpw), or a negative error.  No CUDA call.
+#include "kernels.cuh"
+extern "C" int ceeus_probe_tc_partition(int num_sms, int E, int n, int n_obj, int hidden, int grow, int32_t* cover_out /* [E*n] */,
+                                        int32_t* issuer_rows_out /* [2]: trajectories on issuing warps in pure / in all rounds */) {
+  using namespace ceeus;
+  if (!cover_out || n < 1 || E < 1 || (hidden != 64 && hidden != 128) || n_obj + (grow ? 1 : 0) > 32) return CEEUS_ERR_INVALID;
+  const int NS = 512 / (2 * hidden), tpw = 32 / (n_obj + (grow ? 1 : 0)), Tmax = 4 * tpw, pairs = num_sms / 2;
+  for (int i = 0; i < E * n; ++i) cover_out[i] = 0;
+  int gmax = 0, on_issuer_pure = 0, on_issuer_all = 0;
+  for (int pair = 0; pair < pairs; ++pair) {
+    const TcTile t = tc_tile(pairs, E, pair, n, NS, Tmax, tpw);
+    for (int rank = 0; rank < 2; ++rank)
+      for (int s = 0; s < NS; ++s)
+        for (int rd = 0; rd < t.rounds; ++rd) {
+          int p0, Gc;
+          tc_group(t, n, NS, tpw, rank, s, rd, 0, &p0, &Gc);
+          if (Gc > gmax) gmax = Gc;
+          for (int p = p0; p < p0 + Gc; ++p) {
+            if (p < 0 || p >= n) return CEEUS_ERR_STATE;
+            ++cover_out[t.e * n + p];
+          }
+          // trajectories that land on the MMA-issuing warp (the last-filled warp of a leader-CTA slot)
+          const int over = Gc - 3 * tpw;
+          if (rank == 0 && over > 0) {
+            on_issuer_all += over;
+            if (t.uneven == 1 || (t.uneven == 2 && rd < t.k_pure)) on_issuer_pure += over;
+          }
+        }
+  }
+  if (issuer_rows_out) { issuer_rows_out[0] = on_issuer_pure; issuer_rows_out[1] = on_issuer_all; }
+  return gmax;
+}
