@@ -392,10 +392,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     const uint32_t t_acc = lane_base, t_r1 = lane_base + HD, t_r2 = lane_base + HD + HD / 2;
     uint32_t dph = 0;
     int dbg_n = 0;
-    const bool dbg_on = DBG && dbg != nullptr && (long long)blockIdx.x == (dbg[499] >> 8) && tid == 0;  // probed CTA: flag >> 8
+    // profiling flag (ceeus_tc_debug_flag): bit 0 = slot 1 idles, bits 1..9 = probed thread, bits 12..15 = first probed round,
+    // bits 16.. = probed CTA
+    const bool dbg_on = DBG && dbg != nullptr && (long long)blockIdx.x == (dbg[499] >> 16) && tid == (int)((dbg[499] >> 1) & 0x1ff);
+    int dbg_rd = 0;
     auto stamp = [&](int tag) {
       if constexpr (!DBG) return;  // the timeline probes exist only in the profiling instantiation
-      if (dbg_on && dbg_n < 250) { dbg[2 * dbg_n] = tag; dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
+      if (dbg_on && dbg_rd >= (int)((dbg[499] >> 12) & 0xf) && dbg_n < 250) { dbg[2 * dbg_n] = tag; dbg[2 * dbg_n + 1] = clock64(); ++dbg_n; }
     };
 
     // ---- static row roles ----
@@ -463,6 +466,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 * TcSlots<HD>::v
     for (int j = 0; j < 16; ++j) { dyn[j] = 0.f; agent[j] = 0.f; }  // padded entries take part in the vectorised output update
 
     for (int rd = 0; rd < rounds; ++rd) {
+      if constexpr (DBG) dbg_rd = rd;
       // first trajectory / live trajectories of this group (Gc == 0: pure lock-step filler)
       const int2 grp = tc_group_of(tl.pairs, md.E, pair, ra.n, NS, tl.Tmax, tpw, (int)rank, s, rd, tl.even_rounds);
       const int p0 = grp.x;

@@ -17,7 +17,8 @@ acts = torch.from_numpy(rollout_actions(c, spec)).cuda()
 start = torch.from_numpy(obs).view(1, -1).cuda()
 eng.rollout(start, acts); torch.cuda.synchronize()
 eng.lib.ceeus_tc_debug_timeline(eng.handle, 1, None, 0)
-flag = (1 if len(sys.argv) > 3 and sys.argv[3] == 'single' else 0) | (int(os.environ.get('TL_BLOCK', '0')) << 8)
+flag = ((1 if len(sys.argv) > 3 and sys.argv[3] == 'single' else 0) | (int(os.environ.get('TL_TID', '0')) << 1) |
+        (int(os.environ.get('TL_RD', '0')) << 12) | (int(os.environ.get('TL_BLOCK', '0')) << 16))
 eng.lib.ceeus_tc_debug_flag(eng.handle, flag)
 eng.rollout(start, acts); torch.cuda.synchronize()
 buf = (C.c_longlong * 500)()
