@@ -46,6 +46,7 @@ namespace ceeus {
 
 namespace {
 using namespace tc;
+static_assert(kTcRangeFlag == CEEUS_TC_RANGE, "the kernels' range bit is the one include/ceeus_b200.h documents");
 
 // Warpgroups ("slots") per CTA: each owns 2 * HD TMEM columns, so the 512 columns hold two slots at Hd = 128 (256 threads, up to
 // 255 registers each: the epilogue keeps a whole 128-column row in registers) and four at Hd = 64 (512 threads, 128 registers).
